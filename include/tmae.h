@@ -1,0 +1,165 @@
+/* tmae.h - C ABI of the B200-native TextMAE compression forward path (libtmae_b200.so).
+ *
+ * Drop-in boundary for ONE path of tmkhang1999/TextMAE-Image-Compression: everything
+ * `MCM.forward(imgs, total_scores)` computes up to the rate
+ * (reference models/Compression/MCM.py:590-634 forward_encoder, :714-787 rate half of forward,
+ *  models/Compression/loss/rd_loss.py:15-20 bpp).  The reference has no FFI of its own (it is pure
+ * Python); these entry points are what a ctypes / pybind binding of that path binds
+ * (INTEGRATION.md shows the reference-side stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every pointer is a DEVICE pointer unless the name starts with h_ (tmae_forward_host).
+ *   - activations are channels-last: a reference tensor [N, C, h, w] is passed as [N, h, w, C]
+ *     (the Python host returns .permute(0,3,1,2) views so callers see the reference shape).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and no allocation once the workspace for that batch size exists.
+ *   - return value: 0 on success, otherwise a tmae_status; tmae_last_error() gives the text.
+ *     Nothing throws or aborts across the ABI.  There is no CPU fallback.
+ */
+#ifndef TMAE_H_
+#define TMAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TMAE_ABI_VERSION 1
+#if defined(__GNUC__)
+#define TMAE_API __attribute__((visibility("default")))
+#else
+#define TMAE_API
+#endif
+
+typedef enum {
+    TMAE_OK = 0,
+    TMAE_EINVAL = 1,      /* bad argument / geometry the reference rejects (K > L, K not (4j)^2, size mismatch) */
+    TMAE_ECUDA = 2,       /* CUDA runtime / driver error; text in tmae_last_error */
+    TMAE_ESTATE = 3,      /* call order (weights missing / not finalized) */
+    TMAE_ENOMEM = 4
+} tmae_status;
+
+typedef enum { TMAE_F32 = 0, TMAE_BF16 = 1, TMAE_F16 = 2 } tmae_dtype;
+
+/* Constructor arguments of the reference module, MCM.__init__ (MCM.py:34-52), hot-path subset. */
+typedef struct {
+    int32_t img_size;            /* 224 */
+    int32_t patch_size;          /* 16  */
+    int32_t in_chans;            /* 3   */
+    int32_t encoder_embed_dim;   /* 768 */
+    int32_t encoder_depth;       /* 12  */
+    int32_t encoder_num_heads;   /* 12  */
+    int32_t decoder_embed_dim;   /* 512 : fixes the g_a channel ladder (MCM.py:77-93) */
+    float   mlp_ratio;           /* 4.0 */
+    int32_t latent_depth;        /* 384 */
+    int32_t hyperprior_depth;    /* 192 */
+    int32_t num_slices;          /* 12  */
+    int32_t num_keep_patches;    /* 144 */
+    float   ln_eps;              /* 1e-6 */
+    int32_t softmax_isa;         /* 16 / 8: ATen CPU softmax lane order mirrored by the mask kernel (0 = 16) */
+    int32_t flags;               /* TMAE_FLAG_* */
+} tmae_config;
+
+#define TMAE_FLAG_SKIP_DEAD_LRP 1u   /* rate-only: skip lrp_transform[6..11] (their y_hat feeds only g_s) */
+#define TMAE_FLAG_DEBUG_SIMT    2u   /* bring-up only: run GEMM/conv layers on the CUDA-core checker kernel */
+
+/* Outputs of one forward; any pointer may be NULL (that output is skipped).
+ * N = batch, L = (img/patch)^2, K = num_keep_patches, s = sqrt(K), Cy = latent_depth, Cz = hyperprior_depth. */
+typedef struct {
+    float*   y_likelihoods;   /* [N, s, s, Cy]      == out["likelihoods"]["y"] (MCM.py:787,801), NHWC */
+    float*   z_likelihoods;   /* [N, s/4, s/4, Cz]  == out["likelihoods"]["z"] (MCM.py:741,801), NHWC */
+    int32_t* y_symbols;       /* [N, s, s, Cy]      round(y - mu)       (MCM.py:776)  */
+    int32_t* z_symbols;       /* [N, s/4, s/4, Cz]  round(z - median)   (MCM.py:742-744) */
+    float*   y_hat;           /* [N, s, s, Cy]      after LRP           (MCM.py:783-786) */
+    float*   z_hat;           /* [N, s/4, s/4, Cz] */
+    float*   y;               /* [N, s, s, Cy]      g_a output          (MCM.py:735) */
+    float*   z;               /* [N, s/4, s/4, Cz]  h_a output          (MCM.py:739) */
+    float*   mu;              /* [N, s, s, Cy]      per-slice means     (MCM.py:762-763) */
+    float*   sigma;           /* [N, s, s, Cy]      per-slice raw scales(MCM.py:767-768) */
+    float*   x_remain;        /* [N, K, C]          encoder output      (MCM.py:631-632) */
+    float*   bpp;             /* [N]                per-image rate, rd_loss.py:15-20 with N = 1 */
+    double*  rate_sums;       /* [2]                {sum log2 likelihood over the batch, N * S * S pixels} */
+    int64_t* ids_shuffle;     /* [N, L]             MCM.get_ids_shuffle return value (MCM.py:423) */
+    int64_t* ids_restore;     /* [N, L]             argsort(ids_shuffle) (MCM.py:580) */
+    int64_t* ids_keep;        /* [N, K]             ids_shuffle[:, :K]   (MCM.py:583) */
+} tmae_outputs;
+
+typedef struct tmae_handle tmae_handle;
+
+/* Lifetime -------------------------------------------------------------------------------------- */
+TMAE_API int  tmae_abi_version(void);
+/* Validates geometry exactly like the reference would fail (see tmae_status) and creates a handle on the
+ * current CUDA device. */
+TMAE_API int  tmae_create(const tmae_config* cfg, tmae_handle** out);
+TMAE_API void tmae_destroy(tmae_handle* h);
+TMAE_API const char* tmae_last_error(const tmae_handle* h);   /* h may be NULL: error of the last failed tmae_create */
+
+/* Weights: one call per state-dict entry, names exactly as in MCM.state_dict(), e.g.
+ * "encoder_blocks.3.attn.qkv.weight".  `data` may be a device or host pointer (cudaMemcpyDefault); the library
+ * copies it, so the caller may free it on return.  Unknown names (decoder, g_s, buffers) are ignored and
+ * reported through *ignored when non-NULL. */
+TMAE_API int  tmae_set_weight(tmae_handle* h, const char* name, const void* data, int dtype, int ndim,
+                     const int64_t* shape, int* ignored);
+/* Checks that every tensor the path needs is present, prepacks to bf16 tensor-core layouts, precomputes
+ * softplus/tanh of the factorized-prior parameters.  Synchronises the device. */
+TMAE_API int  tmae_finalize_weights(tmae_handle* h);
+
+/* Workspace: grown on demand inside tmae_forward; this makes the growth explicit (e.g. before CUDA-graph capture). */
+TMAE_API size_t tmae_workspace_bytes(const tmae_handle* h, int N);
+TMAE_API int  tmae_reserve(tmae_handle* h, int N);
+
+/* The hot path --------------------------------------------------------------------------------- */
+/* imgs: f32 [N, in_chans, S, S] NCHW contiguous; scores: f32 [N, L].  (MCM.forward arguments, MCM.py:714) */
+TMAE_API int  tmae_forward(tmae_handle* h, const float* imgs, const float* scores, int N,
+                  const tmae_outputs* out, void* stream);
+/* Same call with HOST buffers: h_imgs / h_scores (pinned for full speed) are copied in on `stream`, the
+ * forward runs, and h_bpp [N] (+ optional h_rate_sums [2]) is copied back; `out` (device pointers) may be NULL. */
+TMAE_API int  tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores, int N,
+                       float* h_bpp, double* h_rate_sums, const tmae_outputs* out, void* stream);
+/* Teacher-forced entry for parity tests: run the rate half only (MCM.py:739-787) from a given latent
+ * y f32 [N, s, s, Cy]. */
+TMAE_API int  tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_outputs* out, void* stream);
+/* Encoder only (MCM.forward_encoder, MCM.py:590-634): fills out->x_remain / ids_*. */
+TMAE_API int  tmae_forward_encoder(tmae_handle* h, const float* imgs, const float* scores, int N,
+                          const tmae_outputs* out, void* stream);
+
+/* Stand-alone operators on the path (each mirrors one reference call) ---------------------------------- */
+/* MCM.get_ids_shuffle + random_masking index work (MCM.py:364-423, 579-583). Outputs may be NULL. */
+TMAE_API int  tmae_mask_select(const float* scores, int N, int L, int K, int softmax_isa,
+                      int64_t* ids_shuffle, int64_t* ids_restore, int64_t* ids_keep, void* stream);
+/* GaussianConditional eval forward + quantize_ste (MCM.py:771-776) on n elements. */
+TMAE_API int  tmae_gaussian_rate(const float* y, const float* mu, const float* sigma, int64_t n,
+                        float* likelihood, int32_t* symbols, float* y_hat, void* stream);
+/* EntropyBottleneck eval forward + quantize_ste (MCM.py:741-744): z f32 [rows, Cz] channels-last. */
+TMAE_API int  tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows,
+                          float* likelihood, int32_t* symbols, float* z_hat, void* stream);
+
+/* Tensor-core GEMM/conv engine self-test hook (tests): C[M,N] = A[M,K] * B[N,K]^T (+bias) with bf16 inputs,
+ * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */
+TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K,
+                    int block_n, int impl, void* stream);
+/* 3x3 pad-1 stride-1 convolution on the engine: x bf16 [N, s, s, Cin] NHWC, w f32 [Cout, Cin, 3, 3] -> f32 NHWC. */
+TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
+                       int Cin, int Cout, int gelu, int impl, void* stream);
+
+/* Per-kernel-family device timing (bench.py roofline): when enabled every launch of tmae_forward is bracketed
+ * by CUDA events on `stream`; read after synchronising. */
+typedef struct {
+    char   name[32];
+    int32_t launches;
+    float  ms;           /* summed device time */
+    double flops;        /* algorithmic flops of those launches (0 for non-GEMM families) */
+    double bytes;        /* algorithmic bytes moved (0 if not tracked) */
+} tmae_profile_entry;
+TMAE_API int  tmae_profile_enable(tmae_handle* h, int enable);
+TMAE_API int  tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entries, int* n_entries);
+/* Number of kernels tmae_forward launches for batch N (after planning). */
+TMAE_API int  tmae_launch_count(tmae_handle* h, int N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMAE_H_ */

@@ -1,0 +1,40 @@
+"""GPU: the tcgen05 GEMM / conv engine against torch fp32 on the same bf16-rounded operands, and against the
+CUDA-core checker kernel that shares its parameter block and epilogue."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 256, 128), (300, 224, 384, 0), (1000, 2304, 768, 256),
+                                       (4160, 768, 3072, 0), (257, 80, 176, 0), (130, 32, 80, 32), (512, 704, 768, 192)])
+@pytest.mark.parametrize("impl", [1, 0])
+def test_gemm_matches_torch(cuda_dev, M, N, K, bn, impl):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    ref = A.float() @ B.float().t() + bias
+    out = G.gemm(A, B, bias, block_n=bn, impl=impl)
+    err = G.rel_err(out, ref)
+    assert err < 2e-5, f"impl={impl} rel err {err}"          # fp32 accumulate of identical bf16 operands
+
+
+@pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (2, 4, 192, 240, True),
+                                                  (5, 8, 80, 32, False), (1, 16, 576, 224, True)])
+@pytest.mark.parametrize("impl", [1, 0])
+def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin)
+    x = torch.randn(N, s, s, Cin, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))).to(cuda_dev)
+    b = torch.randn(Cout, generator=g).to(cuda_dev)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=1)
+    if gelu:
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    out = G.conv3x3(x, w, b, gelu=gelu, impl=impl)
+    err = G.rel_err(out, ref)
+    assert err < 3e-5, f"impl={impl} rel err {err}"

@@ -1,0 +1,199 @@
+"""GPU: the full compression forward path through the reference-facing module (MCM.forward -> C ABI) against the
+fp32 oracle on identical inputs, with the north-star tolerances:
+   mask indices / token order      bit-exact
+   encoder output                  <= 2e-2 relative (bf16 tensor-core operands vs fp32)
+   quantised symbols               bit-exact up to a REPORTED count of boundary flips (bf16 error on y - mu)
+   per-image bpp                   <= 0.5 %
+A JSON report of every measured deviation is written to gpurun_out/parity_report.json."""
+import json
+import os
+from pathlib import Path
+
+import pytest
+import torch
+
+from oracle import ref_model
+from tests import gpu_util as G
+from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict, vit_base
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(img_size=64, encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2, num_keep_patches=16)
+REPORT = {}
+
+
+def _report(key, val):
+    REPORT[key] = val
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", Path(__file__).resolve().parent.parent)) / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_report.json").write_text(json.dumps(REPORT, indent=1, sort_keys=True))
+
+
+def _build(kwargs, sd, dev, **flags):
+    m = MCM(**kwargs, extra_outputs=True, softmax_isa=16, **flags)
+    m.load_state_dict(sd)
+    m.cuda()
+    return m.eval()
+
+
+def _compare(tag, out, ref, cfg, bpp_tol, enc_tol=2e-2):
+    stats = {}
+    # --- bit-exact index work
+    assert torch.equal(out["ids_keep"].cpu(), ref["ids_keep"]), "ids_keep"
+    assert torch.equal(out["ids_restore"].cpu(), ref["ids_restore"]), "ids_restore"
+    # --- encoder
+    stats["x_remain_rel"] = G.rel_err(out["x_remain"].cpu(), ref["x_remain"])
+    stats["y_rel"] = G.rel_err(out["y"].cpu(), ref["y"])
+    stats["z_rel"] = G.rel_err(out["z"].cpu(), ref["z"])
+    stats["mu_rel"] = G.rel_err(out["mu"].cpu(), ref["mu"])
+    stats["sigma_rel"] = G.rel_err(out["sigma"].cpu(), ref["sigma"])
+    # --- symbols
+    ysym, zsym = out["latents"]["y_sym"].cpu(), out["latents"]["z_sym"].cpu()
+    yflip = ysym != ref["y_sym"]
+    stats["y_sym_flips"] = int(yflip.sum()); stats["y_sym_total"] = ysym.numel()
+    stats["z_sym_flips"] = int((zsym != ref["z_sym"]).sum()); stats["z_sym_total"] = zsym.numel()
+    frac = (ref["y"] - ref["mu"]) - torch.floor(ref["y"] - ref["mu"])
+    dist = (frac - 0.5).abs()                                    # oracle's distance to the rounding boundary
+    stats["y_flips_exact_tie(<1e-4)"] = int((yflip & (dist < 1e-4)).sum())
+    delta = ((out["y"].cpu() - out["mu"].cpu()) - (ref["y"] - ref["mu"])).abs()
+    stats["y_flips_explained_by_input_error"] = int((yflip & (dist <= delta + 1e-6)).sum())
+    stats["y_flips_other"] = stats["y_sym_flips"] - stats["y_flips_explained_by_input_error"]
+    stats["y_sym_max_abs_diff"] = int((ysym - ref["y_sym"]).abs().max())
+    # --- likelihoods where the symbols agree
+    lik, rlik = out["likelihoods"]["y"].cpu(), ref["y_lik"]
+    agree = ~yflip
+    rel = ((lik - rlik).abs() / rlik)[agree]
+    stats["y_lik_rel_median"] = rel.median().item(); stats["y_lik_rel_p99"] = rel.quantile(0.99).item() if rel.numel() < 10_000_000 else -1
+    zl, rzl = out["likelihoods"]["z"].cpu(), ref["z_lik"]
+    zagree = zsym == ref["z_sym"]
+    stats["z_lik_rel_max"] = ((zl - rzl).abs() / rzl)[zagree].max().item()
+    # --- rate
+    bpp, rbpp = out["bpp"].cpu(), ref["bpp"]
+    stats["bpp_rel_max"] = ((bpp - rbpp).abs() / rbpp).max().item()
+    stats["bpp"] = bpp.tolist(); stats["bpp_oracle"] = rbpp.tolist()
+    stats["y_hat_rel"] = G.rel_err(out["latents"]["y_hat"].cpu(), ref["y_hat"])
+    _report(tag, stats)
+    print(tag, json.dumps(stats))
+    assert stats["x_remain_rel"] < enc_tol, stats
+    assert stats["y_flips_other"] == 0, stats
+    assert stats["y_sym_flips"] / stats["y_sym_total"] < 0.03, stats
+    assert stats["bpp_rel_max"] < bpp_tol, stats
+    return stats
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["simt_checker", "tcgen05"])
+def test_small_model_full_path(cuda_dev, simt):
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(3, 3, 64, 64, generator=g)
+    scores = torch.rand(3, cfg.num_patches, generator=g)
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(SMALL, sd, cuda_dev, debug_simt=simt)
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    _compare(f"small_{'simt' if simt else 'tc'}", out, ref, cfg, bpp_tol=0.02)
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["simt_checker", "tcgen05"])
+def test_small_model_teacher_forced_rate_half(cuda_dev, simt):
+    """Oracle latent y in -> every conv / entropy kernel of the rate half, no encoder error."""
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(1)
+    imgs = torch.rand(4, 3, 64, 64, generator=g)
+    scores = torch.rand(4, cfg.num_patches, generator=g)
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(SMALL, sd, cuda_dev, debug_simt=simt)
+    out = m.forward_from_latent(ref["y"].cuda())
+    torch.cuda.synchronize()
+    st = {}
+    st["z_rel"] = G.rel_err(out["z"].cpu(), ref["z"])
+    st["mu_rel"] = G.rel_err(out["mu"].cpu(), ref["mu"])
+    st["sigma_rel"] = G.rel_err(out["sigma"].cpu(), ref["sigma"])
+    st["z_sym_flips"] = int((out["latents"]["z_sym"].cpu() != ref["z_sym"]).sum())
+    yflip = out["latents"]["y_sym"].cpu() != ref["y_sym"]
+    st["y_sym_flips"] = int(yflip.sum()); st["y_sym_total"] = yflip.numel()
+    st["bpp_rel_max"] = ((out["bpp"].cpu() - ref["bpp"]).abs() / ref["bpp"]).max().item()
+    _report(f"small_teacher_forced_{'simt' if simt else 'tc'}", st)
+    print(st)
+    assert st["z_rel"] < 1e-2 and st["mu_rel"] < 2e-2 and st["sigma_rel"] < 2e-2, st
+    assert st["y_sym_flips"] / st["y_sym_total"] < 0.02, st
+    assert st["bpp_rel_max"] < 0.01, st
+
+
+@pytest.mark.parametrize("K,n_img", [(64, 2), (144, 1)])
+def test_vit_base_kodak_against_oracle_and_goldens(cuda_dev, kodak, golden_dir, K, n_img):
+    imgs, scores = kodak
+    cfg = vit_base(K)
+    sd = make_state_dict(cfg, seed=0)
+    blob = torch.load(golden_dir / f"model_B{K}.pt")
+    m = _build(dict(num_keep_patches=K), sd, cuda_dev)
+    out = m(imgs[:n_img].cuda(), scores[:n_img].cuda())
+    torch.cuda.synchronize()
+    ref = {k: (v.float() if torch.is_tensor(v) and v.dtype == torch.float16 else v) for k, v in blob.items()}
+    _compare(f"vitB_K{K}_kodak_vs_golden", out, ref, cfg, bpp_tol=0.005)
+    del m
+    torch.cuda.empty_cache()
+
+
+def test_vit_base_batch64_properties(cuda_dev):
+    """BASELINE.json config 2 at full size: size-independent properties + batch independence."""
+    K, N = 64, 64
+    cfg = vit_base(K)
+    sd = make_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(N, 3, 224, 224, generator=g)
+    scores = torch.rand(N, cfg.num_patches, generator=torch.Generator().manual_seed(1))
+    scores[N // 2:] = torch.round(scores[N // 2:] * 30) / 30                  # heavy ties in half of the batch
+    m = _build(dict(num_keep_patches=K), sd, cuda_dev)
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    L = cfg.num_patches
+    ar = torch.arange(L, device=cuda_dev).expand(N, L)
+    assert torch.equal(torch.sort(out["ids_shuffle"], dim=1)[0], ar)
+    assert torch.equal(torch.gather(out["ids_restore"], 1, out["ids_shuffle"]), ar)      # restore o shuffle = identity
+    assert torch.equal(out["ids_keep"], out["ids_shuffle"][:, :K])
+    yl, zl = out["likelihoods"]["y"], out["likelihoods"]["z"]
+    assert yl.shape == (N, 384, 8, 8) and zl.shape == (N, 192, 2, 2)
+    assert (yl >= 1e-9).all() and (yl <= 1.0 + 1e-6).all() and (zl >= 1e-9).all() and (zl <= 1.0 + 1e-6).all()
+    # bpp == rd_loss.py formula applied to the returned likelihoods
+    num_pixels = 224 * 224
+    want = -(torch.log2(yl.double()).reshape(N, -1).sum(1) + torch.log2(zl.double()).reshape(N, -1).sum(1)) / num_pixels
+    assert torch.allclose(out["bpp"].double(), want, rtol=1e-4), (out["bpp"][:4], want[:4])
+    assert abs(out["rate_sums"][1].item() - N * num_pixels) < 0.5
+    assert abs(-out["rate_sums"][0].item() / out["rate_sums"][1].item() - want.mean().item()) < 1e-4 * want.mean().item()
+    # y_hat = sym + mu + 0.5*tanh(.)  ->  |y_hat - (sym + mu)| <= 0.5
+    resid = (out["latents"]["y_hat"] - (out["latents"]["y_sym"].float() + out["mu"])).abs().max().item()
+    assert resid <= 0.5 + 1e-3, resid
+    # ids agree with the C oracle for the whole batch
+    from oracle import ref_mask
+    assert torch.equal(out["ids_shuffle"].cpu(), ref_mask.mask_oracle_c(scores, K, isa=16))
+    # batch independence: image 5 alone gives the same symbols / rate
+    one = m(imgs[5:6].cuda(), scores[5:6].cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(one["latents"]["y_sym"][0], out["latents"]["y_sym"][5])
+    assert torch.allclose(one["bpp"][0], out["bpp"][5], rtol=1e-5)
+    _report("vitB_K64_batch64", {"bpp_mean": out["bpp"].mean().item(), "lrp_resid_max": resid})
+
+
+def test_host_buffer_entry_matches_device_entry(cuda_dev):
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(5, 3, 64, 64, generator=g).pin_memory()
+    scores = torch.rand(5, cfg.num_patches, generator=g).pin_memory()
+    m = _build(SMALL, sd, cuda_dev)
+    out = m(imgs.cuda(), scores.cuda())
+    bpp = m.forward_host(imgs, scores)
+    torch.cuda.synchronize()
+    assert torch.equal(bpp, out["bpp"].cpu())
+
+
+def test_error_classes_on_device(cuda_dev):
+    cfg = PathConfig(**SMALL)
+    m = _build(SMALL, make_state_dict(cfg, seed=3), cuda_dev)
+    with pytest.raises(AssertionError):
+        m(torch.rand(1, 3, 32, 32).cuda(), torch.rand(1, 16).cuda())         # timm PatchEmbed size assert
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 3, 64, 64).cuda(), torch.rand(1, 8).cuda())          # K > len(scores) (MCM.py:374-376)

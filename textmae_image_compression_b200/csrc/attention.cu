@@ -1,0 +1,175 @@
+// Fused softmax attention over the visible tokens of one image and one head (timm 0.4.5 Attention.forward as
+// used by the encoder blocks, MCM.py:313-322, 629-630):  softmax((q k^T) * hd^-0.5) v, head_dim = 64, T <= ~300.
+// One CTA per (image, head); K and V^T of all T keys stay in shared memory, each warp owns 16-query tiles and runs
+// an online-softmax loop over 16-key chunks; S and P never leave registers.  bf16 tensor-core math
+// (mma.sync m16n8k16, fp32 accumulate): this op is 1.7-3 % of the path's FLOPs, so it uses the legacy
+// warp-level MMA; the GEMM / conv engine (gemm_tc.cu) is where tcgen05 is spent.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tmae {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int KPITCH = HD + 8;        // bf16 elements per K row in smem: 36 words -> conflict-free B-fragment loads
+constexpr int kAttnThreads = 128;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// qkv: bf16 [N*T, 3C] with columns [3][H][64] (timm reshape (B,T,3,H,hd)); out: bf16 [N*T, C] columns [H][64].
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
+                 float scale_log2e) {
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);            // [Tp][KPITCH]
+    __nv_bfloat16* sVt = sK + (size_t)Tp * KPITCH;                               // [HD][Tp + 8]
+    const int vpitch = Tp + 8;
+    const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const size_t ld = (size_t)3 * C;
+    const __nv_bfloat16* base = qkv + (size_t)n * T * ld + (size_t)h * HD;
+
+    // ---- stage K (row-major) and V (transposed) for all keys; zero the padding ----
+    for (int e = tid; e < Tp * (HD / 8); e += kAttnThreads) {
+        const int key = e / (HD / 8), c8 = (e - key * (HD / 8)) * 8;
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (key < T) {
+            kv = *reinterpret_cast<const uint4*>(base + (size_t)key * ld + C + c8);
+            vv = *reinterpret_cast<const uint4*>(base + (size_t)key * ld + 2 * C + c8);
+        }
+        *reinterpret_cast<uint4*>(sK + (size_t)key * KPITCH + c8) = kv;
+        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sVt[(size_t)(c8 + i) * vpitch + key] = ve[i];
+    }
+    __syncthreads();
+
+    const int q_tiles = Tp / 16;
+    for (int qt = warp; qt < q_tiles; qt += kAttnThreads / 32) {
+        const int q0 = qt * 16;
+        // Q fragments for the 4 k-steps over head_dim (A operand, row-major 16x16 each)
+        uint32_t qa[4][4];
+        {
+            const int r0 = q0 + g, r1 = q0 + g + 8;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const int c = ks * 16 + 2 * t;
+                qa[ks][0] = r0 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c) : 0u;
+                qa[ks][1] = r1 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c) : 0u;
+                qa[ks][2] = r0 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c + 8) : 0u;
+                qa[ks][3] = r1 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c + 8) : 0u;
+            }
+        }
+        float o[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;     // rows g and g+8
+
+        for (int k0 = 0; k0 < Tp; k0 += 16) {
+            // S chunk = Q (16x64) * K[k0..k0+16)^T : two n-tiles of 8 keys
+            float sacc[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+                const __nv_bfloat16* krow = sK + (size_t)(k0 + nt * 8 + g) * KPITCH + 2 * t;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+                    mma_bf16_16816(sacc[nt], qa[ks], b0, b1);
+                }
+            }
+            // scale (log2 domain), mask padded keys
+            float cmax0 = -INFINITY, cmax1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int key = k0 + nt * 8 + 2 * t;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool ok = (key + (i & 1)) < T;
+                    sacc[nt][i] = ok ? sacc[nt][i] * scale_log2e : -INFINITY;
+                }
+                cmax0 = fmaxf(cmax0, fmaxf(sacc[nt][0], sacc[nt][1]));
+                cmax1 = fmaxf(cmax1, fmaxf(sacc[nt][2], sacc[nt][3]));
+            }
+            cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 1));
+            cmax0 = fmaxf(cmax0, __shfl_xor_sync(0xffffffffu, cmax0, 2));
+            cmax1 = fmaxf(cmax1, __shfl_xor_sync(0xffffffffu, cmax1, 1));
+            cmax1 = fmaxf(cmax1, __shfl_xor_sync(0xffffffffu, cmax1, 2));
+            const float nm0 = fmaxf(m0, cmax0), nm1 = fmaxf(m1, cmax1);   // finite: key 0 of chunk 0 is always valid
+            const float corr0 = exp2f(m0 - nm0), corr1 = exp2f(m1 - nm1);
+            m0 = nm0; m1 = nm1;
+            float rs0 = 0.f, rs1 = 0.f;
+            uint32_t pa[4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const float p0 = exp2f(sacc[nt][0] - nm0), p1 = exp2f(sacc[nt][1] - nm0);
+                const float p2 = exp2f(sacc[nt][2] - nm1), p3 = exp2f(sacc[nt][3] - nm1);
+                rs0 += p0 + p1;
+                rs1 += p2 + p3;
+                pa[nt * 2 + 0] = pack_bf16x2(p0, p1);      // rows g   : a0 (keys 0-7) / a2 (keys 8-15)
+                pa[nt * 2 + 1] = pack_bf16x2(p2, p3);      // rows g+8 : a1 / a3
+            }
+            l0 = l0 * corr0 + rs0;
+            l1 = l1 * corr1 + rs1;
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+                o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1;
+            }
+            // O += P (16 x 16 keys) * V[k0..k0+16) (16 keys x 64)
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) {
+                const __nv_bfloat16* vrow = sVt + (size_t)(dt * 8 + g) * vpitch + k0 + 2 * t;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
+                mma_bf16_16816(o[dt], pa, b0, b1);
+            }
+        }
+        // row sums live per quad: reduce across the 4 lanes that share a row
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        __nv_bfloat16* obase = out + (size_t)n * T * C + (size_t)h * HD;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt) {
+            const int c = dt * 8 + 2 * t;
+            if (r0 < T) *reinterpret_cast<uint32_t*>(obase + (size_t)r0 * C + c) = pack_bf16x2(o[dt][0] * inv0, o[dt][1] * inv0);
+            if (r1 < T) *reinterpret_cast<uint32_t*>(obase + (size_t)r1 * C + c) = pack_bf16x2(o[dt][2] * inv1, o[dt][3] * inv1);
+        }
+    }
+}
+
+inline int attn_tp(int T) { return (T + 15) / 16 * 16; }
+inline size_t attn_smem(int T) {
+    const int Tp = attn_tp(T);
+    return ((size_t)Tp * KPITCH + (size_t)HD * (Tp + 8)) * sizeof(__nv_bfloat16);
+}
+
+}  // namespace
+
+cudaError_t attention_configure(int T) {
+    return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(T));
+}
+
+cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int T, int H, int C, float scale,
+                             cudaStream_t st) {
+    if (C != H * HD) return cudaErrorInvalidValue;
+    const int Tp = attn_tp(T);
+    attention_kernel<<<N * H, kAttnThreads, attn_smem(T), st>>>(qkv, out, T, Tp, H, C,
+                                                                scale * 1.4426950408889634f);
+    return cudaGetLastError();
+}
+
+}  // namespace tmae

@@ -1,0 +1,478 @@
+// HBM-bound kernels of the path: kept-patch gather (im2col), LayerNorm, the entropy-model elementwise work
+// (factorized-prior and Gaussian likelihoods, quantisation, log2-rate reduction) and weight prepacking.
+// All are coalesced, 128-bit vectorised where the layout allows, with warp-shuffle reductions.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tmae {
+
+// ---------------------------------------------------------------------------------------------------------
+// Kept-patch gather: timm PatchEmbed's im2col restricted to the K kept patches (MCM.py:615 + :583-586; the
+// conv is a per-patch linear map, so gathering first is row-wise identical).  Row (n, j) of `patches` holds
+// patch ids_keep[n, j] flattened in (c, p, q) order == Conv2d weight order.  Block (n, j == K) writes the cls row
+// x[n*T + 0] = cls_token + pos_embed[0] (MCM.py:624-626).
+// grid (K + 1, N), block 192: thread = (c, p, q4) handles 4 pixels (16 B read, 8 B write).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192)
+gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict__ ids_keep,
+                      __nv_bfloat16* __restrict__ patches, float* __restrict__ x, const float* __restrict__ cls_token,
+                      const float* __restrict__ pos_embed, int S, int grid_w, int K, int T, int C, int in_chans,
+                      int patch) {
+    const int j = blockIdx.x, n = blockIdx.y;
+    if (j == K) {
+        float* dst = x + (size_t)n * T * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = cls_token[c] + pos_embed[c];
+        return;
+    }
+    const int pid = (int)ids_keep[(size_t)n * K + j];
+    const int py = pid / grid_w, px = pid - py * grid_w;
+    const int per_c = patch * patch;               // 256
+    const int row_len = in_chans * per_c;          // 768
+    __nv_bfloat16* dst = patches + ((size_t)n * K + j) * row_len;
+    for (int e = threadIdx.x * 4; e < row_len; e += blockDim.x * 4) {
+        const int c = e / per_c;
+        const int rem = e - c * per_c;
+        const int p = rem / patch, q = rem - p * patch;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            imgs + (((size_t)n * in_chans + c) * S + (py * patch + p)) * S + px * patch + q));
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(dst + e) = pk;
+    }
+}
+
+cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __nv_bfloat16* patches, float* x,
+                                  const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
+                                  int T, int C, int in_chans, int patch, cudaStream_t st) {
+    dim3 grid(K + 1, N);
+    gather_patches_kernel<<<grid, 192, 0, st>>>(imgs, ids_keep, patches, x, cls_token, pos_embed, S, grid_w, K, T, C,
+                                                in_chans, patch);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-6, MCM.py:46): fp32 residual row in, bf16 normalised row out.  One warp per row, the row is
+// held in registers (C <= 1024 * ... via float4), two-pass mean / centred variance like ATen.
+// drop_cls = 1: the final encoder_norm (MCM.py:631-632) skips token 0 and writes compact rows n*K + (t-1);
+// optionally also fp32 (x_remain output).
+// ---------------------------------------------------------------------------------------------------------
+template <int VEC_PER_LANE>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int rows, int C, int T, int drop_cls,
+                 float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    long long orow = warp;
+    if (drop_cls) {
+        const int n = warp / T, t = warp - n * T;
+        if (t == 0) return;
+        orow = (long long)n * (T - 1) + (t - 1);
+    }
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)warp * C);
+    float4 v[VEC_PER_LANE];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_LANE; ++i) {
+        v[i] = src[i * 32 + lane];
+        sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VEC_PER_LANE; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += a * a + b * b + c * c + d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < VEC_PER_LANE; ++i) {
+        const float4 g = __ldg(g4 + i * 32 + lane), b = __ldg(b4 + i * 32 + lane);
+        const float o0 = (v[i].x - mean) * rstd * g.x + b.x;
+        const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
+        const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
+        const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
+        uint2 pk;
+        pk.x = pack_bf16x2(o0, o1);
+        pk.y = pack_bf16x2(o2, o3);
+        *reinterpret_cast<uint2*>(out + (size_t)orow * C + (i * 32 + lane) * 4) = pk;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)orow * C + (i * 32 + lane) * 4) = make_float4(o0, o1, o2, o3);
+    }
+}
+
+cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
+                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st) {
+    const int blocks = (rows * 32 + 255) / 256;
+    if (C % 128 != 0) return cudaErrorInvalidValue;
+    switch (C / 128) {
+        case 6: layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 8: layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 10: layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 3: layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 4: layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Factorized-prior likelihood of z + quantisation (compressai EntropyBottleneck eval forward, MCM.py:741-744).
+// eb_tab: [Cz][64] fp32 per channel: softplus(matrix0)[3] bias0[3] tanh(factor0)[3] | softplus(matrix1)[9] bias1[3]
+// tanh(factor1)[3] | (x2 more 3x3 layers) | softplus(matrix4)[3] bias4[1] | median at [60].
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float eb_logits(const float* __restrict__ t, float x) {
+    float h[3], g[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        float v = t[i] * x + t[3 + i];
+        h[i] = v + t[6 + i] * tanhf(v);
+    }
+    const float* tt = t + 9;
+#pragma unroll
+    for (int l = 0; l < 3; ++l) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            float v = tt[i * 3 + 0] * h[0];
+            v += tt[i * 3 + 1] * h[1];
+            v += tt[i * 3 + 2] * h[2];
+            v += tt[9 + i];
+            g[i] = v + tt[12 + i] * tanhf(v);
+        }
+        h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
+        tt += 15;
+    }
+    float v = tt[0] * h[0];
+    v += tt[1] * h[1];
+    v += tt[2] * h[2];
+    return v + tt[3];
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// z: [rows, Cz] compact channels-last.  zhat_pad (optional): bf16 haloed layout of side s4 for h_s.
+__global__ void __launch_bounds__(256)
+bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab, long long total, int Cz,
+                  float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
+                  __nv_bfloat16* __restrict__ zhat_pad, int s4, double* __restrict__ rate_acc, int rows_per_image) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float lg = 0.f;
+    int n = 0;
+    if (idx < total) {
+        const long long row = idx / Cz;
+        const int c = (int)(idx - row * Cz);
+        const float* t = eb_tab + (size_t)c * 64;
+        const float med = t[60];
+        const float sym = rintf(z[idx] - med);
+        const float zh = sym + med;
+        const float lower = eb_logits(t, zh - 0.5f);
+        const float upper = eb_logits(t, zh + 0.5f);
+        const float sum = lower + upper;
+        const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
+        float lik = fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
+        lik = fmaxf(lik, 1e-9f);
+        if (lik_out) lik_out[idx] = lik;
+        if (sym_out) sym_out[idx] = (int32_t)sym;
+        if (zhat_out) zhat_out[idx] = zh;
+        n = (int)(row / rows_per_image);
+        if (zhat_pad) {
+            const int j = (int)(row - (long long)n * rows_per_image);
+            const int y = j / s4, x = j - y * s4;
+            const long long prow = (long long)n * (s4 + 1) * (s4 + 1) + y * (s4 + 1) + x;
+            zhat_pad[prow * Cz + c] = __float2bfloat16(zh);
+        }
+        lg = log2f(lik);
+    }
+    if (rate_acc) {
+        // a warp may straddle two images when Cz*rows_per_image is not a multiple of 32: reduce per image id
+        const int n0 = __shfl_sync(0xffffffffu, n, 0);
+        const bool same = __all_sync(0xffffffffu, (idx >= total) || n == n0);
+        if (same) {
+            const float s = warp_sum(lg);
+            if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(rate_acc + n0, (double)s);
+        } else if (idx < total) {
+            atomicAdd(rate_acc + n, (double)lg);
+        }
+    }
+}
+
+cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
+                              float* zhat, __nv_bfloat16* zhat_pad, int s4, double* rate_acc, int rows_per_image,
+                              cudaStream_t st) {
+    const long long total = rows * Cz;
+    if (total == 0) return cudaSuccess;
+    const int blocks = (int)((total + 255) / 256);
+    bottleneck_kernel<<<blocks, 256, 0, st>>>(z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4, rate_acc,
+                                              rows_per_image);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gaussian conditional likelihood + quantisation of one latent slice (compressai GaussianConditional eval
+// forward + quantize_ste, MCM.py:771-776).  Each thread handles 4 consecutive channels (128-bit accesses).
+//   y, mu, sigma, lik, sym, y_hat : fp32 / int32 [rows, ld] with channel offset col0, `cs` channels in the slice.
+//   yhat_pad (optional) : bf16 haloed layout [N*P, ld_pad], same channel offset: support for later slices.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gaussian_elem(float y, float mu, float sigma, float& lik, float& sym, float& yhat) {
+    const float kNegInvSqrt2 = -0.70710678118654752440f;        // float(-(2 ** -0.5))
+    sym = rintf(y - mu);
+    yhat = sym + mu;
+    const float d = fabsf(yhat - mu);
+    const float s = fmaxf(sigma, 0.11f);
+    const float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - d) / s));
+    const float lower = 0.5f * erfcf(kNegInvSqrt2 * ((-0.5f - d) / s));
+    lik = fmaxf(upper - lower, 1e-9f);
+}
+
+__global__ void __launch_bounds__(256)
+gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
+                      long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
+                      int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_pad,
+                      int ld_pad, int s, double* __restrict__ rate_acc) {
+    const int vec_per_row = cs >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = rows * vec_per_row;
+    float lg = 0.f;
+    int n = 0;
+    if (idx < total) {
+        const long long row = idx / vec_per_row;
+        const int c = col0 + (int)(idx - row * vec_per_row) * 4;
+        const size_t off = (size_t)row * ld + c;
+        const float4 yv = *reinterpret_cast<const float4*>(y + off);
+        const float4 mv = *reinterpret_cast<const float4*>(mu + off);
+        const float4 sv = *reinterpret_cast<const float4*>(sigma + off);
+        float4 lk, sy, yh;
+        gaussian_elem(yv.x, mv.x, sv.x, lk.x, sy.x, yh.x);
+        gaussian_elem(yv.y, mv.y, sv.y, lk.y, sy.y, yh.y);
+        gaussian_elem(yv.z, mv.z, sv.z, lk.z, sy.z, yh.z);
+        gaussian_elem(yv.w, mv.w, sv.w, lk.w, sy.w, yh.w);
+        if (lik_out) *reinterpret_cast<float4*>(lik_out + off) = lk;
+        if (sym_out) *reinterpret_cast<int4*>(sym_out + off) = make_int4((int)sy.x, (int)sy.y, (int)sy.z, (int)sy.w);
+        if (yhat_out) *reinterpret_cast<float4*>(yhat_out + off) = yh;
+        const int K = s * s;
+        n = (int)(row / K);
+        if (yhat_pad) {
+            const int j = (int)(row - (long long)n * K);
+            const int py = j / s, px = j - py * s;
+            const long long prow = (long long)n * (s + 1) * (s + 1) + py * (s + 1) + px;
+            uint2 pk;
+            pk.x = pack_bf16x2(yh.x, yh.y);
+            pk.y = pack_bf16x2(yh.z, yh.w);
+            *reinterpret_cast<uint2*>(yhat_pad + prow * ld_pad + c) = pk;
+        }
+        lg = (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
+    }
+    if (rate_acc) {
+        const int n0 = __shfl_sync(0xffffffffu, n, 0);
+        const bool same = __all_sync(0xffffffffu, (idx >= total) || n == n0);
+        if (same) {
+            const float sm = warp_sum(lg);
+            if ((threadIdx.x & 31) == 0 && sm != 0.f) atomicAdd(rate_acc + n0, (double)sm);
+        } else if (idx < total) {
+            atomicAdd(rate_acc + n, (double)lg);
+        }
+    }
+}
+
+cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
+                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_pad, int ld_pad,
+                                  int s, double* rate_acc, cudaStream_t st) {
+    const long long total = rows * (cs / 4);
+    if (total == 0) return cudaSuccess;
+    const int blocks = (int)((total + 255) / 256);
+    gaussian_slice_kernel<<<blocks, 256, 0, st>>>(y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat, yhat_pad, ld_pad, s,
+                                                  rate_acc);
+    return cudaGetLastError();
+}
+
+// flat variant for the stand-alone operator (n elements, no layout)
+__global__ void gaussian_flat_kernel(const float* __restrict__ y, const float* __restrict__ mu,
+                                     const float* __restrict__ sigma, long long n, float* __restrict__ lik,
+                                     int32_t* __restrict__ sym, float* __restrict__ yhat) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float l, s, h;
+    gaussian_elem(y[i], mu[i], sigma[i], l, s, h);
+    if (lik) lik[i] = l;
+    if (sym) sym[i] = (int32_t)s;
+    if (yhat) yhat[i] = h;
+}
+cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* sigma, long long n, float* lik,
+                                 int32_t* sym, float* yhat, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    gaussian_flat_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(y, mu, sigma, n, lik, sym, yhat);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Rate finalise: bpp[n] = -sum(log2 lik) / S^2 (rd_loss.py:15-20, per image) and the batch pair
+// {sum log2 lik, N*S*S} that the data-parallel all-reduce combines.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N, double pixels_per_image,
+                                     float* __restrict__ bpp, double* __restrict__ rate_sums) {
+    double tot = 0.0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const double a = rate_acc[n];
+        if (bpp) bpp[n] = (float)(-a / pixels_per_image);
+        tot += a;
+    }
+    __shared__ double sh[32];
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0 && rate_sums) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+        rate_sums[0] = t;
+        rate_sums[1] = pixels_per_image * N;
+    }
+}
+cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
+                                 double* rate_sums, cudaStream_t st) {
+    rate_finalize_kernel<<<1, 256, 0, st>>>(rate_acc, N, pixels_per_image, bpp, rate_sums);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 compact [N*K, C] -> bf16 haloed layout (teacher-forced entry: y supplied by the caller)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void compact_to_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows,
+                                      int C, int s) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int vec = C >> 2;
+    if (idx >= rows * vec) return;
+    const long long row = idx / vec;
+    const int c = (int)(idx - row * vec) * 4;
+    const int K = s * s;
+    const int n = (int)(row / K);
+    const int j = (int)(row - (long long)n * K);
+    const int y = j / s, x = j - y * s;
+    const long long prow = (long long)n * (s + 1) * (s + 1) + y * (s + 1) + x;
+    const float4 v = *reinterpret_cast<const float4*>(src + row * C + c);
+    uint2 pk;
+    pk.x = pack_bf16x2(v.x, v.y);
+    pk.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(dst + prow * C + c) = pk;
+}
+cudaError_t launch_compact_to_pad(const float* src, __nv_bfloat16* dst, long long rows, int C, int s, cudaStream_t st) {
+    const long long total = rows * (C / 4);
+    if (total == 0) return cudaSuccess;
+    compact_to_pad_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(src, dst, rows, C, s);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight prepack: fp32 [Cout, Cin_total, kh, kw] (or [Cout, Cin] linear) -> bf16 [Cout, Kp], K index =
+// tap-major, then channel segment (each padded to a multiple of 64 with zeros), then channel.
+// shuffle = 1: output row q*Cq + c takes source channel c*4 + q (PixelShuffle(2) made contiguous per quadrant).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                      int Cin_total, int taps, int nseg, int seg_c0, int seg_c1, int seg_c2,
+                                      int shuffle) {
+    const int segc[3] = {seg_c0, seg_c1, seg_c2};
+    int segpad[3], kp_tap = 0;
+    for (int i = 0; i < 3; ++i) {
+        segpad[i] = i < nseg ? ((segc[i] + 63) / 64) * 64 : 0;
+        kp_tap += segpad[i];
+    }
+    const long long Kp = (long long)kp_tap * taps;
+    const long long total = (long long)Cout * Kp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int ro = (int)(idx / Kp);
+        const long long kidx = idx - (long long)ro * Kp;
+        const int tap = (int)(kidx / kp_tap);
+        int within = (int)(kidx - (long long)tap * kp_tap);
+        int ci = -1, cbase = 0;
+        for (int i = 0; i < nseg; ++i) {
+            if (within < segpad[i]) {
+                if (within < segc[i]) ci = cbase + within;
+                break;
+            }
+            within -= segpad[i];
+            cbase += segc[i];
+        }
+        int co = ro;
+        if (shuffle) {
+            const int cq = Cout >> 2;
+            const int q = ro / cq, c = ro - q * cq;
+            co = c * 4 + q;
+        }
+        float v = 0.f;
+        if (ci >= 0) v = w[((size_t)co * Cin_total + ci) * taps + tap];
+        out[idx] = __float2bfloat16(v);
+    }
+}
+cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
+                                  const int* segc, int shuffle, cudaStream_t st) {
+    prepack_weight_kernel<<<1024, 256, 0, st>>>(w, out, Cout, Cin_total, taps, nseg, segc[0], nseg > 1 ? segc[1] : 0,
+                                                nseg > 2 ? segc[2] : 0, shuffle);
+    return cudaGetLastError();
+}
+
+__global__ void permute_bias_shuffle_kernel(const float* __restrict__ b, float* __restrict__ out, int Cout) {
+    const int ro = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ro >= Cout) return;
+    const int cq = Cout >> 2;
+    const int q = ro / cq, c = ro - q * cq;
+    out[ro] = b[c * 4 + q];
+}
+cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st) {
+    permute_bias_shuffle_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(b, out, Cout);
+    return cudaGetLastError();
+}
+
+// Factorized-prior table: softplus(matrix), bias, tanh(factor), median (see bottleneck_kernel).
+__global__ void eb_table_kernel(const float* m0, const float* b0, const float* f0, const float* m1, const float* b1,
+                                const float* f1, const float* m2, const float* b2, const float* f2, const float* m3,
+                                const float* b3, const float* f3, const float* m4, const float* b4,
+                                const float* quantiles, float* tab, int Cz) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cz) return;
+    float* t = tab + (size_t)c * 64;
+    auto softplus = [](float x) { return x > 20.f ? x : log1pf(expf(x)); };   // F.softplus(beta=1, threshold=20)
+    for (int i = 0; i < 3; ++i) {
+        t[i] = softplus(m0[c * 3 + i]);
+        t[3 + i] = b0[c * 3 + i];
+        t[6 + i] = tanhf(f0[c * 3 + i]);
+    }
+    const float* mm[3] = {m1, m2, m3};
+    const float* bb[3] = {b1, b2, b3};
+    const float* ff[3] = {f1, f2, f3};
+    for (int l = 0; l < 3; ++l) {
+        float* tt = t + 9 + 15 * l;
+        for (int i = 0; i < 9; ++i) tt[i] = softplus(mm[l][c * 9 + i]);
+        for (int i = 0; i < 3; ++i) {
+            tt[9 + i] = bb[l][c * 3 + i];
+            tt[12 + i] = tanhf(ff[l][c * 3 + i]);
+        }
+    }
+    float* tl = t + 54;
+    for (int i = 0; i < 3; ++i) tl[i] = softplus(m4[c * 3 + i]);
+    tl[3] = b4[c];
+    t[58] = 0.f; t[59] = 0.f;
+    t[60] = quantiles[c * 3 + 1];
+    t[61] = 0.f; t[62] = 0.f; t[63] = 0.f;
+}
+cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st) {
+    eb_table_kernel<<<(Cz + 127) / 128, 128, 0, st>>>(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6],
+                                                      ptrs[7], ptrs[8], ptrs[9], ptrs[10], ptrs[11], ptrs[12],
+                                                      ptrs[13], ptrs[14], tab, Cz);
+    return cudaGetLastError();
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        o[i] = __float2bfloat16(a[i]);
+}
+cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    f32_to_bf16_kernel<<<512, 256, 0, st>>>(a, o, n);
+    return cudaGetLastError();
+}
+
+}  // namespace tmae

@@ -1,0 +1,76 @@
+// Parameter block of the multi-tap / multi-segment GEMM engine (linear layers, 1x1 convs and 3x3 convs as
+// 9 row-shifted GEMM taps over a zero-haloed channels-last activation matrix).  One GemmParams lives in device
+// memory per layer (per group member for grouped launches); the kernels index it with blockIdx.z.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace tmae {
+
+constexpr int kBlockM = 128;      // UMMA M (cta_group::1)
+constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one 128B-swizzle atom row
+constexpr int kMaxSegs = 3;
+constexpr int kMaxTaps = 9;
+
+enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_PADDED = 2 };
+enum RowMap : int {
+    MAP_SAME = 0,        // out row = m
+    MAP_TO_PAD,          // compact (n, j) -> zero-haloed layout of side s
+    MAP_TO_COMPACT,      // haloed (n, y, x) -> n*s*s + y*s + x
+    MAP_TO_TOKEN,        // compact (n, j) -> token row n*T + 1 + j
+    MAP_S2_PAD,          // stride-2 subsample -> haloed layout of side s/2
+    MAP_S2_COMPACT,      // stride-2 subsample -> compact layout of side s/2
+    MAP_SHUF_PAD,        // PixelShuffle(2): column quadrant q -> haloed layout of side 2s
+    MAP_GATHER1          // row = gather_ids[m] + 1 (pos-embed lookup)
+};
+enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_HALF_TANH = 2 };
+enum OutType : int { OUT_NONE = 0, OUT_BF16 = 1, OUT_F32 = 2 };
+
+struct OutSpec {
+    void* ptr;
+    int ld;        // elements per row
+    int dtype;     // OutType
+    int map;       // RowMap
+};
+
+struct alignas(64) GemmParams {
+    CUtensorMap a_map[kMaxSegs];      // [rows, C_seg] bf16, box 64 x 128, SWIZZLE_128B
+    CUtensorMap b_map;                // [N, Kpacked] bf16, box 64 x block_n, SWIZZLE_128B
+    // raw views of the same operands (CUDA-core checker kernel)
+    const __nv_bfloat16* a_ptr[kMaxSegs];
+    int a_ld[kMaxSegs];
+    int a_cols[kMaxSegs];             // valid channels of the segment
+    long long a_rows[kMaxSegs];       // valid rows of the segment's matrix
+    const __nv_bfloat16* b_ptr;
+    int b_ld;                         // Kpacked
+    // K loop
+    int num_segs;
+    int seg_kblocks[kMaxSegs];        // ceil(C_seg / 64)
+    int num_taps;
+    int tap_off[kMaxTaps];            // row shift of each tap
+    // problem
+    int M;                            // rows of the input row space covered by this launch
+    int N;                            // output channels
+    int block_n;
+    // input row space geometry
+    int in_mode;
+    int s;                            // side of the pixel grid
+    int P;                            // (s+1)^2 rows per image in the haloed layout
+    int K;                            // s*s
+    int T;                            // tokens per image (K + 1)
+    // epilogue
+    const float* bias;                // [N] (already permuted for MAP_SHUF_PAD)
+    int act;
+    const float* resid;               // optional fp32 addend, read at row map `resid_map`
+    int resid_ld;
+    int resid_map;
+    const int64_t* gather_ids;        // MAP_GATHER1
+    OutSpec out[2];
+    double flops;                     // algorithmic flops of this GEMM (profiling)
+};
+
+// haloed layout: per image (s+1) x (s+1) rows; pixel (y, x) at y*(s+1)+x; column s and row s are zero.
+__host__ __device__ inline int halo_rows_per_image(int s) { return (s + 1) * (s + 1); }
+
+}  // namespace tmae

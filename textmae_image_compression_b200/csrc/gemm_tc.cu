@@ -1,0 +1,324 @@
+// tcgen05 / TMEM / TMA GEMM engine for sm_100a.
+//
+// One CTA computes a 128 x block_n fp32 accumulator tile in tensor memory:
+//   warp 0    : TMA producer  - per k-block one 128x64 bf16 A tile (row-shifted per conv tap, channel segment
+//                               per concatenated source) and one block_n x 64 bf16 weight tile, 128B-swizzled
+//   warp 1    : allocates TMEM, single elected thread issues tcgen05.mma (M=128, N=block_n, K=16) x 4 per k-block,
+//               tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5 : epilogue - tcgen05.ld 32 lanes x 32 columns, + bias, GELU / 0.5*tanh, residual / pos-embed add,
+//               row remap (halo layout, stride-2 subsample, PixelShuffle, token rows), bf16 / fp32 stores
+// Serves reference layers: PatchEmbed conv (MCM.py:300-302), Block linears (MCM.py:313-322), g_a 1x1 convs
+// (MCM.py:77-93), h_a / h_s / cc_transform / lrp_transform 3x3 convs (MCM.py:115-293).
+#include <stdio.h>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace tmae {
+
+// ---------------------------------------------------------------------------------------------------------
+// epilogue shared by the tensor-core kernel and the CUDA-core checker
+// ---------------------------------------------------------------------------------------------------------
+struct RowCtx {
+    int valid, n, y, x, lin;
+};
+
+__device__ __forceinline__ RowCtx decode_row(const GemmParams& p, int m) {
+    RowCtx r;
+    r.lin = m;
+    r.valid = m < p.M;
+    r.n = r.y = r.x = 0;
+    if (p.in_mode == IN_PADDED) {
+        const int w = p.s + 1;
+        r.n = m / p.P;
+        const int rem = m - r.n * p.P;
+        r.y = rem / w;
+        r.x = rem - r.y * w;
+        r.valid = r.valid && (r.y < p.s) && (r.x < p.s);
+    } else if (p.in_mode == IN_COMPACT) {
+        r.n = m / p.K;
+        const int j = m - r.n * p.K;
+        r.y = j / p.s;
+        r.x = j - r.y * p.s;
+    }
+    return r;
+}
+
+// q = PixelShuffle quadrant (dy*2+dx) of the column group; returns -1 when this row produces no output.
+__device__ __forceinline__ long long map_row(const GemmParams& p, int map, const RowCtx& r, int q) {
+    switch (map) {
+        case MAP_SAME: return r.lin;
+        case MAP_TO_PAD: return (long long)r.n * p.P + r.y * (p.s + 1) + r.x;
+        case MAP_TO_COMPACT: return (long long)r.n * p.K + r.y * p.s + r.x;
+        case MAP_TO_TOKEN: return (long long)r.n * p.T + 1 + r.y * p.s + r.x;
+        case MAP_S2_PAD: {
+            if ((r.y | r.x) & 1) return -1;
+            const int s2 = p.s >> 1;
+            return (long long)r.n * (s2 + 1) * (s2 + 1) + (r.y >> 1) * (s2 + 1) + (r.x >> 1);
+        }
+        case MAP_S2_COMPACT: {
+            if ((r.y | r.x) & 1) return -1;
+            const int s2 = p.s >> 1;
+            return (long long)r.n * s2 * s2 + (r.y >> 1) * s2 + (r.x >> 1);
+        }
+        case MAP_SHUF_PAD: {
+            const int s2 = p.s << 1;
+            return (long long)r.n * (s2 + 1) * (s2 + 1) + (2 * r.y + (q >> 1)) * (s2 + 1) + 2 * r.x + (q & 1);
+        }
+        case MAP_GATHER1: return p.gather_ids[r.lin] + 1;
+    }
+    return -1;
+}
+
+// Finish 8 consecutive output channels [col, col+8) of one accumulator row.
+__device__ __forceinline__ void epilogue8(const GemmParams& p, const RowCtx& r, int col, float (&v)[8]) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    if (p.act == ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+    } else if (p.act == ACT_HALF_TANH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.5f * tanhf(v[i]);
+    }
+    // PixelShuffle bookkeeping: weights are packed quadrant-major, so 8 consecutive columns share (dy,dx).
+    int q = 0, ocol = col;
+    const bool shuf = (p.out[0].map == MAP_SHUF_PAD) || (p.out[1].map == MAP_SHUF_PAD);
+    if (shuf) {
+        const int cq = p.N >> 2;
+        q = col / cq;
+        ocol = col - q * cq;
+    }
+    if (p.resid != nullptr) {
+        const long long rr = map_row(p, p.resid_map, r, q);
+        const float* src = p.resid + rr * p.resid_ld + ocol;
+        const float4 r0 = *reinterpret_cast<const float4*>(src);
+        const float4 r1 = *reinterpret_cast<const float4*>(src + 4);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+        v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+        const OutSpec& os = p.out[o];
+        if (os.dtype == OUT_NONE) continue;
+        const long long orow = map_row(p, os.map, r, q);
+        if (orow < 0) continue;
+        if (os.dtype == OUT_BF16) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(os.ptr) + orow * os.ld + ocol) = pk;
+        } else {
+            float* dst = reinterpret_cast<float*>(os.ptr) + orow * os.ld + ocol;
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor-core kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGemmThreads = 192;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
+    const GemmParams& p = params[blockIdx.z];
+    const int m0 = blockIdx.x * kBlockM;
+    const int n0 = blockIdx.y * p.block_n;
+    if (m0 >= p.M || n0 >= p.N) return;   // grouped launches: grid is sized for the largest member
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int block_n = p.block_n;
+    const int b_stage_bytes = block_n * kBlockK * 2;
+    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* accum_bar = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)block_n) tmem_cols <<= 1;
+
+    int kb_per_tap = 0;
+    for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
+    const int total_kb = kb_per_tap * p.num_taps;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        for (int sg = 0; sg < p.num_segs; ++sg) tma_prefetch_desc(&p.a_map[sg]);
+        tma_prefetch_desc(&p.b_map);
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int kb = 0;
+            const uint32_t tx_bytes = (uint32_t)stage_bytes;
+            for (int tap = 0; tap < p.num_taps; ++tap) {
+                const int row = m0 + p.tap_off[tap];
+                for (int sg = 0; sg < p.num_segs; ++sg) {
+                    const int nkb = p.seg_kblocks[sg];
+                    for (int k = 0; k < nkb; ++k, ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sA = smem + (size_t)stage * stage_bytes;
+                        uint8_t* sB = sA + kAStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+                        tma_load_2d(sA, &p.a_map[sg], &full_bar[stage], k * kBlockK, row);
+                        tma_load_2d(sB, &p.b_map, &full_bar[stage], kb * kBlockK, n0);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
+                const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kAStageBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                              (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[stage]);      // smem stage reusable once these MMAs retire
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            umma_commit(accum_bar);                  // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====
+        const int quarter = warp & 3;
+        const int m = m0 + quarter * 32 + lane;
+        const RowCtx r = decode_row(p, m);
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        for (int c0 = 0; c0 < block_n; c0 += 32) {
+            uint32_t acc[32];
+            if (block_n - c0 >= 32) {
+                tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
+            } else {                                  // block_n is a multiple of 16
+                uint32_t a16[16];
+                tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, a16);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { acc[i] = a16[i]; acc[16 + i] = 0u; }
+            }
+            tmem_ld_wait();
+            if (r.valid) {
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const int col = n0 + c0 + g8 * 8;
+                    if (c0 + g8 * 8 < block_n && col < p.N) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g8 * 8 + i]);
+                        epilogue8(p, r, col, v);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CUDA-core checker: same parameter block, same epilogue, plain loads.  Bring-up / tests only.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gemm_simt_kernel(const GemmParams* __restrict__ params) {
+    const GemmParams& p = params[blockIdx.z];
+    const int m = blockIdx.x;
+    if (m >= p.M) return;
+    const RowCtx r = decode_row(p, m);
+    if (!r.valid) return;
+    int kp_per_tap = 0;
+    for (int sg = 0; sg < p.num_segs; ++sg) kp_per_tap += p.seg_kblocks[sg] * kBlockK;
+    for (int col = threadIdx.x * 8; col < p.N; col += blockDim.x * 8) {
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int tap = 0; tap < p.num_taps; ++tap) {
+            const long long row = (long long)m + p.tap_off[tap];
+            int kbase = tap * kp_per_tap;
+            for (int sg = 0; sg < p.num_segs; ++sg) {
+                if (row >= 0 && row < p.a_rows[sg]) {
+                    const __nv_bfloat16* a = p.a_ptr[sg] + row * p.a_ld[sg];
+                    for (int c = 0; c < p.a_cols[sg]; ++c) {
+                        const float av = __bfloat162float(a[c]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            v[i] = fmaf(av, __bfloat162float(p.b_ptr[(long long)(col + i) * p.b_ld + kbase + c]), v[i]);
+                    }
+                }
+                kbase += p.seg_kblocks[sg] * kBlockK;
+            }
+        }
+        epilogue8(p, r, col, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------------------
+int gemm_pick_stages(int block_n, int* smem_bytes) {
+    const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    *smem_bytes = 1024 + stages * stage_bytes + 256;
+    return stages;
+}
+
+cudaError_t gemm_tc_configure() {
+    return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
+cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, bool simt,
+                        cudaStream_t stream) {
+    if (simt) {
+        dim3 grid(max_M, 1, groups);
+        gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
+        return cudaGetLastError();
+    }
+    int smem = 0;
+    const int stages = gemm_pick_stages(block_n, &smem);
+    dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
+    gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    return cudaGetLastError();
+}
+
+}  // namespace tmae

@@ -1,0 +1,1237 @@
+// Host runtime behind include/tmae.h: handle, weight ingestion / prepack, per-batch-size launch plans, the forward.
+// Every layer of the reference's compression forward path (MCM.py:590-634, 714-787) is one or more entries of a
+// static launch plan; tmae_forward only walks the plan (no host sync, no allocation once the plan exists).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/tmae.h"
+#include "gemm.cuh"
+#include "kernels.h"
+
+using namespace tmae;
+
+namespace {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string g_create_error;
+
+struct RawTensor {
+    float* ptr = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+};
+
+struct Layer {                      // one prepacked linear / conv
+    __nv_bfloat16* w = nullptr;     // [Cout, Kp]
+    float* bias = nullptr;          // [Cout] (permuted for PixelShuffle layers)
+    int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
+};
+
+enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE, ST_Y_TO_PAD };
+enum Family { FAM_GEMM = 0, FAM_ATTN, FAM_LN, FAM_MASK, FAM_GATHER, FAM_ENTROPY, FAM_MISC, FAM_COUNT };
+const char* kFamilyNames[FAM_COUNT] = {"gemm_tc", "attention", "layernorm", "mask_select", "gather_patches",
+                                       "entropy_elementwise", "misc"};
+
+struct Step {
+    StepKind kind;
+    int family = FAM_MISC;
+    // GEMM
+    int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0;
+    double flops = 0, bytes = 0;
+    // LN
+    const float* ln_gamma = nullptr;
+    const float* ln_beta = nullptr;
+    int ln_final = 0;
+    // GC
+    int slice = 0;
+    std::string tag;
+};
+
+struct Plan {
+    int N = 0;
+    std::vector<Step> steps;
+    std::vector<GemmParams> host_params;
+    GemmParams* d_params = nullptr;
+    bool from_latent_ok = true;
+    int first_rate_step = 0;        // index of the first step of the rate half (h_a)
+    int encoder_end_step = 0;       // one past the final LayerNorm
+};
+
+struct Workspace {
+    int cap_N = 0;
+    size_t bytes = 0;
+    std::vector<void*> allocs;
+    // encoder
+    int64_t* ids_keep = nullptr;
+    __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *h1 = nullptr, *enc = nullptr;
+    float* x = nullptr;
+    // g_a
+    __nv_bfloat16 *ga1 = nullptr, *ga2 = nullptr, *ga3 = nullptr, *y_pad = nullptr;
+    float *y = nullptr, *z = nullptr, *mu = nullptr, *sigma = nullptr, *yhat = nullptr;
+    // h_a / h_s
+    __nv_bfloat16 *ha1 = nullptr, *ha2 = nullptr, *ha3 = nullptr, *ha4 = nullptr, *zhat_pad = nullptr;
+    __nv_bfloat16 *hs1[2] = {nullptr, nullptr}, *hs2[2] = {nullptr, nullptr}, *hs3[2] = {nullptr, nullptr},
+                  *hs4[2] = {nullptr, nullptr}, *lat[2] = {nullptr, nullptr};     // 0 = means, 1 = scales
+    __nv_bfloat16* yhat_pad = nullptr;
+    __nv_bfloat16* t[3][4] = {{nullptr}};      // per net (mean, scale, lrp) 4 intermediate activations
+    double* rate_acc = nullptr;
+    float* bpp = nullptr;
+    double* rate_sums = nullptr;
+    // host-buffer entry staging
+    float *st_imgs = nullptr, *st_scores = nullptr;
+};
+
+}  // namespace
+
+struct tmae_handle {
+    tmae_config cfg;
+    int L, K, T, s, C, H, hd, mlp, Cy, Cz, nsl, sc, grid_w, patch_dim, P, s2, P2, s4, P4;
+    int ga_ch[5];
+    std::string err;
+    std::map<std::string, RawTensor> raw;
+    std::map<std::string, Layer> layers;
+    std::map<std::string, float*> vecs;       // fp32 vectors kept as-is (LN params, cls, pos-embed)
+    float* eb_tab = nullptr;
+    bool finalized = false;
+    Workspace ws;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    PFN_encodeTiled encode = nullptr;
+    std::vector<void*> weight_allocs;
+    // profiling
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<int> prof_family;
+    std::vector<double> prof_flops, prof_bytes;
+    size_t prof_used = 0;
+    int dev = 0;
+};
+
+namespace {
+
+int fail(tmae_handle* h, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((h), TMAE_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename Tp>
+int dev_alloc(tmae_handle* h, std::vector<void*>& pool, Tp** out, size_t count, size_t* total = nullptr) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(Tp);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(h, TMAE_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return fail(h, TMAE_ECUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    pool.push_back(p);
+    *out = reinterpret_cast<Tp*>(p);
+    if (total) *total += bytes;
+    return TMAE_OK;
+}
+
+int pad64(int c) { return (c + 63) / 64 * 64; }
+int round16(int c) { return (c + 15) / 16 * 16; }
+
+// ---- geometry ------------------------------------------------------------------------------------------
+int derive_geometry(tmae_handle* h) {
+    const tmae_config& c = h->cfg;
+    if (c.img_size <= 0 || c.patch_size <= 0 || c.img_size % c.patch_size != 0)
+        return fail(nullptr, TMAE_EINVAL, "image size %d must be a positive multiple of patch size %d", c.img_size, c.patch_size);
+    h->grid_w = c.img_size / c.patch_size;
+    h->L = h->grid_w * h->grid_w;
+    h->K = c.num_keep_patches;
+    if (h->K > h->L)
+        return fail(nullptr, TMAE_EINVAL, "Number of patches should not be greater than the length of scores");   // MCM.py:374-376
+    h->s = (int)lround(sqrt((double)h->K));
+    if (h->s * h->s != h->K)
+        return fail(nullptr, TMAE_EINVAL, "num_keep_patches=%d is not a perfect square (reference view() at MCM.py:729 fails)", h->K);
+    if (h->s % 4 != 0)
+        return fail(nullptr, TMAE_EINVAL, "sqrt(num_keep_patches)=%d must be a multiple of 4 (reference torch.cat at MCM.py:761 fails)", h->s);
+    h->T = h->K + 1;
+    h->C = c.encoder_embed_dim;
+    h->H = c.encoder_num_heads;
+    if (h->H <= 0 || h->C % h->H != 0 || h->C / h->H != 64)
+        return fail(nullptr, TMAE_EINVAL, "head_dim must be 64 (embed %d / heads %d)", h->C, h->H);
+    h->hd = 64;
+    h->mlp = (int)(h->C * c.mlp_ratio);
+    h->Cy = c.latent_depth;
+    h->Cz = c.hyperprior_depth;
+    h->nsl = c.num_slices;
+    if (h->nsl != 12 || h->Cy % h->nsl != 0 || (h->Cy / h->nsl) % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "unsupported latent_depth/num_slices %d/%d", h->Cy, h->nsl);
+    h->sc = h->Cy / h->nsl;
+    h->patch_dim = c.in_chans * c.patch_size * c.patch_size;
+    if (c.patch_size % 4 != 0 || h->C % 128 != 0)
+        return fail(nullptr, TMAE_EINVAL, "patch_size %% 4 and embed_dim %% 128 required");
+    h->P = (h->s + 1) * (h->s + 1);
+    h->s2 = h->s / 2; h->P2 = (h->s2 + 1) * (h->s2 + 1);
+    h->s4 = h->s / 4; h->P4 = (h->s4 + 1) * (h->s4 + 1);
+    const int e = h->C, d = c.decoder_embed_dim;
+    h->ga_ch[0] = e;
+    h->ga_ch[1] = (int)(d + (e - d) * 3 / 4.0);
+    h->ga_ch[2] = (int)(d + (e - d) * 2 / 4.0);
+    h->ga_ch[3] = d;
+    h->ga_ch[4] = h->Cy;
+    for (int i = 0; i < 5; ++i)
+        if (h->ga_ch[i] % 8 != 0) return fail(nullptr, TMAE_EINVAL, "g_a channel %d not a multiple of 8", h->ga_ch[i]);
+    return TMAE_OK;
+}
+
+void ha_layers(const tmae_handle* h, int cin[5], int cout[5], int stride[5]) {
+    const int m = h->Cy, z = h->Cz;
+    const int c1 = (int)(z + (m - z) * 3 / 4.0), c2 = (int)(z + (m - z) * 2 / 4.0), c3 = (int)(z + (m - z) / 4.0);
+    const int ci[5] = {m, m, c1, c2, c3}, co[5] = {m, c1, c2, c3, z}, st[5] = {1, 1, 2, 1, 2};
+    for (int i = 0; i < 5; ++i) { cin[i] = ci[i]; cout[i] = co[i]; stride[i] = st[i]; }
+}
+void hs_layers(const tmae_handle* h, int cin[5], int cout[5], int up[5]) {
+    const int m = h->Cy, z = h->Cz;
+    const int c1 = (int)(z + (m - z) / 4.0), c2 = (int)(z + (m - z) * 2 / 4.0), c3 = (int)(z + (m - z) * 3 / 4.0);
+    const int ci[5] = {z, c1, c2, c3, m}, co[5] = {c1, c2, c3, m, m}, u[5] = {1, 2, 1, 2, 1};
+    for (int i = 0; i < 5; ++i) { cin[i] = ci[i]; cout[i] = co[i]; up[i] = u[i]; }
+}
+void cc_channels(const tmae_handle* h, int ch[6], int i, bool lrp) {
+    const int sc = h->sc, ns = h->nsl;
+    const int sup = lrp ? (i + 1 < ns / 2 + 1 ? i + 1 : ns / 2 + 1) : (i < ns / 2 ? i : ns / 2);
+    ch[0] = h->Cy + sc * sup;
+    ch[1] = (int)(sc * (ns / 2 + 1));
+    ch[2] = (int)(sc * (ns / 2 * 3 / 4.0 + 1));
+    ch[3] = (int)(sc * (ns / 2 * 2 / 4.0 + 1));
+    ch[4] = (int)(sc * (ns / 2 * 1 / 4.0 + 1));
+    ch[5] = sc;
+}
+
+// ---- weights -------------------------------------------------------------------------------------------
+bool name_is_needed(const tmae_handle* h, const std::string& n) {
+    static const char* prefixes[] = {"cls_token", "encoder_pos_embed", "encoder_embed.", "encoder_blocks.",
+                                     "encoder_norm.", "g_a.", "h_a.", "h_s_mean.", "h_s_scale.", "cc_transform_mean.",
+                                     "cc_transform_scale.", "lrp_transform.", "entropy_bottleneck._matrix",
+                                     "entropy_bottleneck._bias", "entropy_bottleneck._factor",
+                                     "entropy_bottleneck.quantiles"};
+    for (const char* p : prefixes)
+        if (n.compare(0, strlen(p), p) == 0) return true;
+    (void)h;
+    return false;
+}
+
+const RawTensor* find_raw(tmae_handle* h, const std::string& name) {
+    auto it = h->raw.find(name);
+    return it == h->raw.end() ? nullptr : &it->second;
+}
+
+int need_raw(tmae_handle* h, const std::string& name, size_t numel, const RawTensor** out) {
+    const RawTensor* r = find_raw(h, name);
+    if (!r) return fail(h, TMAE_ESTATE, "missing weight '%s'", name.c_str());
+    if (r->numel != numel)
+        return fail(h, TMAE_EINVAL, "weight '%s' has %zu elements, expected %zu", name.c_str(), r->numel, numel);
+    *out = r;
+    return TMAE_OK;
+}
+
+// Prepack one conv / linear: weight [Cout, Cin, taps] fp32 -> bf16 [Cout, Kp]; bias fp32 (permuted if shuffle).
+int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname, int Cout, int Cin, int taps, int nseg,
+               const int* segc, int shuffle) {
+    const RawTensor *w = nullptr, *b = nullptr;
+    int rc = need_raw(h, wname + ".weight", (size_t)Cout * Cin * taps, &w);
+    if (rc) return rc;
+    rc = need_raw(h, wname + ".bias", (size_t)Cout, &b);
+    if (rc) return rc;
+    Layer L;
+    L.Cout = Cout; L.Cin = Cin; L.taps = taps; L.nseg = nseg; L.shuffle = shuffle;
+    int kp_tap = 0, csum = 0;
+    for (int i = 0; i < nseg; ++i) { L.segc[i] = segc[i]; kp_tap += pad64(segc[i]); csum += segc[i]; }
+    if (csum != Cin) return fail(h, TMAE_EINVAL, "layer %s: segments sum %d != Cin %d", key.c_str(), csum, Cin);
+    L.Kp = kp_tap * taps;
+    rc = dev_alloc(h, h->weight_allocs, &L.w, (size_t)Cout * L.Kp);
+    if (rc) return rc;
+    rc = dev_alloc(h, h->weight_allocs, &L.bias, (size_t)Cout);
+    if (rc) return rc;
+    CUDA_TRY(h, launch_prepack_weight(w->ptr, L.w, Cout, Cin, taps, nseg, L.segc, shuffle, 0));
+    if (shuffle) CUDA_TRY(h, launch_permute_bias_shuffle(b->ptr, L.bias, Cout, 0));
+    else CUDA_TRY(h, cudaMemcpyAsync(L.bias, b->ptr, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+    h->layers[key] = L;
+    return TMAE_OK;
+}
+
+int keep_vec(tmae_handle* h, const std::string& name, size_t numel) {
+    const RawTensor* r = nullptr;
+    int rc = need_raw(h, name, numel, &r);
+    if (rc) return rc;
+    float* p = nullptr;
+    rc = dev_alloc(h, h->weight_allocs, &p, numel);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(p, r->ptr, numel * sizeof(float), cudaMemcpyDeviceToDevice, 0));
+    h->vecs[name] = p;
+    return TMAE_OK;
+}
+
+// ---- tensor maps ---------------------------------------------------------------------------------------
+int make_map(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+             uint32_t box_rows) {
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    if (rows == 0 || cols == 0) return fail(h, TMAE_EINVAL, "empty tensor map");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstr[0] & 15) != 0)
+        return fail(h, TMAE_EINVAL, "tensor map base/stride not 16-byte aligned");
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled failed (%d): cols %llu rows %llu ld %llu box_rows %u", (int)r,
+                    (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_elems, box_rows);
+    return TMAE_OK;
+}
+
+// Choose the N tile: fewest column tiles that still give the machine >= ~120 CTAs (148 SMs), multiple of 16.
+int pick_block_n(int m_tiles, int N, int groups) {
+    int best = round16(N) > 256 ? 256 : round16(N);
+    for (int nt = 1; nt <= 16; ++nt) {
+        int bn = round16((N + nt - 1) / nt);
+        if (bn > 256) continue;
+        best = bn;
+        if ((long long)m_tiles * nt * groups >= 120 || bn <= 64) break;
+    }
+    return best;
+}
+
+struct SegSrc {
+    const __nv_bfloat16* ptr;   // first column of the segment
+    int cols;                   // channels in the segment
+    int ld;                     // row pitch (elements)
+};
+
+struct GemmDesc {
+    const Layer* layer = nullptr;
+    SegSrc seg[3];
+    int nseg = 1;
+    long long a_rows = 0;       // rows of the A matrices
+    int M = 0;                  // rows to compute
+    int in_mode = IN_LINEAR;
+    int side = 0;               // grid side for IN_COMPACT / IN_PADDED
+    bool conv3 = false;
+    int act = ACT_NONE;
+    const float* resid = nullptr; int resid_ld = 0; int resid_map = MAP_SAME;
+    const int64_t* gather_ids = nullptr;
+    OutSpec out0 = {nullptr, 0, OUT_NONE, MAP_SAME};
+    OutSpec out1 = {nullptr, 0, OUT_NONE, MAP_SAME};
+    double flops = 0;
+};
+
+int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmParams* p, int force_block_n) {
+    memset(p, 0, sizeof(*p));
+    const Layer& L = *d.layer;
+    if (d.nseg != L.nseg) return fail(h, TMAE_EINVAL, "segment count mismatch");
+    p->num_segs = d.nseg;
+    for (int i = 0; i < d.nseg; ++i) {
+        if (d.seg[i].cols != L.segc[i]) return fail(h, TMAE_EINVAL, "segment %d width %d != packed %d", i, d.seg[i].cols, L.segc[i]);
+        p->a_ptr[i] = d.seg[i].ptr;
+        p->a_ld[i] = d.seg[i].ld;
+        p->a_cols[i] = d.seg[i].cols;
+        p->a_rows[i] = d.a_rows;
+        p->seg_kblocks[i] = pad64(d.seg[i].cols) / 64;
+        int rc = make_map(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
+        if (rc) return rc;
+    }
+    p->b_ptr = L.w;
+    p->b_ld = L.Kp;
+    p->num_taps = L.taps;
+    p->s = d.side;
+    p->P = (d.side + 1) * (d.side + 1);
+    p->K = d.side * d.side;
+    p->T = p->K + 1;
+    if (L.taps == 9) {
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) p->tap_off[kh * 3 + kw] = (kh - 1) * (d.side + 1) + (kw - 1);
+    } else {
+        p->tap_off[0] = 0;
+    }
+    p->M = d.M;
+    p->N = L.Cout;
+    const int m_tiles = (d.M + kBlockM - 1) / kBlockM;
+    p->block_n = force_block_n > 0 ? force_block_n : pick_block_n(m_tiles, L.Cout, groups_for_tiling);
+    int rc = make_map(h, &p->b_map, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)p->block_n);
+    if (rc) return rc;
+    p->in_mode = d.in_mode;
+    p->bias = L.bias;
+    p->act = d.act;
+    p->resid = d.resid; p->resid_ld = d.resid_ld; p->resid_map = d.resid_map;
+    p->gather_ids = d.gather_ids;
+    p->out[0] = d.out0;
+    p->out[1] = d.out1;
+    p->flops = d.flops;
+    return TMAE_OK;
+}
+
+// ---- workspace -----------------------------------------------------------------------------------------
+void free_pool(std::vector<void*>& pool) {
+    for (void* p : pool) cudaFree(p);
+    pool.clear();
+}
+
+int ensure_workspace(tmae_handle* h, int N) {
+    Workspace& w = h->ws;
+    if (N <= w.cap_N) return TMAE_OK;
+    // plans hold pointers into the workspace: drop them
+    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    h->plans.clear();
+    free_pool(w.allocs);
+    w = Workspace();
+    size_t tot = 0;
+    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rp = (size_t)N * h->P, rp2 = (size_t)N * h->P2,
+                 rp4 = (size_t)N * h->P4, rz = (size_t)N * h->s4 * h->s4;
+    const int C = h->C, Cy = h->Cy, Cz = h->Cz;
+    int ci[5], co[5], aux[5];
+#define WS_ALLOC(field, count)                                                        \
+    do { int _rc = dev_alloc(h, w.allocs, &(field), (count), &tot); if (_rc) return _rc; } while (0)
+    WS_ALLOC(w.ids_keep, rk);
+    WS_ALLOC(w.patches, rk * h->patch_dim);
+    WS_ALLOC(w.x, rt * C);
+    WS_ALLOC(w.xn, rt * C);
+    WS_ALLOC(w.qkv, rt * 3 * C);
+    WS_ALLOC(w.attn, rt * C);
+    WS_ALLOC(w.h1, rt * h->mlp);
+    WS_ALLOC(w.enc, rk * C);
+    WS_ALLOC(w.ga1, rk * h->ga_ch[1]);
+    WS_ALLOC(w.ga2, rk * h->ga_ch[2]);
+    WS_ALLOC(w.ga3, rk * h->ga_ch[3]);
+    WS_ALLOC(w.y_pad, rp * Cy);
+    WS_ALLOC(w.y, rk * Cy);
+    WS_ALLOC(w.z, rz * Cz);
+    WS_ALLOC(w.mu, rk * Cy);
+    WS_ALLOC(w.sigma, rk * Cy);
+    WS_ALLOC(w.yhat, rk * Cy);
+    ha_layers(h, ci, co, aux);
+    WS_ALLOC(w.ha1, rp * co[0]);
+    WS_ALLOC(w.ha2, rp * co[1]);
+    WS_ALLOC(w.ha3, rp2 * co[2]);
+    WS_ALLOC(w.ha4, rp2 * co[3]);
+    WS_ALLOC(w.zhat_pad, rp4 * Cz);
+    hs_layers(h, ci, co, aux);
+    for (int net = 0; net < 2; ++net) {
+        WS_ALLOC(w.hs1[net], rp4 * co[0]);
+        WS_ALLOC(w.hs2[net], rp2 * co[1]);
+        WS_ALLOC(w.hs3[net], rp2 * co[2]);
+        WS_ALLOC(w.hs4[net], rp * co[3]);
+        WS_ALLOC(w.lat[net], rp * Cy);
+    }
+    WS_ALLOC(w.yhat_pad, rp * Cy);
+    int ch[6];
+    cc_channels(h, ch, 0, false);
+    for (int net = 0; net < 3; ++net)
+        for (int l = 0; l < 4; ++l) WS_ALLOC(w.t[net][l], rp * ch[l + 1]);
+    WS_ALLOC(w.rate_acc, (size_t)N);
+    WS_ALLOC(w.bpp, (size_t)N);
+    WS_ALLOC(w.rate_sums, (size_t)2);
+    WS_ALLOC(w.st_imgs, (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size);
+    WS_ALLOC(w.st_scores, (size_t)N * h->L);
+#undef WS_ALLOC
+    w.cap_N = N;
+    w.bytes = tot;
+    return TMAE_OK;
+}
+
+size_t workspace_bytes_estimate(const tmae_handle* h, int N) {
+    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rp = (size_t)N * h->P, rp2 = (size_t)N * h->P2,
+                 rp4 = (size_t)N * h->P4;
+    const size_t C = h->C;
+    size_t b = rk * 8 + rk * h->patch_dim * 2 + rt * C * 4 + rt * C * 2 * 2 + rt * 3 * C * 2 + rt * h->mlp * 2 + rk * C * 2;
+    b += rk * (h->ga_ch[1] + h->ga_ch[2] + h->ga_ch[3]) * 2 + rp * h->Cy * 2 + rk * h->Cy * 4 * 4 + rk / 16 * h->Cz * 4;
+    b += rp * (384 + 336) * 2 + rp2 * (288 + 240) * 2 + rp4 * h->Cz * 2;
+    b += 2 * (rp4 * 240 + rp2 * (288 + 336) + rp * (384 + 384)) * 2 + rp * h->Cy * 2;
+    b += 3 * rp * (224 + 176 + 128 + 80) * 2;
+    b += (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size * 4 + (size_t)N * h->L * 4;
+    return b;
+}
+
+// ---- plan ----------------------------------------------------------------------------------------------
+double conv_flops(long long out_positions, int cin, int cout, int taps) {
+    return 2.0 * (double)out_positions * cin * cout * taps;
+}
+
+int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, const char* tag) {
+    Step st;
+    st.kind = ST_GEMM;
+    st.family = FAM_GEMM;
+    st.param_index = (int)pl.host_params.size();
+    st.groups = groups;
+    st.tag = tag;
+    int max_M = 0, max_N = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (descs[g].M > max_M) max_M = descs[g].M;
+        if (descs[g].layer->Cout > max_N) max_N = descs[g].layer->Cout;
+    }
+    const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
+    const int bn = pick_block_n(m_tiles, max_N, groups);
+    for (int g = 0; g < groups; ++g) {
+        GemmParams p;
+        int rc = fill_params(h, descs[g], groups, &p, bn);
+        if (rc) return rc;
+        pl.host_params.push_back(p);
+        st.flops += descs[g].flops;
+    }
+    st.max_M = max_M; st.max_N = max_N; st.block_n = bn;
+    pl.steps.push_back(st);
+    return TMAE_OK;
+}
+
+SegSrc seg(const __nv_bfloat16* p, int cols, int ld) { SegSrc s; s.ptr = p; s.cols = cols; s.ld = ld; return s; }
+OutSpec outspec(void* p, int ld, int dtype, int map) { OutSpec o; o.ptr = p; o.ld = ld; o.dtype = dtype; o.map = map; return o; }
+
+const Layer* get_layer(tmae_handle* h, const std::string& key) {
+    auto it = h->layers.find(key);
+    return it == h->layers.end() ? nullptr : &it->second;
+}
+
+int build_plan(tmae_handle* h, int N, Plan** out) {
+    auto it = h->plans.find(N);
+    if (it != h->plans.end()) { *out = it->second.get(); return TMAE_OK; }
+    int rc = ensure_workspace(h, N);
+    if (rc) return rc;
+    it = h->plans.find(N);          // ensure_workspace may have cleared the map
+    std::unique_ptr<Plan> plp(new Plan());
+    Plan& pl = *plp;
+    pl.N = N;
+    Workspace& w = h->ws;
+    const int C = h->C, T = h->T, K = h->K, s = h->s, Cy = h->Cy, Cz = h->Cz;
+    const long long rt = (long long)N * T, rk = (long long)N * K, rp = (long long)N * h->P, rp2 = (long long)N * h->P2,
+                    rp4 = (long long)N * h->P4;
+    char tag[96];
+    auto simple = [&](StepKind k, int fam, const char* t) { Step st; st.kind = k; st.family = fam; st.tag = t; pl.steps.push_back(st); };
+
+    simple(ST_ZERO_RATE, FAM_MISC, "zero_rate");
+    simple(ST_MASK, FAM_MASK, "mask_select");
+    simple(ST_GATHER, FAM_GATHER, "gather_patches");
+    {   // patch embed: conv k16 s16 == linear over (c,p,q) patches; + bias + pos_embed[id+1]  (MCM.py:615-618)
+        GemmDesc d;
+        d.layer = get_layer(h, "encoder_embed.proj");
+        d.seg[0] = seg(w.patches, h->patch_dim, h->patch_dim);
+        d.a_rows = rk; d.M = (int)rk; d.in_mode = IN_COMPACT; d.side = s;
+        d.resid = h->vecs["encoder_pos_embed"]; d.resid_ld = C; d.resid_map = MAP_GATHER1; d.gather_ids = w.ids_keep;
+        d.out0 = outspec(w.x, C, OUT_F32, MAP_TO_TOKEN);
+        d.flops = 2.0 * (double)N * h->L * h->patch_dim * C;       // reference embeds all L patches
+        rc = add_gemm_group(h, pl, &d, 1, "patch_embed");
+        if (rc) return rc;
+    }
+    for (int i = 0; i < h->cfg.encoder_depth; ++i) {
+        const std::string pre = "encoder_blocks." + std::to_string(i);
+        Step ln; ln.kind = ST_LN; ln.family = FAM_LN; ln.ln_gamma = h->vecs[pre + ".norm1.weight"]; ln.ln_beta = h->vecs[pre + ".norm1.bias"]; ln.tag = pre + ".norm1";
+        pl.steps.push_back(ln);
+        GemmDesc d;
+        d.layer = get_layer(h, pre + ".attn.qkv");
+        d.seg[0] = seg(w.xn, C, C); d.a_rows = rt; d.M = (int)rt;
+        d.out0 = outspec(w.qkv, 3 * C, OUT_BF16, MAP_SAME);
+        d.flops = 2.0 * rt * C * 3.0 * C;
+        snprintf(tag, sizeof(tag), "blk%d.qkv", i);
+        rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
+        Step at; at.kind = ST_ATTN; at.family = FAM_ATTN; at.flops = 4.0 * (double)N * T * T * C; at.tag = pre + ".attn";
+        pl.steps.push_back(at);
+        GemmDesc p2;
+        p2.layer = get_layer(h, pre + ".attn.proj");
+        p2.seg[0] = seg(w.attn, C, C); p2.a_rows = rt; p2.M = (int)rt;
+        p2.resid = w.x; p2.resid_ld = C; p2.resid_map = MAP_SAME;
+        p2.out0 = outspec(w.x, C, OUT_F32, MAP_SAME);
+        p2.flops = 2.0 * rt * C * (double)C;
+        snprintf(tag, sizeof(tag), "blk%d.proj", i);
+        rc = add_gemm_group(h, pl, &p2, 1, tag); if (rc) return rc;
+        Step ln2; ln2.kind = ST_LN; ln2.family = FAM_LN; ln2.ln_gamma = h->vecs[pre + ".norm2.weight"]; ln2.ln_beta = h->vecs[pre + ".norm2.bias"]; ln2.tag = pre + ".norm2";
+        pl.steps.push_back(ln2);
+        GemmDesc f1;
+        f1.layer = get_layer(h, pre + ".mlp.fc1");
+        f1.seg[0] = seg(w.xn, C, C); f1.a_rows = rt; f1.M = (int)rt; f1.act = ACT_GELU;
+        f1.out0 = outspec(w.h1, h->mlp, OUT_BF16, MAP_SAME);
+        f1.flops = 2.0 * rt * C * (double)h->mlp;
+        snprintf(tag, sizeof(tag), "blk%d.fc1", i);
+        rc = add_gemm_group(h, pl, &f1, 1, tag); if (rc) return rc;
+        GemmDesc f2;
+        f2.layer = get_layer(h, pre + ".mlp.fc2");
+        f2.seg[0] = seg(w.h1, h->mlp, h->mlp); f2.a_rows = rt; f2.M = (int)rt;
+        f2.resid = w.x; f2.resid_ld = C; f2.resid_map = MAP_SAME;
+        f2.out0 = outspec(w.x, C, OUT_F32, MAP_SAME);
+        f2.flops = 2.0 * rt * C * (double)h->mlp;
+        snprintf(tag, sizeof(tag), "blk%d.fc2", i);
+        rc = add_gemm_group(h, pl, &f2, 1, tag); if (rc) return rc;
+    }
+    {
+        Step ln; ln.kind = ST_LN; ln.family = FAM_LN; ln.ln_gamma = h->vecs["encoder_norm.weight"]; ln.ln_beta = h->vecs["encoder_norm.bias"]; ln.ln_final = 1; ln.tag = "encoder_norm";
+        pl.steps.push_back(ln);
+    }
+    pl.encoder_end_step = (int)pl.steps.size();
+    {   // g_a: four 1x1 convs == per-token linears (MCM.py:77-93, 735)
+        const __nv_bfloat16* srcs[4] = {w.enc, w.ga1, w.ga2, w.ga3};
+        __nv_bfloat16* dsts[3] = {w.ga1, w.ga2, w.ga3};
+        for (int l = 0; l < 4; ++l) {
+            GemmDesc d;
+            d.layer = get_layer(h, "g_a." + std::to_string(2 * l));
+            d.seg[0] = seg(srcs[l], h->ga_ch[l], h->ga_ch[l]); d.a_rows = rk; d.M = (int)rk;
+            d.in_mode = IN_COMPACT; d.side = s;
+            if (l < 3) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], h->ga_ch[l + 1], OUT_BF16, MAP_SAME); }
+            else { d.out0 = outspec(w.y, Cy, OUT_F32, MAP_SAME); d.out1 = outspec(w.y_pad, Cy, OUT_BF16, MAP_TO_PAD); }
+            d.flops = 2.0 * rk * h->ga_ch[l] * (double)h->ga_ch[l + 1];
+            snprintf(tag, sizeof(tag), "g_a.%d", 2 * l);
+            rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
+        }
+    }
+    pl.first_rate_step = (int)pl.steps.size();
+    {   // h_a (MCM.py:115-129, 739)
+        int ci[5], co[5], st[5];
+        ha_layers(h, ci, co, st);
+        const __nv_bfloat16* srcs[5] = {w.y_pad, w.ha1, w.ha2, w.ha3, w.ha4};
+        __nv_bfloat16* dsts[4] = {w.ha1, w.ha2, w.ha3, w.ha4};
+        const int sides[5] = {s, s, s, h->s2, h->s2};
+        const long long rows[5] = {rp, rp, rp, rp2, rp2};
+        for (int l = 0; l < 5; ++l) {
+            GemmDesc d;
+            d.layer = get_layer(h, "h_a." + std::to_string(2 * l));
+            d.seg[0] = seg(srcs[l], ci[l], ci[l]); d.a_rows = rows[l]; d.M = (int)rows[l];
+            d.in_mode = IN_PADDED; d.side = sides[l];
+            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], co[l], OUT_BF16, st[l] == 2 ? MAP_S2_PAD : MAP_SAME); }
+            else d.out0 = outspec(w.z, Cz, OUT_F32, MAP_S2_COMPACT);
+            const long long outpos = (long long)N * (sides[l] / st[l]) * (sides[l] / st[l]);
+            d.flops = conv_flops(outpos, ci[l], co[l], 9);
+            snprintf(tag, sizeof(tag), "h_a.%d", 2 * l);
+            rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
+        }
+    }
+    simple(ST_EB, FAM_ENTROPY, "entropy_bottleneck");
+    {   // h_s_mean / h_s_scale as a group of two per layer (MCM.py:132-162, 747-748)
+        int ci[5], co[5], up[5];
+        hs_layers(h, ci, co, up);
+        const int sides[5] = {h->s4, h->s4, h->s2, h->s2, s};
+        const long long rows[5] = {rp4, rp4, rp2, rp2, rp};
+        const char* nets[2] = {"h_s_mean", "h_s_scale"};
+        for (int l = 0; l < 5; ++l) {
+            GemmDesc d[2];
+            for (int net = 0; net < 2; ++net) {
+                const __nv_bfloat16* srcs[5] = {w.zhat_pad, w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net]};
+                __nv_bfloat16* dsts[5] = {w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net], w.lat[net]};
+                d[net].layer = get_layer(h, std::string(nets[net]) + "." + std::to_string(2 * l));
+                d[net].seg[0] = seg(srcs[l], ci[l], ci[l]); d[net].a_rows = rows[l]; d[net].M = (int)rows[l];
+                d[net].in_mode = IN_PADDED; d[net].side = sides[l];
+                d[net].act = l < 4 ? ACT_GELU : ACT_NONE;
+                d[net].out0 = outspec(dsts[l], co[l], OUT_BF16, up[l] == 2 ? MAP_SHUF_PAD : MAP_SAME);
+                d[net].flops = conv_flops((long long)N * sides[l] * sides[l], ci[l], co[l] * up[l] * up[l], 9);
+            }
+            snprintf(tag, sizeof(tag), "h_s.%d", 2 * l);
+            rc = add_gemm_group(h, pl, d, 2, tag); if (rc) return rc;
+        }
+    }
+    const bool skip_dead = (h->cfg.flags & TMAE_FLAG_SKIP_DEAD_LRP) != 0;
+    for (int i = 0; i < h->nsl; ++i) {   // slice loop (MCM.py:755-784)
+        const int sup = i < h->nsl / 2 ? i : h->nsl / 2;
+        int ch[6];
+        cc_channels(h, ch, i, false);
+        for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i], grouped
+            GemmDesc d[2];
+            for (int net = 0; net < 2; ++net) {
+                const char* nm = net == 0 ? "cc_transform_mean." : "cc_transform_scale.";
+                d[net].layer = get_layer(h, std::string(nm) + std::to_string(i) + "." + std::to_string(2 * l));
+                if (l == 0) {
+                    d[net].seg[0] = seg(w.lat[net], Cy, Cy);
+                    d[net].nseg = 1;
+                    if (sup > 0) { d[net].seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); d[net].nseg = 2; }
+                } else {
+                    d[net].seg[0] = seg(w.t[net][l - 1], ch[l], ch[l]);
+                }
+                d[net].a_rows = rp; d[net].M = (int)rp; d[net].in_mode = IN_PADDED; d[net].side = s;
+                if (l < 4) { d[net].act = ACT_GELU; d[net].out0 = outspec(w.t[net][l], ch[l + 1], OUT_BF16, MAP_SAME); }
+                else d[net].out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
+                d[net].flops = conv_flops(rk, ch[l], ch[l + 1], 9);
+            }
+            snprintf(tag, sizeof(tag), "cc.%d.%d", i, 2 * l);
+            rc = add_gemm_group(h, pl, d, 2, tag); if (rc) return rc;
+        }
+        { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i; g.tag = "gaussian." + std::to_string(i); pl.steps.push_back(g); }
+        if (skip_dead && i >= h->nsl / 2) continue;
+        int lch[6];
+        cc_channels(h, lch, i, true);
+        for (int l = 0; l < 5; ++l) {    // lrp_transform[i] (MCM.py:780-783)
+            GemmDesc d;
+            d.layer = get_layer(h, "lrp_transform." + std::to_string(i) + "." + std::to_string(2 * l));
+            if (l == 0) {
+                d.seg[0] = seg(w.lat[0], Cy, Cy);
+                if (i < h->nsl / 2) { d.seg[1] = seg(w.yhat_pad, h->sc * (i + 1), Cy); d.nseg = 2; }
+                else { d.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); d.seg[2] = seg(w.yhat_pad + i * h->sc, h->sc, Cy); d.nseg = 3; }
+            } else {
+                d.seg[0] = seg(w.t[2][l - 1], lch[l], lch[l]);
+            }
+            d.a_rows = rp; d.M = (int)rp; d.in_mode = IN_PADDED; d.side = s;
+            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(w.t[2][l], lch[l + 1], OUT_BF16, MAP_SAME); }
+            else {
+                d.act = ACT_HALF_TANH;
+                d.resid = w.yhat + i * h->sc; d.resid_ld = Cy; d.resid_map = MAP_TO_COMPACT;
+                d.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
+                d.out1 = outspec(w.yhat_pad + i * h->sc, Cy, OUT_BF16, MAP_SAME);
+            }
+            d.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
+            snprintf(tag, sizeof(tag), "lrp.%d.%d", i, 2 * l);
+            rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
+        }
+    }
+    simple(ST_RATE, FAM_ENTROPY, "rate_finalize");
+
+    for (const Step& st : pl.steps)
+        if (st.kind == ST_GEMM && pl.host_params[st.param_index].num_segs < 1) return fail(h, TMAE_EINVAL, "bad plan");
+    void* dp = nullptr;
+    CUDA_TRY(h, cudaMalloc(&dp, pl.host_params.size() * sizeof(GemmParams)));
+    pl.d_params = reinterpret_cast<GemmParams*>(dp);
+    CUDA_TRY(h, cudaMemcpy(pl.d_params, pl.host_params.data(), pl.host_params.size() * sizeof(GemmParams), cudaMemcpyHostToDevice));
+    *out = plp.get();
+    h->plans[N] = std::move(plp);
+    return TMAE_OK;
+}
+
+// ---- execution -----------------------------------------------------------------------------------------
+struct RunArgs {
+    const float* imgs = nullptr;
+    const float* scores = nullptr;
+    const tmae_outputs* out = nullptr;
+    int begin = 0, end = 0;
+};
+
+int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e0, e1;
+        CUDA_TRY(h, cudaEventCreate(&e0));
+        CUDA_TRY(h, cudaEventCreate(&e1));
+        h->prof_events.push_back({e0, e1});
+        h->prof_family.push_back(0);
+        h->prof_flops.push_back(0);
+        h->prof_bytes.push_back(0);
+    }
+    *a = h->prof_events[h->prof_used].first;
+    *b = h->prof_events[h->prof_used].second;
+    h->prof_family[h->prof_used] = st.family;
+    h->prof_flops[h->prof_used] = st.flops;
+    h->prof_bytes[h->prof_used] = st.bytes;
+    ++h->prof_used;
+    return TMAE_OK;
+}
+
+int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
+    Workspace& w = h->ws;
+    const int N = pl.N, C = h->C, T = h->T, K = h->K, s = h->s;
+    static const tmae_outputs kNoOut = {};
+    const tmae_outputs& o = a.out ? *a.out : kNoOut;
+    const bool simt = (h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) != 0;
+    for (int si = a.begin; si < a.end; ++si) {
+        const Step& sp = pl.steps[si];
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (h->profiling) {
+            int rc = prof_slot(h, sp, &e0, &e1);
+            if (rc) return rc;
+            CUDA_TRY(h, cudaEventRecord(e0, st));
+        }
+        switch (sp.kind) {
+            case ST_ZERO_RATE:
+                CUDA_TRY(h, cudaMemsetAsync(w.rate_acc, 0, sizeof(double) * N, st));
+                break;
+            case ST_MASK:
+                CUDA_TRY(h, launch_mask_select(a.scores, N, h->L, K, h->cfg.softmax_isa == 8 ? 8 : 16, o.ids_shuffle,
+                                               o.ids_restore, w.ids_keep, st));
+                break;
+            case ST_GATHER:
+                CUDA_TRY(h, launch_gather_patches(a.imgs, w.ids_keep, w.patches, w.x, h->vecs["cls_token"],
+                                                  h->vecs["encoder_pos_embed"], N, h->cfg.img_size, h->grid_w, K, T, C,
+                                                  h->cfg.in_chans, h->cfg.patch_size, st));
+                break;
+            case ST_GEMM:
+                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, simt, st));
+                break;
+            case ST_LN:
+                if (sp.ln_final)
+                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.enc, o.x_remain, N * T, C, T, 1, h->cfg.ln_eps, st));
+                else
+                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.xn, nullptr, N * T, C, T, 0, h->cfg.ln_eps, st));
+                break;
+            case ST_ATTN:
+                CUDA_TRY(h, launch_attention(w.qkv, w.attn, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                break;
+            case ST_EB:
+                CUDA_TRY(h, launch_bottleneck(w.z, h->eb_tab, (long long)N * h->s4 * h->s4, h->Cz, o.z_likelihoods,
+                                              o.z_symbols, o.z_hat, w.zhat_pad, h->s4, w.rate_acc, h->s4 * h->s4, st));
+                break;
+            case ST_GC:
+                CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc,
+                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_pad, h->Cy, s, w.rate_acc, st));
+                break;
+            case ST_RATE:
+                CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
+                                                 o.bpp ? o.bpp : w.bpp, o.rate_sums ? o.rate_sums : w.rate_sums, st));
+                break;
+            case ST_Y_TO_PAD:
+                break;
+        }
+        if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, st));
+    }
+    return TMAE_OK;
+}
+
+int copy_outputs(tmae_handle* h, int N, const tmae_outputs* out, bool rate_half, bool encoder_half, cudaStream_t st) {
+    if (!out) return TMAE_OK;
+    Workspace& w = h->ws;
+    const size_t rk = (size_t)N * h->K;
+    if (encoder_half && out->ids_keep)
+        CUDA_TRY(h, cudaMemcpyAsync(out->ids_keep, w.ids_keep, rk * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (rate_half) {
+        if (out->y) CUDA_TRY(h, cudaMemcpyAsync(out->y, w.y, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
+        if (out->z) CUDA_TRY(h, cudaMemcpyAsync(out->z, w.z, (size_t)N * h->s4 * h->s4 * h->Cz * 4, cudaMemcpyDeviceToDevice, st));
+        if (out->mu) CUDA_TRY(h, cudaMemcpyAsync(out->mu, w.mu, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
+        if (out->sigma) CUDA_TRY(h, cudaMemcpyAsync(out->sigma, w.sigma, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
+        if (out->y_hat) CUDA_TRY(h, cudaMemcpyAsync(out->y_hat, w.yhat, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return TMAE_OK;
+}
+
+int check_ready(tmae_handle* h, int N) {
+    if (!h) return TMAE_EINVAL;
+    if (!h->finalized) return fail(h, TMAE_ESTATE, "weights not finalized (call tmae_finalize_weights)");
+    if (N <= 0) return fail(h, TMAE_EINVAL, "batch size must be positive");
+    return TMAE_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+int tmae_abi_version(void) { return TMAE_ABI_VERSION; }
+
+const char* tmae_last_error(const tmae_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tmae_create(const tmae_config* cfg, tmae_handle** out) {
+    if (!cfg || !out) return fail(nullptr, TMAE_EINVAL, "null argument");
+    *out = nullptr;
+    std::unique_ptr<tmae_handle> h(new tmae_handle());
+    h->cfg = *cfg;
+    if (h->cfg.ln_eps <= 0.f) h->cfg.ln_eps = 1e-6f;
+    if (h->cfg.mlp_ratio <= 0.f) h->cfg.mlp_ratio = 4.0f;
+    int rc = derive_geometry(h.get());
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TMAE_ECUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    e = cudaGetDevice(&h->dev);
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, h->dev);
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, TMAE_ECUDA, "device '%s' is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(nullptr, TMAE_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    e = gemm_tc_configure();
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gemm configure: %s", cudaGetErrorString(e));
+    e = attention_configure(h->T);
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
+    *out = h.release();
+    return TMAE_OK;
+}
+
+void tmae_destroy(tmae_handle* h) {
+    if (!h) return;
+    cudaDeviceSynchronize();
+    for (auto& kv : h->raw) cudaFree(kv.second.ptr);
+    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    free_pool(h->ws.allocs);
+    free_pool(h->weight_allocs);
+    for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    delete h;
+}
+
+int tmae_set_weight(tmae_handle* h, const char* name, const void* data, int dtype, int ndim, const int64_t* shape,
+                    int* ignored) {
+    if (!h || !name || !data || ndim < 0 || (ndim > 0 && !shape)) return fail(h, TMAE_EINVAL, "null/invalid argument");
+    if (ignored) *ignored = 0;
+    const std::string n(name);
+    if (!name_is_needed(h, n)) { if (ignored) *ignored = 1; return TMAE_OK; }
+    if (dtype != TMAE_F32) return fail(h, TMAE_EINVAL, "weight '%s': only f32 weights are accepted", name);
+    RawTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= (size_t)shape[i]; }
+    void* p = nullptr;
+    CUDA_TRY(h, cudaMalloc(&p, t.numel * sizeof(float) + 16));
+    t.ptr = reinterpret_cast<float*>(p);
+    cudaError_t e = cudaMemcpy(t.ptr, data, t.numel * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) { cudaFree(p); return fail(h, TMAE_ECUDA, "copy of weight '%s' failed: %s", name, cudaGetErrorString(e)); }
+    auto it = h->raw.find(n);
+    if (it != h->raw.end()) cudaFree(it->second.ptr);
+    h->raw[n] = t;
+    h->finalized = false;
+    return TMAE_OK;
+}
+
+int tmae_finalize_weights(tmae_handle* h) {
+    if (!h) return TMAE_EINVAL;
+    // re-finalize: drop previous packs
+    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    h->plans.clear();
+    free_pool(h->weight_allocs);
+    h->layers.clear();
+    h->vecs.clear();
+    h->eb_tab = nullptr;
+    const int C = h->C, one[1] = {0};
+    (void)one;
+    int rc;
+    if ((rc = keep_vec(h, "cls_token", C))) return rc;
+    if ((rc = keep_vec(h, "encoder_pos_embed", (size_t)(h->L + 1) * C))) return rc;
+    { int sg[1] = {h->patch_dim}; if ((rc = pack_layer(h, "encoder_embed.proj", "encoder_embed.proj", C, h->patch_dim, 1, 1, sg, 0))) return rc; }
+    for (int i = 0; i < h->cfg.encoder_depth; ++i) {
+        const std::string pre = "encoder_blocks." + std::to_string(i);
+        for (const char* nm : {".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"})
+            if ((rc = keep_vec(h, pre + nm, C))) return rc;
+        int sgC[1] = {C}, sgM[1] = {h->mlp};
+        if ((rc = pack_layer(h, pre + ".attn.qkv", pre + ".attn.qkv", 3 * C, C, 1, 1, sgC, 0))) return rc;
+        if ((rc = pack_layer(h, pre + ".attn.proj", pre + ".attn.proj", C, C, 1, 1, sgC, 0))) return rc;
+        if ((rc = pack_layer(h, pre + ".mlp.fc1", pre + ".mlp.fc1", h->mlp, C, 1, 1, sgC, 0))) return rc;
+        if ((rc = pack_layer(h, pre + ".mlp.fc2", pre + ".mlp.fc2", C, h->mlp, 1, 1, sgM, 0))) return rc;
+    }
+    if ((rc = keep_vec(h, "encoder_norm.weight", C))) return rc;
+    if ((rc = keep_vec(h, "encoder_norm.bias", C))) return rc;
+    for (int l = 0; l < 4; ++l) {
+        int sg[1] = {h->ga_ch[l]};
+        const std::string nm = "g_a." + std::to_string(2 * l);
+        if ((rc = pack_layer(h, nm, nm, h->ga_ch[l + 1], h->ga_ch[l], 1, 1, sg, 0))) return rc;
+    }
+    {
+        int ci[5], co[5], aux[5];
+        ha_layers(h, ci, co, aux);
+        for (int l = 0; l < 5; ++l) {
+            int sg[1] = {ci[l]};
+            const std::string nm = "h_a." + std::to_string(2 * l);
+            if ((rc = pack_layer(h, nm, nm, co[l], ci[l], 9, 1, sg, 0))) return rc;
+        }
+        hs_layers(h, ci, co, aux);
+        for (const char* net : {"h_s_mean", "h_s_scale"})
+            for (int l = 0; l < 5; ++l) {
+                int sg[1] = {ci[l]};
+                const std::string key = std::string(net) + "." + std::to_string(2 * l);
+                const std::string wname = aux[l] == 2 ? key + ".0" : key;      // subpel = Sequential(conv, PixelShuffle)
+                if ((rc = pack_layer(h, key, wname, co[l] * aux[l] * aux[l], ci[l], 9, 1, sg, aux[l] == 2))) return rc;
+            }
+    }
+    for (int i = 0; i < h->nsl; ++i) {
+        const int sup = i < h->nsl / 2 ? i : h->nsl / 2;
+        int ch[6];
+        cc_channels(h, ch, i, false);
+        for (const char* net : {"cc_transform_mean.", "cc_transform_scale."})
+            for (int l = 0; l < 5; ++l) {
+                const std::string nm = std::string(net) + std::to_string(i) + "." + std::to_string(2 * l);
+                int sg[3] = {ch[l], 0, 0};
+                int nseg = 1;
+                if (l == 0 && sup > 0) { sg[0] = h->Cy; sg[1] = h->sc * sup; nseg = 2; }
+                if ((rc = pack_layer(h, nm, nm, ch[l + 1], ch[l], 9, nseg, sg, 0))) return rc;
+            }
+        int lch[6];
+        cc_channels(h, lch, i, true);
+        for (int l = 0; l < 5; ++l) {
+            const std::string nm = "lrp_transform." + std::to_string(i) + "." + std::to_string(2 * l);
+            int sg[3] = {lch[l], 0, 0};
+            int nseg = 1;
+            if (l == 0) {
+                sg[0] = h->Cy;
+                if (i < h->nsl / 2) { sg[1] = h->sc * (i + 1); nseg = 2; }
+                else { sg[1] = h->sc * sup; sg[2] = h->sc; nseg = 3; }
+            }
+            if ((rc = pack_layer(h, nm, nm, lch[l + 1], lch[l], 9, nseg, sg, 0))) return rc;
+        }
+    }
+    {   // factorized prior table
+        const int Cz = h->Cz;
+        const size_t sizes[15] = {3, 3, 3, 9, 3, 3, 9, 3, 3, 9, 3, 3, 3, 1, 3};
+        const char* names[15] = {"_matrix0", "_bias0", "_factor0", "_matrix1", "_bias1", "_factor1", "_matrix2", "_bias2",
+                                 "_factor2", "_matrix3", "_bias3", "_factor3", "_matrix4", "_bias4", "quantiles"};
+        const float* ptrs[15];
+        for (int i = 0; i < 15; ++i) {
+            const RawTensor* r = nullptr;
+            if ((rc = need_raw(h, std::string("entropy_bottleneck.") + names[i], sizes[i] * Cz, &r))) return rc;
+            ptrs[i] = r->ptr;
+        }
+        if ((rc = dev_alloc(h, h->weight_allocs, &h->eb_tab, (size_t)Cz * 64))) return rc;
+        CUDA_TRY(h, launch_eb_table(ptrs, h->eb_tab, Cz, 0));
+    }
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (auto& kv : h->raw) cudaFree(kv.second.ptr);
+    h->raw.clear();
+    h->finalized = true;
+    return TMAE_OK;
+}
+
+size_t tmae_workspace_bytes(const tmae_handle* h, int N) { return h && N > 0 ? workspace_bytes_estimate(h, N) : 0; }
+
+int tmae_reserve(tmae_handle* h, int N) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    Plan* pl = nullptr;
+    return build_plan(h, N, &pl);
+}
+
+int tmae_launch_count(tmae_handle* h, int N) {
+    Plan* pl = nullptr;
+    if (check_ready(h, N) || build_plan(h, N, &pl)) return -1;
+    return (int)pl->steps.size();
+}
+
+int tmae_forward(tmae_handle* h, const float* imgs, const float* scores, int N, const tmae_outputs* out, void* stream) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    if (!imgs || !scores) return fail(h, TMAE_EINVAL, "imgs / scores must not be null");
+    Plan* pl = nullptr;
+    if ((rc = build_plan(h, N, &pl))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RunArgs a;
+    a.imgs = imgs; a.scores = scores; a.out = out; a.begin = 0; a.end = (int)pl->steps.size();
+    if (h->profiling) h->prof_used = 0;
+    if ((rc = run_steps(h, *pl, a, st))) return rc;
+    return copy_outputs(h, N, out, true, true, st);
+}
+
+int tmae_forward_encoder(tmae_handle* h, const float* imgs, const float* scores, int N, const tmae_outputs* out,
+                         void* stream) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    if (!imgs || !scores) return fail(h, TMAE_EINVAL, "imgs / scores must not be null");
+    Plan* pl = nullptr;
+    if ((rc = build_plan(h, N, &pl))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    RunArgs a;
+    a.imgs = imgs; a.scores = scores; a.out = out; a.begin = 0; a.end = pl->encoder_end_step;
+    if (h->profiling) h->prof_used = 0;
+    if ((rc = run_steps(h, *pl, a, st))) return rc;
+    return copy_outputs(h, N, out, false, true, st);
+}
+
+int tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_outputs* out, void* stream) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    if (!y) return fail(h, TMAE_EINVAL, "y must not be null");
+    Plan* pl = nullptr;
+    if ((rc = build_plan(h, N, &pl))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace& w = h->ws;
+    const size_t rk = (size_t)N * h->K;
+    CUDA_TRY(h, cudaMemsetAsync(w.rate_acc, 0, sizeof(double) * N, st));
+    CUDA_TRY(h, cudaMemcpyAsync(w.y, y, rk * h->Cy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, launch_compact_to_pad(w.y, w.y_pad, (long long)rk, h->Cy, h->s, st));
+    RunArgs a;
+    a.out = out; a.begin = pl->first_rate_step; a.end = (int)pl->steps.size();
+    if (h->profiling) h->prof_used = 0;
+    if ((rc = run_steps(h, *pl, a, st))) return rc;
+    return copy_outputs(h, N, out, true, false, st);
+}
+
+int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores, int N, float* h_bpp,
+                      double* h_rate_sums, const tmae_outputs* out, void* stream) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    if (!h_imgs || !h_scores) return fail(h, TMAE_EINVAL, "h_imgs / h_scores must not be null");
+    Plan* pl = nullptr;
+    if ((rc = build_plan(h, N, &pl))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace& w = h->ws;
+    const size_t img_elems = (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size;
+    CUDA_TRY(h, cudaMemcpyAsync(w.st_imgs, h_imgs, img_elems * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(w.st_scores, h_scores, (size_t)N * h->L * sizeof(float), cudaMemcpyHostToDevice, st));
+    tmae_outputs o = out ? *out : tmae_outputs{};
+    if (!o.bpp) o.bpp = w.bpp;
+    if (!o.rate_sums) o.rate_sums = w.rate_sums;
+    RunArgs a;
+    a.imgs = w.st_imgs; a.scores = w.st_scores; a.out = &o; a.begin = 0; a.end = (int)pl->steps.size();
+    if (h->profiling) h->prof_used = 0;
+    if ((rc = run_steps(h, *pl, a, st))) return rc;
+    if ((rc = copy_outputs(h, N, out, true, true, st))) return rc;
+    if (h_bpp) CUDA_TRY(h, cudaMemcpyAsync(h_bpp, o.bpp, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (h_rate_sums) CUDA_TRY(h, cudaMemcpyAsync(h_rate_sums, o.rate_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return TMAE_OK;
+}
+
+// ---- stand-alone operators -----------------------------------------------------------------------------
+int tmae_mask_select(const float* scores, int N, int L, int K, int softmax_isa, int64_t* ids_shuffle,
+                     int64_t* ids_restore, int64_t* ids_keep, void* stream) {
+    if (!scores || N < 0 || L <= 0) return fail(nullptr, TMAE_EINVAL, "invalid argument");
+    if (K > L) return fail(nullptr, TMAE_EINVAL, "Number of patches should not be greater than the length of scores");
+    cudaError_t e = launch_mask_select(scores, N, L, K, softmax_isa, ids_shuffle, ids_restore, ids_keep,
+                                       reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "mask_select: %s", cudaGetErrorString(e));
+    return TMAE_OK;
+}
+
+int tmae_gaussian_rate(const float* y, const float* mu, const float* sigma, int64_t n, float* likelihood,
+                       int32_t* symbols, float* y_hat, void* stream) {
+    if (!y || !mu || !sigma || n < 0) return fail(nullptr, TMAE_EINVAL, "invalid argument");
+    cudaError_t e = launch_gaussian_flat(y, mu, sigma, n, likelihood, symbols, y_hat, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gaussian_rate: %s", cudaGetErrorString(e));
+    return TMAE_OK;
+}
+
+int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* likelihood, int32_t* symbols, float* z_hat,
+                         void* stream) {
+    if (!h || !h->finalized) return fail(h, TMAE_ESTATE, "weights not finalized");
+    if (!z || rows < 0) return fail(h, TMAE_EINVAL, "invalid argument");
+    CUDA_TRY(h, launch_bottleneck(z, h->eb_tab, rows, h->Cz, likelihood, symbols, z_hat, nullptr, 1, nullptr, 1,
+                                  reinterpret_cast<cudaStream_t>(stream)));
+    return TMAE_OK;
+}
+
+// ---- engine self-tests ---------------------------------------------------------------------------------
+static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int impl, cudaStream_t st) {
+    GemmParams p;
+    int rc = fill_params(tmp, d, 1, &p, block_n);
+    if (rc) return rc;
+    GemmParams* dp = nullptr;
+    if (cudaMalloc(reinterpret_cast<void**>(&dp), sizeof(GemmParams)) != cudaSuccess) return fail(tmp, TMAE_ENOMEM, "cudaMalloc params");
+    cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, impl == 1, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(dp);
+    if (e != cudaSuccess || e2 != cudaSuccess)
+        return fail(tmp, TMAE_ECUDA, "engine launch: %s / %s", cudaGetErrorString(e), cudaGetErrorString(e2));
+    return TMAE_OK;
+}
+
+static int make_tmp_handle(std::unique_ptr<tmae_handle>& tmp) {
+    tmp.reset(new tmae_handle());
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return fail(nullptr, TMAE_ECUDA, "cuTensorMapEncodeTiled unavailable");
+    tmp->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    e = gemm_tc_configure();
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gemm configure: %s", cudaGetErrorString(e));
+    return TMAE_OK;
+}
+
+int tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* Cmat, int M, int N, int K, int block_n,
+                   int impl, void* stream) {
+    if (!A || !B || !Cmat || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "tmae_gemm_bf16: invalid shape (need K %% 8 == 0, N %% 8 == 0)");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // pack B [N, K] bf16 into [N, pad64(K)] (zero padded) and a zero bias if none
+    const int Kp = pad64(K);
+    __nv_bfloat16* wp = nullptr;
+    float* bz = nullptr;
+    std::vector<void*> pool;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    cudaMemcpy2DAsync(wp, (size_t)Kp * 2, B, (size_t)K * 2, (size_t)K * 2, N, cudaMemcpyDeviceToDevice, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.Kp = Kp;
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(A), K, K);
+    d.a_rows = M; d.M = M;
+    d.out0 = outspec(Cmat, N, OUT_F32, MAP_SAME);
+    rc = engine_common(tmp.get(), d, block_n, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float* out, int N, int s, int Cin, int Cout,
+                      int gelu, int impl, void* stream) {
+    if (!x || !wgt || !out || N <= 0 || s <= 0 || Cin % 8 != 0 || Cout % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_bf16: invalid shape");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int P = (s + 1) * (s + 1), Kp = pad64(Cin) * 9;
+    std::vector<void*> pool;
+    __nv_bfloat16 *wp = nullptr, *xpad = nullptr;
+    float *bz = nullptr, *xf = nullptr;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout)) ||
+        (rc = dev_alloc(tmp.get(), pool, &xpad, (size_t)N * P * Cin))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    (void)xf;
+    int sg[1] = {Cin};
+    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st);
+    // x bf16 compact NHWC -> haloed layout: one strided 2-D copy per image (s rows of s*Cin elements)
+    for (int n = 0; n < N && e == cudaSuccess; ++n)
+        e = cudaMemcpy2DAsync(xpad + (size_t)n * P * Cin, (size_t)(s + 1) * Cin * 2,
+                              reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)n * s * s * Cin, (size_t)s * Cin * 2,
+                              (size_t)s * Cin * 2, s, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "conv3x3 staging: %s", cudaGetErrorString(e)); }
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.Kp = Kp;
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(xpad, Cin, Cin);
+    d.a_rows = (long long)N * P; d.M = N * P; d.in_mode = IN_PADDED; d.side = s;
+    d.act = gelu ? ACT_GELU : ACT_NONE;
+    d.out0 = outspec(out, Cout, OUT_F32, MAP_TO_COMPACT);
+    rc = engine_common(tmp.get(), d, 0, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+// ---- profiling -----------------------------------------------------------------------------------------
+int tmae_profile_enable(tmae_handle* h, int enable) {
+    if (!h) return TMAE_EINVAL;
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    return TMAE_OK;
+}
+
+int tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entries, int* n_entries) {
+    if (!h || !entries || !n_entries) return TMAE_EINVAL;
+    tmae_profile_entry fam[FAM_COUNT];
+    memset(fam, 0, sizeof(fam));
+    for (int f = 0; f < FAM_COUNT; ++f) snprintf(fam[f].name, sizeof(fam[f].name), "%s", kFamilyNames[f]);
+    for (size_t i = 0; i < h->prof_used; ++i) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second);
+        if (e != cudaSuccess) return fail(h, TMAE_ECUDA, "cudaEventElapsedTime: %s (synchronise the stream first)", cudaGetErrorString(e));
+        tmae_profile_entry& f = fam[h->prof_family[i]];
+        f.launches += 1;
+        f.ms += ms;
+        f.flops += h->prof_flops[i];
+        f.bytes += h->prof_bytes[i];
+    }
+    int n = 0;
+    for (int f = 0; f < FAM_COUNT && n < max_entries; ++f)
+        if (fam[f].launches > 0) entries[n++] = fam[f];
+    *n_entries = n;
+    return TMAE_OK;
+}
+
+}  // extern "C"
