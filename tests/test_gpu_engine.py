@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 256, 128), (300, 224, 384, 0), (1000, 2304, 768, 256),
                                        (4160, 768, 3072, 0), (257, 80, 176, 0), (130, 32, 80, 32), (512, 704, 768, 192)])
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
 def test_gemm_matches_torch(cuda_dev, M, N, K, bn, impl):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev).bfloat16()
@@ -25,7 +25,7 @@ def test_gemm_matches_torch(cuda_dev, M, N, K, bn, impl):
 
 @pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (2, 4, 192, 240, True),
                                                   (5, 8, 80, 32, False), (1, 16, 576, 224, True)])
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
 def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin)
     x = torch.randn(N, s, s, Cin, generator=g).to(cuda_dev).bfloat16()
