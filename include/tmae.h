@@ -156,6 +156,15 @@ typedef struct {
 } tmae_profile_entry;
 TMAE_API int  tmae_profile_enable(tmae_handle* h, int enable);
 TMAE_API int  tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entries, int* n_entries);
+/* Per-launch view of the same events (one entry per plan step, in launch order). */
+typedef struct {
+    char   name[64];     /* layer tag, e.g. "cc.3.0" */
+    float  ms;
+    double flops;
+    int32_t ctas;        /* CTAs launched (GEMM steps), else 0 */
+    int32_t block_n;     /* N tile (GEMM steps), else 0 */
+} tmae_profile_step;
+TMAE_API int  tmae_profile_read_steps(tmae_handle* h, tmae_profile_step* steps, int max_steps, int* n_steps);
 /* Number of kernels tmae_forward launches for batch N (after planning). */
 TMAE_API int  tmae_launch_count(tmae_handle* h, int N);
 

@@ -25,7 +25,8 @@ def test_gaussian_rate_operator(cuda_dev):
     out_ref, lik_ref = ref_model.gaussian_conditional_eval(y, sigma, mu)
     sym_ref = torch.round(y - mu).to(torch.int32)
     lik = torch.empty(n, device=cuda_dev); sym = torch.empty(n, dtype=torch.int32, device=cuda_dev); yh = torch.empty(n, device=cuda_dev)
-    rc = _native.load().tmae_gaussian_rate(G.ptr(y.to(cuda_dev)), G.ptr(mu.to(cuda_dev)), G.ptr(sigma.to(cuda_dev)), n,
+    yd, md, sd_ = y.to(cuda_dev), mu.to(cuda_dev), sigma.to(cuda_dev)        # keep the device copies alive
+    rc = _native.load().tmae_gaussian_rate(G.ptr(yd), G.ptr(md), G.ptr(sd_), n,
                                            G.ptr(lik), G.ptr(sym), G.ptr(yh), G.stream())
     _native.check(rc)
     torch.cuda.synchronize()

@@ -38,6 +38,11 @@ class TmaeProfileEntry(C.Structure):
                 ("bytes", C.c_double)]
 
 
+class TmaeProfileStep(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("ms", C.c_float), ("flops", C.c_double), ("ctas", C.c_int32),
+                ("block_n", C.c_int32)]
+
+
 # every symbol include/tmae.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -60,6 +65,7 @@ SIGNATURES = {
     "tmae_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_profile_enable": (C.c_int, [_P, C.c_int]),
     "tmae_profile_read": (C.c_int, [_P, C.POINTER(TmaeProfileEntry), C.c_int, C.POINTER(C.c_int)]),
+    "tmae_profile_read_steps": (C.c_int, [_P, C.POINTER(TmaeProfileStep), C.c_int, C.POINTER(C.c_int)]),
     "tmae_launch_count": (C.c_int, [_P, C.c_int]),
 }
 

@@ -114,6 +114,8 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
         case 6: layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         case 8: layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         case 10: layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 1: layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 2: layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         case 3: layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         case 4: layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         default: return cudaErrorInvalidValue;

@@ -115,6 +115,8 @@ struct tmae_handle {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     std::vector<int> prof_family;
     std::vector<double> prof_flops, prof_bytes;
+    std::vector<std::string> prof_tag;
+    std::vector<int> prof_ctas, prof_bn;
     size_t prof_used = 0;
     int dev = 0;
 };
@@ -722,12 +724,18 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
         h->prof_family.push_back(0);
         h->prof_flops.push_back(0);
         h->prof_bytes.push_back(0);
+        h->prof_tag.push_back("");
+        h->prof_ctas.push_back(0);
+        h->prof_bn.push_back(0);
     }
     *a = h->prof_events[h->prof_used].first;
     *b = h->prof_events[h->prof_used].second;
     h->prof_family[h->prof_used] = st.family;
     h->prof_flops[h->prof_used] = st.flops;
     h->prof_bytes[h->prof_used] = st.bytes;
+    h->prof_tag[h->prof_used] = st.tag;
+    h->prof_ctas[h->prof_used] = st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
+    h->prof_bn[h->prof_used] = st.kind == ST_GEMM ? st.block_n : 0;
     ++h->prof_used;
     return TMAE_OK;
 }
@@ -1231,6 +1239,24 @@ int tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entri
     for (int f = 0; f < FAM_COUNT && n < max_entries; ++f)
         if (fam[f].launches > 0) entries[n++] = fam[f];
     *n_entries = n;
+    return TMAE_OK;
+}
+
+int tmae_profile_read_steps(tmae_handle* h, tmae_profile_step* steps, int max_steps, int* n_steps) {
+    if (!h || !steps || !n_steps) return TMAE_EINVAL;
+    int n = 0;
+    for (size_t i = 0; i < h->prof_used && n < max_steps; ++i, ++n) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second);
+        if (e != cudaSuccess) return fail(h, TMAE_ECUDA, "cudaEventElapsedTime: %s (synchronise the stream first)", cudaGetErrorString(e));
+        memset(&steps[n], 0, sizeof(steps[n]));
+        snprintf(steps[n].name, sizeof(steps[n].name), "%s", h->prof_tag[i].c_str());
+        steps[n].ms = ms;
+        steps[n].flops = h->prof_flops[i];
+        steps[n].ctas = h->prof_ctas[i];
+        steps[n].block_n = h->prof_bn[i];
+    }
+    *n_steps = n;
     return TMAE_OK;
 }
 

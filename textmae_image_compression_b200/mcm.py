@@ -337,6 +337,13 @@ class MCM(nn.Module):
         return [{"name": arr[i].name.decode(), "launches": arr[i].launches, "ms": arr[i].ms, "flops": arr[i].flops,
                  "bytes": arr[i].bytes} for i in range(n.value)]
 
+    def profile_read_steps(self):
+        arr = (_native.TmaeProfileStep * 512)()
+        n = C.c_int(0)
+        _native.check(_native.load().tmae_profile_read_steps(self._handle, arr, 512, C.byref(n)), self._handle, RuntimeError)
+        return [{"name": arr[i].name.decode(), "ms": arr[i].ms, "flops": arr[i].flops, "ctas": arr[i].ctas,
+                 "block_n": arr[i].block_n} for i in range(n.value)]
+
     def launch_count(self, N: int) -> int:
         self._ensure_handle()
         return int(_native.load().tmae_launch_count(self._handle, N))
