@@ -19,11 +19,30 @@ namespace tmae {
 // ---------------------------------------------------------------------------------------------------------
 // epilogue shared by the tensor-core kernel and the CUDA-core checker
 // ---------------------------------------------------------------------------------------------------------
+// Register-resident copy of the epilogue description (the parameter block lives in global memory; the inline-asm
+// "memory" clobbers of the tcgen05 wrappers would otherwise force every field to be re-read per use).
+struct EpiCtx {
+    const float* bias;
+    const float* resid;
+    const int64_t* gather_ids;
+    OutSpec out[2];
+    int act, resid_ld, resid_map, M, N, in_mode, s, P, K, T;
+};
+
+__device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
+    EpiCtx e;
+    e.bias = p.bias; e.resid = p.resid; e.gather_ids = p.gather_ids;
+    e.out[0] = p.out[0]; e.out[1] = p.out[1];
+    e.act = p.act; e.resid_ld = p.resid_ld; e.resid_map = p.resid_map;
+    e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.P = p.P; e.K = p.K; e.T = p.T;
+    return e;
+}
+
 struct RowCtx {
     int valid, n, y, x, lin;
 };
 
-__device__ __forceinline__ RowCtx decode_row(const GemmParams& p, int m) {
+__device__ __forceinline__ RowCtx decode_row(const EpiCtx& p, int m) {
     RowCtx r;
     r.lin = m;
     r.valid = m < p.M;
@@ -45,7 +64,8 @@ __device__ __forceinline__ RowCtx decode_row(const GemmParams& p, int m) {
 }
 
 // q = PixelShuffle quadrant (dy*2+dx) of the column group; returns -1 when this row produces no output.
-__device__ __forceinline__ long long map_row(const GemmParams& p, int map, const RowCtx& r, int q) {
+__device__ __forceinline__ long long map_row(const EpiCtx& p, int map, const RowCtx& r, int q) {
+    if (!r.valid) return -1;
     switch (map) {
         case MAP_SAME: return r.lin;
         case MAP_TO_PAD: return (long long)r.n * p.P + r.y * (p.s + 1) + r.x;
@@ -70,52 +90,66 @@ __device__ __forceinline__ long long map_row(const GemmParams& p, int map, const
     return -1;
 }
 
-// Finish 8 consecutive output channels [col, col+8) of one accumulator row.
-__device__ __forceinline__ void epilogue8(const GemmParams& p, const RowCtx& r, int col, float (&v)[8]) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    if (p.act == ACT_GELU) {
+__device__ __forceinline__ float apply_act(float v, int act) {
+    if (act == ACT_GELU) return gelu_erf(v);
+    if (act == ACT_HALF_TANH) return 0.5f * tanhf(v);
+    return v;
+}
+
+// Residual add + stores for `NV` (4 or 8) consecutive output channels of one row, rows already mapped.
+template <int NV>
+__device__ __forceinline__ void finish_store(const EpiCtx& p, float (&v)[NV], int ocol, long long rrow, long long orow0,
+                                             long long orow1) {
+    if (p.resid != nullptr && rrow >= 0) {
+        const float* src = p.resid + rrow * p.resid_ld + ocol;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-    } else if (p.act == ACT_HALF_TANH) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.5f * tanhf(v[i]);
-    }
-    // PixelShuffle bookkeeping: weights are packed quadrant-major, so 8 consecutive columns share (dy,dx).
-    int q = 0, ocol = col;
-    const bool shuf = (p.out[0].map == MAP_SHUF_PAD) || (p.out[1].map == MAP_SHUF_PAD);
-    if (shuf) {
-        const int cq = p.N >> 2;
-        q = col / cq;
-        ocol = col - q * cq;
-    }
-    if (p.resid != nullptr) {
-        const long long rr = map_row(p, p.resid_map, r, q);
-        const float* src = p.resid + rr * p.resid_ld + ocol;
-        const float4 r0 = *reinterpret_cast<const float4*>(src);
-        const float4 r1 = *reinterpret_cast<const float4*>(src + 4);
-        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-        v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        for (int i = 0; i < NV; i += 4) {
+            const float4 r4 = *reinterpret_cast<const float4*>(src + i);
+            v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+        }
     }
 #pragma unroll
     for (int o = 0; o < 2; ++o) {
         const OutSpec& os = p.out[o];
-        if (os.dtype == OUT_NONE) continue;
-        const long long orow = map_row(p, os.map, r, q);
-        if (orow < 0) continue;
+        const long long orow = o == 0 ? orow0 : orow1;
+        if (os.dtype == OUT_NONE || orow < 0) continue;
         if (os.dtype == OUT_BF16) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(os.ptr) + orow * os.ld + ocol) = pk;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(os.ptr) + orow * os.ld + ocol;
+            if (NV == 8) {
+                uint4 pk;
+                pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                pk.z = pack_bf16x2(v[NV - 4], v[NV - 3]); pk.w = pack_bf16x2(v[NV - 2], v[NV - 1]);
+                *reinterpret_cast<uint4*>(dst) = pk;
+            } else {
+                uint2 pk;
+                pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            }
         } else {
             float* dst = reinterpret_cast<float*>(os.ptr) + orow * os.ld + ocol;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
     }
+}
+
+// Row-per-thread variant (CUDA-core checker): finish 8 consecutive output channels [col, col+8) of one row.
+__device__ __forceinline__ void epilogue8(const EpiCtx& p, const RowCtx& r, int col, float (&v)[8]) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
+    // PixelShuffle bookkeeping: weights are packed quadrant-major, so consecutive columns share (dy,dx).
+    int q = 0, ocol = col;
+    if (p.out[0].map == MAP_SHUF_PAD || p.out[1].map == MAP_SHUF_PAD) {
+        const int cq = p.N >> 2;
+        q = col / cq;
+        ocol = col - q * cq;
+    }
+    const long long rrow = p.resid ? map_row(p, p.resid_map, r, q) : -1;
+    finish_store<8>(p, v, ocol, rrow, map_row(p, p.out[0].map, r, q), map_row(p, p.out[1].map, r, q));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -220,9 +254,19 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         __syncwarp();
     } else {
         // ===== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====
+        // Phase 1 (thread = accumulator row): TMEM -> registers, + bias, activation, -> smem staging tile.
+        // Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): residual add and
+        // coalesced 64 / 128-byte row segments to global memory.  The staging tile reuses the (now idle)
+        // pipeline buffers: accum_bar completes only after every MMA has finished reading them.
+        const EpiCtx e = load_epi(p);
         const int quarter = warp & 3;
         const int m = m0 + quarter * 32 + lane;
-        const RowCtx r = decode_row(p, m);
+        const RowCtx r = decode_row(e, m);
+        const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
+        const int cq = e.N >> 2;
+        constexpr int kPitch = 36;                                    // floats per staged row (32 + 4 pad)
+        float* stage_tile = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * kPitch;
+        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -237,18 +281,41 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
                 for (int i = 0; i < 16; ++i) { acc[i] = a16[i]; acc[16 + i] = 0u; }
             }
             tmem_ld_wait();
-            if (r.valid) {
+            const int colbase = n0 + c0;
+            const int q = shuf ? colbase / cq : 0;                     // cq % 32 == 0 for PixelShuffle layers
+            // mapped rows of THIS thread's row for this column chunk
+            const long long my_rrow = e.resid ? map_row(e, e.resid_map, r, q) : -1;
+            const long long my_orow0 = e.out[0].dtype != OUT_NONE ? map_row(e, e.out[0].map, r, q) : -1;
+            const long long my_orow1 = e.out[1].dtype != OUT_NONE ? map_row(e, e.out[1].map, r, q) : -1;
 #pragma unroll
-                for (int g8 = 0; g8 < 4; ++g8) {
-                    const int col = n0 + c0 + g8 * 8;
-                    if (c0 + g8 * 8 < block_n && col < p.N) {
-                        float v[8];
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const int col = colbase + g4 * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col < e.N) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
+                    v.x = apply_act(__uint_as_float(acc[g4 * 4 + 0]) + b.x, e.act);
+                    v.y = apply_act(__uint_as_float(acc[g4 * 4 + 1]) + b.y, e.act);
+                    v.z = apply_act(__uint_as_float(acc[g4 * 4 + 2]) + b.z, e.act);
+                    v.w = apply_act(__uint_as_float(acc[g4 * 4 + 3]) + b.w, e.act);
+                }
+                *reinterpret_cast<float4*>(stage_tile + lane * kPitch + g4 * 4) = v;
+            }
+            __syncwarp();
+            const int col = colbase + c4;
+            const int ocol = col - q * (shuf ? cq : 0);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(acc[g8 * 8 + i]);
-                        epilogue8(p, r, col, v);
-                    }
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rsub;
+                const long long rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
+                const long long orow0 = __shfl_sync(0xffffffffu, my_orow0, rr);
+                const long long orow1 = __shfl_sync(0xffffffffu, my_orow1, rr);
+                if (col < e.N && c0 + c4 < block_n && (orow0 >= 0 || orow1 >= 0)) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(stage_tile + rr * kPitch + c4);
+                    float v[4] = {t4.x, t4.y, t4.z, t4.w};
+                    finish_store<4>(e, v, ocol, rrow, orow0, orow1);
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -264,7 +331,8 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
     const GemmParams& p = params[blockIdx.z];
     const int m = blockIdx.x;
     if (m >= p.M) return;
-    const RowCtx r = decode_row(p, m);
+    const EpiCtx e = load_epi(p);
+    const RowCtx r = decode_row(e, m);
     if (!r.valid) return;
     int kp_per_tap = 0;
     for (int sg = 0; sg < p.num_segs; ++sg) kp_per_tap += p.seg_kblocks[sg] * kBlockK;
@@ -286,7 +354,7 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
                 kbase += p.seg_kblocks[sg] * kBlockK;
             }
         }
-        epilogue8(p, r, col, v);
+        epilogue8(e, r, col, v);
     }
 }
 
@@ -294,11 +362,19 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
 int gemm_pick_stages(int block_n, int* smem_bytes) {
+    // Two CTAs per SM (one's epilogue overlaps the other's main loop) when >= 3 stages still fit in half the
+    // shared memory; otherwise one CTA per SM with a deeper pipeline.
     const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
-    int stages = (200 * 1024) / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) stages = 2;
-    *smem_bytes = 1024 + stages * stage_bytes + 256;
+    const int overhead = 1024 + 256;
+    int stages = (113 * 1024 - overhead) / stage_bytes;
+    if (stages >= 3) {
+        if (stages > 4) stages = 4;
+    } else {
+        stages = (226 * 1024 - overhead) / stage_bytes;
+        if (stages > 6) stages = 6;
+        if (stages < 2) stages = 2;
+    }
+    *smem_bytes = overhead + stages * stage_bytes;
     return stages;
 }
 

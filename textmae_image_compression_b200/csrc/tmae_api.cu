@@ -488,7 +488,9 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         if (descs[g].layer->Cout > max_N) max_N = descs[g].layer->Cout;
     }
     const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
-    const int bn = pick_block_n(m_tiles, max_N, groups);
+    int bn = pick_block_n(m_tiles, max_N, groups);
+    for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
+        if (descs[g].out0.map == MAP_SHUF_PAD || descs[g].out1.map == MAP_SHUF_PAD) bn = (bn + 31) / 32 * 32;
     for (int g = 0; g < groups; ++g) {
         GemmParams p;
         int rc = fill_params(h, descs[g], groups, &p, bn);
