@@ -28,6 +28,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // --------------------------------------------------------------------------------------------
 // shared-memory addresses, elect
 // --------------------------------------------------------------------------------------------

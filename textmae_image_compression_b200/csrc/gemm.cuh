@@ -68,6 +68,7 @@ struct alignas(64) GemmParams {
     const int64_t* gather_ids;        // MAP_GATHER1
     OutSpec out[2];
     double flops;                     // algorithmic flops of this GEMM (profiling)
+    long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)
 };
 
 // haloed layout: per image (s+1) x (s+1) rows; pixel (y, x) at y*(s+1)+x; column s and row s are zero.

@@ -90,6 +90,28 @@ __device__ __forceinline__ long long map_row(const EpiCtx& p, int map, const Row
     return -1;
 }
 
+// erf-form GELU with erf from Abramowitz & Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~12 FMA instead of erff's ~40
+// instructions; the result is rounded to bf16 (2^-9 relative) right after, so the approximation is invisible.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    const float erf_abs = 1.0f - poly * __expf(-z * z);
+    const float erf_v = copysignf(erf_abs, x);
+    return 0.5f * x * (1.0f + erf_v);
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fast(float v) {
+    if (ACT == ACT_GELU) return gelu_erf_fast(v);
+    if (ACT == ACT_HALF_TANH) return 0.5f * tanhf(v);
+    return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == ACT_GELU) return gelu_erf(v);
     if (act == ACT_HALF_TANH) return 0.5f * tanhf(v);
@@ -155,9 +177,11 @@ __device__ __forceinline__ void epilogue8(const EpiCtx& p, const RowCtx& r, int 
 // ---------------------------------------------------------------------------------------------------------
 // tensor-core kernel
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;                     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiPitch = 36;                         // floats per staged accumulator row (32 + 4 pad)
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 
+template <int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     const GemmParams& p = params[blockIdx.z];
@@ -177,6 +201,8 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    long long* ticks = p.dbg_ticks ? p.dbg_ticks + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x)) * 8 : nullptr;
+    if (ticks && threadIdx.x == 0) ticks[0] = globaltimer_ns();
 
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)block_n) tmem_cols <<= 1;
@@ -203,6 +229,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (ticks && threadIdx.x == 0) ticks[1] = globaltimer_ns();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -222,6 +249,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
                         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
                         tma_load_2d(sA, &p.a_map[sg], &full_bar[stage], k * kBlockK, row);
                         tma_load_2d(sB, &p.b_map, &full_bar[stage], kb * kBlockK, n0);
+                        if (ticks && kb == 0) ticks[2] = globaltimer_ns();
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -237,6 +265,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
             for (int kb = 0; kb < total_kb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
+                if (ticks && kb == 0) ticks[3] = globaltimer_ns();
                 const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
                 const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kAStageBytes);
@@ -250,27 +279,33 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
             umma_commit(accum_bar);                  // accumulator complete
+            if (ticks) ticks[4] = globaltimer_ns();
         }
         __syncwarp();
     } else {
-        // ===== epilogue (warps 2..5; TMEM lane quarter = warp % 4) =====
-        // Phase 1 (thread = accumulator row): TMEM -> registers, + bias, activation, -> smem staging tile.
-        // Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): residual add and
-        // coalesced 64 / 128-byte row segments to global memory.  The staging tile reuses the (now idle)
-        // pipeline buffers: accum_bar completes only after every MMA has finished reading them.
+        // ===== epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter alternate 32-column chunks) =====
+        // Phase 1 (thread = accumulator row): TMEM -> registers -> smem staging tile (raw fp32 accumulators).
+        // Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): + bias, activation,
+        // residual add, coalesced 64 / 128-byte row segments to global memory.  The staging tiles reuse the (now
+        // idle) pipeline buffers: accum_bar completes only after every MMA has finished reading them.
         const EpiCtx e = load_epi(p);
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int m = m0 + quarter * 32 + lane;
         const RowCtx r = decode_row(e, m);
         const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
         const int cq = e.N >> 2;
-        constexpr int kPitch = 36;                                    // floats per staged row (32 + 4 pad)
-        float* stage_tile = reinterpret_cast<float*>(smem) + (size_t)quarter * 32 * kPitch;
+        float* stage_tile = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kEpiPitch;
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+        // mapped rows of THIS thread's accumulator row (quadrant-dependent ones are refreshed per chunk)
+        int my_rrow = e.resid ? (int)map_row(e, e.resid_map, r, 0) : -1;
+        int my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, 0) : -1;
+        int my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, 0) : -1;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
+        if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c0 = 0; c0 < block_n; c0 += 32) {
+        for (int c0 = half * 32; c0 < block_n; c0 += 64) {
             uint32_t acc[32];
             if (block_n - c0 >= 32) {
                 tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
@@ -281,45 +316,46 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
                 for (int i = 0; i < 16; ++i) { acc[i] = a16[i]; acc[16 + i] = 0u; }
             }
             tmem_ld_wait();
-            const int colbase = n0 + c0;
-            const int q = shuf ? colbase / cq : 0;                     // cq % 32 == 0 for PixelShuffle layers
-            // mapped rows of THIS thread's row for this column chunk
-            const long long my_rrow = e.resid ? map_row(e, e.resid_map, r, q) : -1;
-            const long long my_orow0 = e.out[0].dtype != OUT_NONE ? map_row(e, e.out[0].map, r, q) : -1;
-            const long long my_orow1 = e.out[1].dtype != OUT_NONE ? map_row(e, e.out[1].map, r, q) : -1;
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const int col = colbase + g4 * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (col < e.N) {
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col));
-                    v.x = apply_act(__uint_as_float(acc[g4 * 4 + 0]) + b.x, e.act);
-                    v.y = apply_act(__uint_as_float(acc[g4 * 4 + 1]) + b.y, e.act);
-                    v.z = apply_act(__uint_as_float(acc[g4 * 4 + 2]) + b.z, e.act);
-                    v.w = apply_act(__uint_as_float(acc[g4 * 4 + 3]) + b.w, e.act);
-                }
-                *reinterpret_cast<float4*>(stage_tile + lane * kPitch + g4 * 4) = v;
+            for (int g4 = 0; g4 < 8; ++g4)
+                *reinterpret_cast<uint4*>(stage_tile + lane * kEpiPitch + g4 * 4) =
+                    make_uint4(acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2], acc[g4 * 4 + 3]);
+            const int colbase = n0 + c0;
+            int q = 0;
+            if (shuf) {                                               // cq % 32 == 0 for PixelShuffle layers
+                q = colbase / cq;
+                my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, q) : -1;
+                my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, q) : -1;
             }
             __syncwarp();
             const int col = colbase + c4;
+            const bool col_ok = col < e.N && c0 + c4 < block_n;
             const int ocol = col - q * (shuf ? cq : 0);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rr = it * 4 + rsub;
-                const long long rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
-                const long long orow0 = __shfl_sync(0xffffffffu, my_orow0, rr);
-                const long long orow1 = __shfl_sync(0xffffffffu, my_orow1, rr);
-                if (col < e.N && c0 + c4 < block_n && (orow0 >= 0 || orow1 >= 0)) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(stage_tile + rr * kPitch + c4);
-                    float v[4] = {t4.x, t4.y, t4.z, t4.w};
+                const int rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
+                const int orow0 = __shfl_sync(0xffffffffu, my_orow0, rr);
+                const int orow1 = __shfl_sync(0xffffffffu, my_orow1, rr);
+                if (col_ok && (orow0 >= 0 || orow1 >= 0)) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(stage_tile + rr * kEpiPitch + c4);
+                    float v[4];
+                    v[0] = act_fast<ACT>(t4.x + b4.x);
+                    v[1] = act_fast<ACT>(t4.y + b4.y);
+                    v[2] = act_fast<ACT>(t4.z + b4.z);
+                    v[3] = act_fast<ACT>(t4.w + b4.w);
                     finish_store<4>(e, v, ocol, rrow, orow0, orow1);
                 }
             }
             __syncwarp();
         }
+        if (ticks && warp == 2 && lane == 0) ticks[6] = globaltimer_ns();
     }
     tc_fence_before();
     __syncthreads();
+    if (ticks && threadIdx.x == 0) ticks[7] = globaltimer_ns();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
@@ -379,11 +415,15 @@ int gemm_pick_stages(int block_n, int* smem_bytes) {
 }
 
 cudaError_t gemm_tc_configure() {
-    return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tc_kernel<ACT_HALF_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
-cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, bool simt,
+cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, bool simt,
                         cudaStream_t stream) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
@@ -393,7 +433,11 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     int smem = 0;
     const int stages = gemm_pick_stages(block_n, &smem);
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
-    gemm_tc_kernel<<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    switch (act) {            // every member of a grouped launch shares the activation
+        case ACT_GELU: gemm_tc_kernel<ACT_GELU><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
+        case ACT_HALF_TANH: gemm_tc_kernel<ACT_HALF_TANH><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
+        default: gemm_tc_kernel<ACT_NONE><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
+    }
     return cudaGetLastError();
 }
 
