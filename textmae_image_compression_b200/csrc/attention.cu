@@ -167,6 +167,7 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
                              cudaStream_t st) {
     if (C != H * HD) return cudaErrorInvalidValue;
     const int Tp = attn_tp(T);
+    TMAE_CARVEOUT_ONCE(attention_kernel);
     attention_kernel<<<N * H, kAttnThreads, attn_smem(T), st>>>(qkv, out, T, Tp, H, C,
                                                                 scale * 1.4426950408889634f);
     return cudaGetLastError();

@@ -7,6 +7,18 @@
 
 namespace tmae {
 
+// Every kernel of the library asks for the same (maximum) shared-memory carve-out, so the SMs never have to
+// reconfigure the L1/shared split between the smem-heavy GEMM launches and the small kernels around them.
+template <typename K>
+inline void prefer_max_smem_carveout(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define TMAE_CARVEOUT_ONCE(kernel)                       \
+    do {                                                 \
+        static bool _done = false;                       \
+        if (!_done) { prefer_max_smem_carveout(kernel); _done = true; } \
+    } while (0)
+
 // --------------------------------------------------------------------------------------------
 // small math
 // --------------------------------------------------------------------------------------------

@@ -48,6 +48,7 @@ cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __
                                   const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
                                   int T, int C, int in_chans, int patch, cudaStream_t st) {
     dim3 grid(K + 1, N);
+    TMAE_CARVEOUT_ONCE(gather_patches_kernel);
     gather_patches_kernel<<<grid, 192, 0, st>>>(imgs, ids_keep, patches, x, cls_token, pos_embed, S, grid_w, K, T, C,
                                                 in_chans, patch);
     return cudaGetLastError();
@@ -111,13 +112,13 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
     const int blocks = (rows * 32 + 255) / 256;
     if (C % 128 != 0) return cudaErrorInvalidValue;
     switch (C / 128) {
-        case 6: layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 8: layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 10: layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 1: layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 2: layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 3: layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 4: layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -208,6 +209,7 @@ cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long row
     const long long total = rows * Cz;
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
+    TMAE_CARVEOUT_ONCE(bottleneck_kernel);
     bottleneck_kernel<<<blocks, 256, 0, st>>>(z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4, rate_acc,
                                               rows_per_image);
     return cudaGetLastError();
@@ -286,6 +288,7 @@ cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* 
     const long long total = rows * (cs / 4);
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
+    TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
     gaussian_slice_kernel<<<blocks, 256, 0, st>>>(y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat, yhat_pad, ld_pad, s,
                                                   rate_acc);
     return cudaGetLastError();
@@ -335,6 +338,7 @@ __global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N,
 }
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
                                  double* rate_sums, cudaStream_t st) {
+    TMAE_CARVEOUT_ONCE(rate_finalize_kernel);
     rate_finalize_kernel<<<1, 256, 0, st>>>(rate_acc, N, pixels_per_image, bpp, rate_sums);
     return cudaGetLastError();
 }

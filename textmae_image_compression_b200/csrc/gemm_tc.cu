@@ -397,24 +397,29 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
-int gemm_pick_stages(int block_n, int* smem_bytes) {
-    // Two CTAs per SM (one's epilogue overlaps the other's main loop) when >= 3 stages still fit in half the
-    // shared memory; otherwise one CTA per SM with a deeper pipeline.
+int gemm_pick_stages(int block_n, int total_ctas, int* smem_bytes) {
+    // The main loop is latency bound for small tiles (one TMA round trip per stage), so bytes in flight per SM is
+    // what matters.  A single wave (<= 148 CTAs) gets the whole shared memory of its SM; larger grids run two CTAs
+    // per SM so that one CTA's epilogue overlaps the other's main loop.
     const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
     const int overhead = 1024 + 256;
-    int stages = (113 * 1024 - overhead) / stage_bytes;
-    if (stages >= 3) {
-        if (stages > 4) stages = 4;
-    } else {
+    int stages;
+    if (total_ctas <= 148) {
         stages = (226 * 1024 - overhead) / stage_bytes;
+        if (stages > 10) stages = 10;
+    } else {
+        stages = (113 * 1024 - overhead) / stage_bytes;
         if (stages > 6) stages = 6;
-        if (stages < 2) stages = 2;
     }
+    if (stages < 2) stages = 2;
     *smem_bytes = overhead + stages * stage_bytes;
     return stages;
 }
 
 cudaError_t gemm_tc_configure() {
+    prefer_max_smem_carveout(gemm_tc_kernel<ACT_NONE>);
+    prefer_max_smem_carveout(gemm_tc_kernel<ACT_GELU>);
+    prefer_max_smem_carveout(gemm_tc_kernel<ACT_HALF_TANH>);
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -431,8 +436,8 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         return cudaGetLastError();
     }
     int smem = 0;
-    const int stages = gemm_pick_stages(block_n, &smem);
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
+    const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), &smem);
     switch (act) {            // every member of a grouped launch shares the activation
         case ACT_GELU: gemm_tc_kernel<ACT_GELU><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
         case ACT_HALF_TANH: gemm_tc_kernel<ACT_HALF_TANH><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;

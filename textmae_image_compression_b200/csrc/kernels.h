@@ -10,7 +10,7 @@ namespace tmae {
 
 // gemm_tc.cu
 cudaError_t gemm_tc_configure();
-int gemm_pick_stages(int block_n, int* smem_bytes);
+int gemm_pick_stages(int block_n, int total_ctas, int* smem_bytes);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, bool simt,
                         cudaStream_t stream);
 

@@ -324,6 +324,7 @@ cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int sof
         cudaError_t e = cudaFuncSetAttribute(mask_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    TMAE_CARVEOUT_ONCE(mask_select_kernel);
     mask_select_kernel<<<N, kThreads, smem, st>>>(scores, L, Lp2, K, softmax_isa == 8 ? 8 : 16, ids_shuffle,
                                                   ids_restore, ids_keep);
     return cudaGetLastError();

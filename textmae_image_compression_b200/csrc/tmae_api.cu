@@ -57,7 +57,7 @@ struct Step {
     const float* ln_beta = nullptr;
     int ln_final = 0;
     // GC
-    int slice = 0;
+    int slice = 0, gc_slices = 1;
     std::string tag;
 };
 
@@ -87,7 +87,7 @@ struct Workspace {
     __nv_bfloat16 *hs1[2] = {nullptr, nullptr}, *hs2[2] = {nullptr, nullptr}, *hs3[2] = {nullptr, nullptr},
                   *hs4[2] = {nullptr, nullptr}, *lat[2] = {nullptr, nullptr};     // 0 = means, 1 = scales
     __nv_bfloat16* yhat_pad = nullptr;
-    __nv_bfloat16* t[3][4] = {{nullptr}};      // per net (mean, scale, lrp) 4 intermediate activations
+    __nv_bfloat16* t[18][4] = {{nullptr}};     // [slice-group member j (0..5) * 3 + net (mean, scale, lrp)][layer]
     double* rate_acc = nullptr;
     float* bpp = nullptr;
     double* rate_sums = nullptr;
@@ -445,7 +445,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.yhat_pad, rp * Cy);
     int ch[6];
     cc_channels(h, ch, 0, false);
-    for (int net = 0; net < 3; ++net)
+    for (int net = 0; net < 18; ++net)
         for (int l = 0; l < 4; ++l) WS_ALLOC(w.t[net][l], rp * ch[l + 1]);
     WS_ALLOC(w.rate_acc, (size_t)N);
     WS_ALLOC(w.bpp, (size_t)N);
@@ -466,7 +466,7 @@ size_t workspace_bytes_estimate(const tmae_handle* h, int N) {
     b += rk * (h->ga_ch[1] + h->ga_ch[2] + h->ga_ch[3]) * 2 + rp * h->Cy * 2 + rk * h->Cy * 4 * 4 + rk / 16 * h->Cz * 4;
     b += rp * (384 + 336) * 2 + rp2 * (288 + 240) * 2 + rp4 * h->Cz * 2;
     b += 2 * (rp4 * 240 + rp2 * (288 + 336) + rp * (384 + 384)) * 2 + rp * h->Cy * 2;
-    b += 3 * rp * (224 + 176 + 128 + 80) * 2;
+    b += 18 * rp * (224 + 176 + 128 + 80) * 2;
     b += (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size * 4 + (size_t)N * h->L * 4;
     return b;
 }
@@ -647,56 +647,69 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         }
     }
     const bool skip_dead = (h->cfg.flags & TMAE_FLAG_SKIP_DEAD_LRP) != 0;
-    for (int i = 0; i < h->nsl; ++i) {   // slice loop (MCM.py:755-784)
-        const int sup = i < h->nsl / 2 ? i : h->nsl / 2;
+    // Slice loop (MCM.py:755-784).  Slice i reads y_hat of slices [0, min(i, 6)): slices 0..5 form a serial chain,
+    // slices 6..11 depend only on 0..5 and are mutually independent, so they run as ONE grouped launch per layer.
+    const int half_sl = h->nsl / 2;
+    for (int i0 = 0; i0 < h->nsl;) {
+        const int cnt = i0 < half_sl ? 1 : h->nsl - i0;          // members of this slice group
+        const int sup = i0 < half_sl ? i0 : half_sl;
         int ch[6];
-        cc_channels(h, ch, i, false);
-        for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i], grouped
-            GemmDesc d[2];
-            for (int net = 0; net < 2; ++net) {
-                const char* nm = net == 0 ? "cc_transform_mean." : "cc_transform_scale.";
-                d[net].layer = get_layer(h, std::string(nm) + std::to_string(i) + "." + std::to_string(2 * l));
-                if (l == 0) {
-                    d[net].seg[0] = seg(w.lat[net], Cy, Cy);
-                    d[net].nseg = 1;
-                    if (sup > 0) { d[net].seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); d[net].nseg = 2; }
-                } else {
-                    d[net].seg[0] = seg(w.t[net][l - 1], ch[l], ch[l]);
+        cc_channels(h, ch, i0, false);
+        for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i] of every member, grouped
+            std::vector<GemmDesc> d((size_t)cnt * 2);
+            for (int j = 0; j < cnt; ++j)
+                for (int net = 0; net < 2; ++net) {
+                    GemmDesc& g = d[(size_t)j * 2 + net];
+                    const int i = i0 + j;
+                    const char* nm = net == 0 ? "cc_transform_mean." : "cc_transform_scale.";
+                    g.layer = get_layer(h, std::string(nm) + std::to_string(i) + "." + std::to_string(2 * l));
+                    if (l == 0) {
+                        g.seg[0] = seg(w.lat[net], Cy, Cy);
+                        g.nseg = 1;
+                        if (sup > 0) { g.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); g.nseg = 2; }
+                    } else {
+                        g.seg[0] = seg(w.t[j * 3 + net][l - 1], ch[l], ch[l]);
+                    }
+                    g.a_rows = rp; g.M = (int)rp; g.in_mode = IN_PADDED; g.side = s;
+                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + net][l], ch[l + 1], OUT_BF16, MAP_SAME); }
+                    else g.out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
+                    g.flops = conv_flops(rk, ch[l], ch[l + 1], 9);
                 }
-                d[net].a_rows = rp; d[net].M = (int)rp; d[net].in_mode = IN_PADDED; d[net].side = s;
-                if (l < 4) { d[net].act = ACT_GELU; d[net].out0 = outspec(w.t[net][l], ch[l + 1], OUT_BF16, MAP_SAME); }
-                else d[net].out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
-                d[net].flops = conv_flops(rk, ch[l], ch[l + 1], 9);
-            }
-            snprintf(tag, sizeof(tag), "cc.%d.%d", i, 2 * l);
-            rc = add_gemm_group(h, pl, d, 2, tag); if (rc) return rc;
+            snprintf(tag, sizeof(tag), "cc.%d.%d", i0, 2 * l);
+            rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc;
         }
-        { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i; g.tag = "gaussian." + std::to_string(i); pl.steps.push_back(g); }
-        if (skip_dead && i >= h->nsl / 2) continue;
-        int lch[6];
-        cc_channels(h, lch, i, true);
-        for (int l = 0; l < 5; ++l) {    // lrp_transform[i] (MCM.py:780-783)
-            GemmDesc d;
-            d.layer = get_layer(h, "lrp_transform." + std::to_string(i) + "." + std::to_string(2 * l));
-            if (l == 0) {
-                d.seg[0] = seg(w.lat[0], Cy, Cy);
-                if (i < h->nsl / 2) { d.seg[1] = seg(w.yhat_pad, h->sc * (i + 1), Cy); d.nseg = 2; }
-                else { d.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); d.seg[2] = seg(w.yhat_pad + i * h->sc, h->sc, Cy); d.nseg = 3; }
-            } else {
-                d.seg[0] = seg(w.t[2][l - 1], lch[l], lch[l]);
+        { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i0; g.gc_slices = cnt; g.tag = "gaussian." + std::to_string(i0); pl.steps.push_back(g); }
+        if (!(skip_dead && i0 >= half_sl)) {
+            int lch[6];
+            cc_channels(h, lch, i0, true);
+            for (int l = 0; l < 5; ++l) {    // lrp_transform[i] (MCM.py:780-783)
+                std::vector<GemmDesc> d((size_t)cnt);
+                for (int j = 0; j < cnt; ++j) {
+                    GemmDesc& g = d[j];
+                    const int i = i0 + j;
+                    g.layer = get_layer(h, "lrp_transform." + std::to_string(i) + "." + std::to_string(2 * l));
+                    if (l == 0) {
+                        g.seg[0] = seg(w.lat[0], Cy, Cy);
+                        if (i < half_sl) { g.seg[1] = seg(w.yhat_pad, h->sc * (i + 1), Cy); g.nseg = 2; }
+                        else { g.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); g.seg[2] = seg(w.yhat_pad + i * h->sc, h->sc, Cy); g.nseg = 3; }
+                    } else {
+                        g.seg[0] = seg(w.t[j * 3 + 2][l - 1], lch[l], lch[l]);
+                    }
+                    g.a_rows = rp; g.M = (int)rp; g.in_mode = IN_PADDED; g.side = s;
+                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + 2][l], lch[l + 1], OUT_BF16, MAP_SAME); }
+                    else {
+                        g.act = ACT_HALF_TANH;
+                        g.resid = w.yhat + i * h->sc; g.resid_ld = Cy; g.resid_map = MAP_TO_COMPACT;
+                        g.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
+                        g.out1 = outspec(w.yhat_pad + i * h->sc, Cy, OUT_BF16, MAP_SAME);
+                    }
+                    g.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
+                }
+                snprintf(tag, sizeof(tag), "lrp.%d.%d", i0, 2 * l);
+                rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc;
             }
-            d.a_rows = rp; d.M = (int)rp; d.in_mode = IN_PADDED; d.side = s;
-            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(w.t[2][l], lch[l + 1], OUT_BF16, MAP_SAME); }
-            else {
-                d.act = ACT_HALF_TANH;
-                d.resid = w.yhat + i * h->sc; d.resid_ld = Cy; d.resid_map = MAP_TO_COMPACT;
-                d.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
-                d.out1 = outspec(w.yhat_pad + i * h->sc, Cy, OUT_BF16, MAP_SAME);
-            }
-            d.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
-            snprintf(tag, sizeof(tag), "lrp.%d.%d", i, 2 * l);
-            rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
         }
+        i0 += cnt;
     }
     simple(ST_RATE, FAM_ENTROPY, "rate_finalize");
 
@@ -788,7 +801,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                                               o.z_symbols, o.z_hat, w.zhat_pad, h->s4, w.rate_acc, h->s4 * h->s4, st));
                 break;
             case ST_GC:
-                CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc,
+                CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc * sp.gc_slices,
                                                   o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_pad, h->Cy, s, w.rate_acc, st));
                 break;
             case ST_RATE:
@@ -1149,7 +1162,7 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
         for (int c = 0; c < ctas; ++c) { if (t[c * 8] < tmin) tmin = t[c * 8]; if (t[c * 8 + 7] > tend) tend = t[c * 8 + 7]; }
         double avg[8] = {0};
         for (int c = 0; c < ctas; ++c) for (int k = 1; k < 8; ++k) avg[k] += (double)(t[c * 8 + k] - t[c * 8]) / ctas;
-        int smem = 0; const int stages = gemm_pick_stages(p.block_n, &smem);
+        int smem = 0; const int stages = gemm_pick_stages(p.block_n, ctas, &smem);
         fprintf(stderr, "[gemm timing] M=%d N=%d Kb=%d taps=%d bn=%d ctas=%d stages=%d smem=%d | kernel %.1f us (events), first-start..last-end %.1f us | "
                 "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f, exit %.0f\n",
                 p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, smem, ms * 1e3,
