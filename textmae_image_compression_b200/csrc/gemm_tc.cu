@@ -155,6 +155,20 @@ __device__ __forceinline__ void finish_store(const EpiCtx& p, float (&v)[NV], in
     }
 }
 
+// Store 4 consecutive channels of one mapped row (row < 0: nothing to write).
+__device__ __forceinline__ void store_out4(const OutSpec& os, int orow, int ocol, const float (&v)[4]) {
+    if (os.dtype == OUT_NONE || orow < 0) return;
+    if (os.dtype == OUT_BF16) {
+        uint2 pk;
+        pk.x = pack_bf16x2(v[0], v[1]);
+        pk.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(os.ptr) + (long long)orow * os.ld + ocol) = pk;
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(os.ptr) + (long long)orow * os.ld + ocol) =
+            make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 // Row-per-thread variant (CUDA-core checker): finish 8 consecutive output channels [col, col+8) of one row.
 __device__ __forceinline__ void epilogue8(const EpiCtx& p, const RowCtx& r, int col, float (&v)[8]) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -182,7 +196,7 @@ constexpr int kEpiPitch = 36;                         // floats per staged accum
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 
 template <int ACT>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     const GemmParams& p = params[blockIdx.z];
     const int m0 = blockIdx.x * kBlockM;
@@ -198,6 +212,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* accum_bar = empty_bar + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    int* sm_tap = reinterpret_cast<int*>(tmem_slot + 2);                 // [kMaxTaps] row shift per conv tap
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -225,63 +240,80 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         tmem_alloc(tmem_slot, tmem_cols);
         tmem_relinquish();
     }
+    if (warp == 2 && lane < kMaxTaps) sm_tap[lane] = lane < p.num_taps ? p.tap_off[lane] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (ticks && threadIdx.x == 0) ticks[1] = globaltimer_ns();
 
+    // Producer and MMA loops are WARP-UNIFORM (all 32 lanes run the loop on identical values, only the TMA / MMA /
+    // commit instructions are elect-predicated), so the compiler keeps addresses and descriptors in uniform registers
+    // instead of moving them from a divergent lane for every instruction.
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int kb = 0;
-            const uint32_t tx_bytes = (uint32_t)stage_bytes;
-            for (int tap = 0; tap < p.num_taps; ++tap) {
-                const int row = m0 + p.tap_off[tap];
-                for (int sg = 0; sg < p.num_segs; ++sg) {
-                    const int nkb = p.seg_kblocks[sg];
-                    for (int k = 0; k < nkb; ++k, ++kb) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1u);
-                        uint8_t* sA = smem + (size_t)stage * stage_bytes;
-                        uint8_t* sB = sA + kAStageBytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-                        tma_load_2d(sA, &p.a_map[sg], &full_bar[stage], k * kBlockK, row);
-                        tma_load_2d(sB, &p.b_map, &full_bar[stage], kb * kBlockK, n0);
-                        if (ticks && kb == 0) ticks[2] = globaltimer_ns();
-                        if (++stage == stages) { stage = 0; phase ^= 1u; }
-                    }
-                }
+        const int nseg = p.num_segs;
+        const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
+        const void* map0 = &p.a_map[0];
+        const void* map1 = &p.a_map[1];
+        const void* map2 = &p.a_map[2];
+        const void* mapb = &p.b_map;
+        const uint32_t tx_bytes = (uint32_t)stage_bytes;
+        int stage = 0, sg = 0, k = 0, tap = 0;
+        int skb_cur = skb0;
+        const void* map_cur = map0;
+        int row = m0 + sm_tap[0];
+        uint32_t phase = 0, stage_off = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+            if (elect_one()) {
+                const uint32_t fb = full_a + 8u * stage;
+                mbar_arrive_expect_tx_a(fb, tx_bytes);
+                tma_load_2d_a(smem_base + stage_off, map_cur, fb, k * kBlockK, row);
+                tma_load_2d_a(smem_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
+                if (ticks && kb == 0) ticks[2] = globaltimer_ns();
             }
+            __syncwarp();
+            if (++k == skb_cur) {
+                k = 0;
+                if (++sg == nseg) { sg = 0; ++tap; row = m0 + sm_tap[tap < kMaxTaps ? tap : 0]; }
+                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+            }
+            stage_off += (uint32_t)stage_bytes;
+            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int kb = 0; kb < total_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+        const uint64_t desc0 = umma_smem_desc_sw128(smem_base);       // + (byte offset >> 4) selects stage / k-slice
+        int stage = 0;
+        uint32_t phase = 0, stage_off = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait_a(full_a + 8u * stage, phase);
+            tc_fence_after();
+            const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
+            const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
+            if (elect_one()) {
                 if (ticks && kb == 0) ticks[3] = globaltimer_ns();
-                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint64_t a_desc = umma_smem_desc_sw128(a_addr);
-                const uint64_t b_desc = umma_smem_desc_sw128(a_addr + kAStageBytes);
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
                     umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                               (kb | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[stage]);      // smem stage reusable once these MMAs retire
-                if (++stage == stages) { stage = 0; phase ^= 1u; }
+                umma_commit_a(empty_a + 8u * stage);      // smem stage reusable once these MMAs retire
+                if (kb == total_kb - 1) {
+                    umma_commit(accum_bar);                // accumulator complete
+                    if (ticks) ticks[4] = globaltimer_ns();
+                }
             }
-            umma_commit(accum_bar);                  // accumulator complete
-            if (ticks) ticks[4] = globaltimer_ns();
+            __syncwarp();
+            stage_off += (uint32_t)stage_bytes;
+            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
         }
-        __syncwarp();
     } else {
         // ===== epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter alternate 32-column chunks) =====
         // Phase 1 (thread = accumulator row): TMEM -> registers -> smem staging tile (raw fp32 accumulators).
@@ -301,11 +333,21 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         int my_rrow = e.resid ? (int)map_row(e, e.resid_map, r, 0) : -1;
         int my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, 0) : -1;
         int my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, 0) : -1;
+        // bias of this lane's 4 channels for each of its (up to 4) column chunks: fetched before the accumulator wait
+        auto load_bias = [&](int c0) {
+            const int col = n0 + c0 + c4;
+            return (c0 + c4 < block_n && col < e.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 bias_next = load_bias(half * 32);
+        const bool has_resid = e.resid != nullptr;
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
         for (int c0 = half * 32; c0 < block_n; c0 += 64) {
+            const float4 b4 = bias_next;
+            bias_next = load_bias(c0 + 64);                             // prefetch for the next chunk of this warp
             uint32_t acc[32];
             if (block_n - c0 >= 32) {
                 tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
@@ -331,22 +373,35 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
             const int col = colbase + c4;
             const bool col_ok = col < e.N && c0 + c4 < block_n;
             const int ocol = col - q * (shuf ? cq : 0);
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok) b4 = __ldg(reinterpret_cast<const float4*>(e.bias + col));
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int rr = it * 4 + rsub;
-                const int rrow = __shfl_sync(0xffffffffu, my_rrow, rr);
-                const int orow0 = __shfl_sync(0xffffffffu, my_orow0, rr);
-                const int orow1 = __shfl_sync(0xffffffffu, my_orow1, rr);
-                if (col_ok && (orow0 >= 0 || orow1 >= 0)) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(stage_tile + rr * kEpiPitch + c4);
-                    float v[4];
-                    v[0] = act_fast<ACT>(t4.x + b4.x);
-                    v[1] = act_fast<ACT>(t4.y + b4.y);
-                    v[2] = act_fast<ACT>(t4.z + b4.z);
-                    v[3] = act_fast<ACT>(t4.w + b4.w);
-                    finish_store<4>(e, v, ocol, rrow, orow0, orow1);
+            for (int hb = 0; hb < 2; ++hb) {                          // two batches of 4 row-groups: loads first, then math
+                int rrow[4], orow0[4], orow1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = (hb * 4 + j) * 4 + rsub;
+                    rrow[j] = __shfl_sync(0xffffffffu, my_rrow, rr);
+                    orow0[j] = __shfl_sync(0xffffffffu, my_orow0, rr);
+                    orow1[j] = __shfl_sync(0xffffffffu, my_orow1, rr);
+                }
+                if (col_ok) {
+                    float4 rs[4], t4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (has_resid)                                 // clamped row: always a valid address
+                            rs[j] = *reinterpret_cast<const float4*>(e.resid + (long long)max(rrow[j], 0) * e.resid_ld + ocol);
+                        t4[j] = *reinterpret_cast<const float4*>(stage_tile + ((hb * 4 + j) * 4 + rsub) * kEpiPitch + c4);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[4];
+                        v[0] = act_fast<ACT>(t4[j].x + b4.x) + rs[j].x;
+                        v[1] = act_fast<ACT>(t4[j].y + b4.y) + rs[j].y;
+                        v[2] = act_fast<ACT>(t4[j].z + b4.z) + rs[j].z;
+                        v[3] = act_fast<ACT>(t4[j].w + b4.w) + rs[j].w;
+                        store_out4(e.out[0], orow0[j], ocol, v);
+                        store_out4(e.out[1], orow1[j], ocol, v);
+                    }
                 }
             }
             __syncwarp();

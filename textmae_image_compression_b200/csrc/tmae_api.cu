@@ -1167,6 +1167,35 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
                 "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f, exit %.0f\n",
                 p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, smem, ms * 1e3,
                 (tend - tmin) * 1e-3, avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
+        // steady-state cost of back-to-back dependent launches of this kernel: plain stream vs CUDA graph
+        {
+            p.dbg_ticks = nullptr;
+            cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
+            const int reps = 50;
+            cudaStreamSynchronize(st);
+            cudaEventRecord(ev0, st);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, st);
+            cudaEventRecord(ev1, st);
+            cudaStreamSynchronize(st);
+            float ms_plain = 0; cudaEventElapsedTime(&ms_plain, ev0, ev1);
+            cudaStream_t cs; cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+            cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
+            cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, cs);
+            cudaStreamEndCapture(cs, &graph);
+            float ms_graph = -1;
+            if (graph && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
+                cudaGraphLaunch(gexec, cs); cudaStreamSynchronize(cs);
+                cudaEventRecord(ev0, cs); cudaGraphLaunch(gexec, cs); cudaEventRecord(ev1, cs);
+                cudaStreamSynchronize(cs);
+                cudaEventElapsedTime(&ms_graph, ev0, ev1);
+                cudaGraphExecDestroy(gexec);
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            fprintf(stderr, "[gemm timing]   back-to-back x%d: %.2f us/launch (stream), %.2f us/launch (graph)\n", reps,
+                    ms_plain * 1e3 / reps, ms_graph * 1e3 / reps);
+        }
         cudaFree(dticks);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
