@@ -165,16 +165,25 @@ def run_b200(args, kwargs, batch, desc, wl):
         dist.init_process_group("nccl", device_id=dev)
     cfg = PathConfig(**kwargs)
     sd = make_state_dict(cfg, seed=0)                         # replicated weights
-    model = MCM(**kwargs, skip_dead_lrp=False)
-    model.load_state_dict(sd)
-    model.cuda().eval()
+    # `--streams S` pipelines S batches through S independent handles (own workspace, own CUDA stream): the serial
+    # slice chain of one batch leaves most SMs idle, a second batch in flight fills them.  A step is still one batch.
+    S = max(1, args.streams)
+    models = []
+    for _ in range(S):
+        m_ = MCM(**kwargs, skip_dead_lrp=False)
+        m_.load_state_dict(sd)
+        m_.cuda().eval()
+        models.append(m_)
+    model = models[0]
     del sd
     n_rot = 8                                                 # rotating input batches: 8 x 38.5 MB > 126 MB L2
     imgs_h, scores_h = make_inputs(kwargs, batch, 1000 + rank, n_rot)
     imgs_d = [t.cuda() for t in imgs_h]
     scores_d = [t.cuda() for t in scores_h]
-    model.reserve(batch)
+    for m_ in models:
+        m_.reserve(batch)
     stream = torch.cuda.current_stream()
+    side = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
     def barrier():
         if world > 1:
@@ -182,10 +191,21 @@ def run_b200(args, kwargs, batch, desc, wl):
         torch.cuda.synchronize()
 
     def step_dev(i):
-        out = model(imgs_d[i % n_rot], scores_d[i % n_rot])
-        if world > 1:
-            D.aggregate_rate(out["rate_sums"])                # the path's only collective (16 bytes)
+        with torch.cuda.stream(side[i % S]):
+            out = models[i % S](imgs_d[i % n_rot], scores_d[i % n_rot])
+            if world > 1:
+                D.aggregate_rate(out["rate_sums"])            # the path's only collective (16 bytes)
         return out
+
+    def fork(ev):
+        ev.record(stream)
+        for s_ in side:
+            s_.wait_event(ev)
+
+    def join(ev):
+        for s_ in side:
+            stream.wait_stream(s_)
+        ev.record(stream)
 
     # ---- device-resident throughput -------------------------------------------------------------------
     for i in range(args.warmup):
@@ -196,10 +216,10 @@ def run_b200(args, kwargs, batch, desc, wl):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record(stream)
+    fork(e0)
     for i in range(args.steps):
         out = step_dev(i)
-    e1.record(stream)
+    join(e1)
     barrier()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -212,14 +232,18 @@ def run_b200(args, kwargs, batch, desc, wl):
     pin_i = [t.pin_memory() for t in imgs_h[:3]]
     pin_s = [t.pin_memory() for t in scores_h[:3]]
     bpp_pin = [torch.empty(batch, dtype=torch.float32).pin_memory() for _ in range(3)]
-    for i in range(min(args.warmup, 3)):
-        model.forward_host(pin_i[i % 3], pin_s[i % 3], bpp_pin[i % 3])
+    def step_host(i):
+        # pinned host inputs -> H2D -> forward -> D2H of the per-image bpp, all on the step's stream
+        models[i % S].forward_host(pin_i[i % 3], pin_s[i % 3], bpp_pin[i % 3], stream=side[i % S])
+
+    for i in range(max(args.warmup, S)):
+        step_host(i)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
+    fork(e2)
     for i in range(args.steps):
-        model.forward_host(pin_i[i % 3], pin_s[i % 3], bpp_pin[i % 3])
-    e3.record(stream)
+        step_host(i)
+    join(e3)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
@@ -234,7 +258,7 @@ def run_b200(args, kwargs, batch, desc, wl):
     peaks = load_peaks()
     model.profile(True)
     for i in range(2):
-        step_dev(i)
+        model(imgs_d[i % n_rot], scores_d[i % n_rot])
     torch.cuda.synchronize()
     fams = model.profile_read()
     model.profile(False)
@@ -278,6 +302,7 @@ def run_b200(args, kwargs, batch, desc, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": desc, "name": wl, "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world} (images sharded, weights replicated, 16-byte rate all-reduce)",
+                       "streams_per_gpu": S,
                        "l2_policy": f"inputs rotate over {n_rot} batches ({n_rot * imgs_h[0].numel() * 4 / 1e6:.0f} MB) "
                                     "+ 350 MB of weights per step > 126 MB L2",
                        "algorithmic_gflop_per_image": ALGO_GFLOP_PER_IMG.get(wl)},
@@ -301,6 +326,7 @@ def main():
     ap.add_argument("--workload", default="B64", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=3, help="batches in flight per GPU (independent handles/streams)")
     args = ap.parse_args()
     kwargs, batch, desc = WORKLOADS[args.workload]
     if args.impl == "reference":
