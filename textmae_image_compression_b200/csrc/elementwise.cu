@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(192)
 gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict__ ids_keep,
                       __nv_bfloat16* __restrict__ patches, float* __restrict__ x, const float* __restrict__ cls_token,
                       const float* __restrict__ pos_embed, int S, int grid_w, int K, int T, int C, int in_chans,
-                      int patch) {
+                      int patch, const IoBlock* __restrict__ io) {
+    if (io) imgs = io->imgs;
     const int j = blockIdx.x, n = blockIdx.y;
     if (j == K) {
         float* dst = x + (size_t)n * T * C;
@@ -46,11 +47,11 @@ gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict_
 
 cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __nv_bfloat16* patches, float* x,
                                   const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
-                                  int T, int C, int in_chans, int patch, cudaStream_t st) {
+                                  int T, int C, int in_chans, int patch, cudaStream_t st, const IoBlock* io) {
     dim3 grid(K + 1, N);
     TMAE_CARVEOUT_ONCE(gather_patches_kernel);
     gather_patches_kernel<<<grid, 192, 0, st>>>(imgs, ids_keep, patches, x, cls_token, pos_embed, S, grid_w, K, T, C,
-                                                in_chans, patch);
+                                                in_chans, patch, io);
     return cudaGetLastError();
 }
 
@@ -64,7 +65,8 @@ template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int rows, int C, int T, int drop_cls,
-                 float eps) {
+                 float eps, const IoBlock* __restrict__ io) {
+    if (io) out_f32 = io->out.x_remain;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
@@ -108,17 +110,17 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
-                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st) {
+                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st, const IoBlock* io) {
     const int blocks = (rows * 32 + 255) / 256;
     if (C % 128 != 0) return cudaErrorInvalidValue;
     switch (C / 128) {
-        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
-        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps); break;
+        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -161,7 +163,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void __launch_bounds__(256)
 bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab, long long total, int Cz,
                   float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
-                  __nv_bfloat16* __restrict__ zhat_pad, int s4, double* __restrict__ rate_acc, int rows_per_image) {
+                  __nv_bfloat16* __restrict__ zhat_pad, int s4, double* __restrict__ rate_acc, int rows_per_image,
+                  const IoBlock* __restrict__ io) {
+    if (io) { lik_out = io->out.z_likelihoods; sym_out = io->out.z_symbols; zhat_out = io->out.z_hat; }
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float lg = 0.f;
     int n = 0;
@@ -205,13 +209,13 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
 
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
                               float* zhat, __nv_bfloat16* zhat_pad, int s4, double* rate_acc, int rows_per_image,
-                              cudaStream_t st) {
+                              cudaStream_t st, const IoBlock* io) {
     const long long total = rows * Cz;
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(bottleneck_kernel);
     bottleneck_kernel<<<blocks, 256, 0, st>>>(z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4, rate_acc,
-                                              rows_per_image);
+                                              rows_per_image, io);
     return cudaGetLastError();
 }
 
@@ -236,7 +240,8 @@ __global__ void __launch_bounds__(256)
 gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
                       int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_pad,
-                      int ld_pad, int s, double* __restrict__ rate_acc) {
+                      int ld_pad, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
+    if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; }
     const int vec_per_row = cs >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = rows * vec_per_row;
@@ -284,13 +289,13 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
 
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
                                   int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_pad, int ld_pad,
-                                  int s, double* rate_acc, cudaStream_t st) {
+                                  int s, double* rate_acc, cudaStream_t st, const IoBlock* io) {
     const long long total = rows * (cs / 4);
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
     gaussian_slice_kernel<<<blocks, 256, 0, st>>>(y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat, yhat_pad, ld_pad, s,
-                                                  rate_acc);
+                                                  rate_acc, io);
     return cudaGetLastError();
 }
 
@@ -318,7 +323,12 @@ cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* s
 // {sum log2 lik, N*S*S} that the data-parallel all-reduce combines.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N, double pixels_per_image,
-                                     float* __restrict__ bpp, double* __restrict__ rate_sums) {
+                                     float* __restrict__ bpp, double* __restrict__ rate_sums,
+                                     const IoBlock* __restrict__ io) {
+    if (io) {                                  // caller buffers when given, else the workspace defaults passed in
+        if (io->out.bpp) bpp = io->out.bpp;
+        if (io->out.rate_sums) rate_sums = io->out.rate_sums;
+    }
     double tot = 0.0;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         const double a = rate_acc[n];
@@ -337,9 +347,37 @@ __global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N,
     }
 }
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
-                                 double* rate_sums, cudaStream_t st) {
+                                 double* rate_sums, cudaStream_t st, const IoBlock* io) {
     TMAE_CARVEOUT_ONCE(rate_finalize_kernel);
-    rate_finalize_kernel<<<1, 256, 0, st>>>(rate_acc, N, pixels_per_image, bpp, rate_sums);
+    rate_finalize_kernel<<<1, 256, 0, st>>>(rate_acc, N, pixels_per_image, bpp, rate_sums, io);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Optional copies of workspace-resident results into the caller's buffers (pointers read from the IoBlock).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void copy_outputs_kernel(const IoBlock* __restrict__ io, const float4* __restrict__ y, const float4* __restrict__ z,
+                                    const float4* __restrict__ mu, const float4* __restrict__ sigma,
+                                    const float4* __restrict__ yhat, const int64_t* __restrict__ ids_keep, long long n_y4,
+                                    long long n_z4, long long n_ids) {
+    const tmae_outputs o = io->out;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_y4; i += stride) {
+        if (o.y) reinterpret_cast<float4*>(o.y)[i] = y[i];
+        if (o.mu) reinterpret_cast<float4*>(o.mu)[i] = mu[i];
+        if (o.sigma) reinterpret_cast<float4*>(o.sigma)[i] = sigma[i];
+        if (o.y_hat) reinterpret_cast<float4*>(o.y_hat)[i] = yhat[i];
+        if (i < n_z4 && o.z) reinterpret_cast<float4*>(o.z)[i] = z[i];
+        if (i < n_ids && o.ids_keep) o.ids_keep[i] = ids_keep[i];
+    }
+}
+cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* z, const float* mu, const float* sigma,
+                                const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
+                                cudaStream_t st) {
+    TMAE_CARVEOUT_ONCE(copy_outputs_kernel);
+    copy_outputs_kernel<<<296, 256, 0, st>>>(io, reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z),
+                                             reinterpret_cast<const float4*>(mu), reinterpret_cast<const float4*>(sigma),
+                                             reinterpret_cast<const float4*>(yhat), ids_keep, n_y / 4, n_z / 4, n_ids);
     return cudaGetLastError();
 }
 

@@ -4,9 +4,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/tmae.h"
 #include "gemm.cuh"
 
 namespace tmae {
+
+// Per-call pointers of one forward, resident in device memory: kernels captured in a CUDA graph read the caller's
+// buffers through it, so one instantiated graph serves every call of that batch size.
+struct IoBlock {
+    const float* imgs;
+    const float* scores;
+    tmae_outputs out;
+};
 
 // gemm_tc.cu
 cudaError_t gemm_tc_configure();
@@ -16,7 +25,7 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
 
 // mask.cu
 cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int softmax_isa, int64_t* ids_shuffle,
-                               int64_t* ids_restore, int64_t* ids_keep, cudaStream_t st);
+                               int64_t* ids_restore, int64_t* ids_keep, cudaStream_t st, const IoBlock* io = nullptr);
 
 // attention.cu
 cudaError_t attention_configure(int T);
@@ -26,19 +35,23 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
 // elementwise.cu
 cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __nv_bfloat16* patches, float* x,
                                   const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
-                                  int T, int C, int in_chans, int patch, cudaStream_t st);
+                                  int T, int C, int in_chans, int patch, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
-                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st);
+                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
                               float* zhat, __nv_bfloat16* zhat_pad, int s4, double* rate_acc, int rows_per_image,
-                              cudaStream_t st);
+                              cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
                                   int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_pad, int ld_pad,
-                                  int s, double* rate_acc, cudaStream_t st);
+                                  int s, double* rate_acc, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* sigma, long long n, float* lik,
                                  int32_t* sym, float* yhat, cudaStream_t st);
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
-                                 double* rate_sums, cudaStream_t st);
+                                 double* rate_sums, cudaStream_t st, const IoBlock* io = nullptr);
+// copies the workspace-resident results the caller asked for (io->out.{y,z,mu,sigma,y_hat,ids_keep})
+cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* z, const float* mu, const float* sigma,
+                                const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
+                                cudaStream_t st);
 cudaError_t launch_compact_to_pad(const float* src, __nv_bfloat16* dst, long long rows, int C, int s, cudaStream_t st);
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
                                   const int* segc, int shuffle, cudaStream_t st);

@@ -124,7 +124,8 @@ __device__ int block_exclusive_scan(int* a, int len, int* warp_tmp) {
 
 __global__ void __launch_bounds__(kThreads)
 mask_select_kernel(const float* __restrict__ scores, int L, int Lp2, int K, int isa, int64_t* __restrict__ ids_shuffle,
-                   int64_t* __restrict__ ids_restore, int64_t* __restrict__ ids_keep) {
+                   int64_t* __restrict__ ids_restore, int64_t* __restrict__ ids_keep, const IoBlock* __restrict__ io) {
+    if (io) { scores = io->scores; ids_shuffle = io->out.ids_shuffle; ids_restore = io->out.ids_restore; }
     extern __shared__ float smf[];
     float* s = smf;                                   // scores in index order
     float* srt = s + Lp2;                             // ascending, +INF padded
@@ -314,7 +315,7 @@ mask_select_kernel(const float* __restrict__ scores, int L, int Lp2, int K, int 
 }  // namespace
 
 cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int softmax_isa, int64_t* ids_shuffle,
-                               int64_t* ids_restore, int64_t* ids_keep, cudaStream_t st) {
+                               int64_t* ids_restore, int64_t* ids_keep, cudaStream_t st, const IoBlock* io) {
     if (N == 0) return cudaSuccess;
     int Lp2 = 32;
     while (Lp2 < L) Lp2 <<= 1;
@@ -326,7 +327,7 @@ cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int sof
     }
     TMAE_CARVEOUT_ONCE(mask_select_kernel);
     mask_select_kernel<<<N, kThreads, smem, st>>>(scores, L, Lp2, K, softmax_isa == 8 ? 8 : 16, ids_shuffle,
-                                                  ids_restore, ids_keep);
+                                                  ids_restore, ids_keep, io);
     return cudaGetLastError();
 }
 

@@ -67,6 +67,8 @@ struct Plan {
     std::vector<GemmParams> host_params;
     GemmParams* d_params = nullptr;
     bool from_latent_ok = true;
+    cudaGraphExec_t graph = nullptr; // whole forward (steps + output copies), pointers via the device IoBlock
+    int calls = 0;                   // the first call runs plain launches (one-time function attributes), then capture
     int first_rate_step = 0;        // index of the first step of the rate half (h_a)
     int encoder_end_step = 0;       // one past the final LayerNorm
 };
@@ -93,6 +95,7 @@ struct Workspace {
     double* rate_sums = nullptr;
     // host-buffer entry staging
     float *st_imgs = nullptr, *st_scores = nullptr;
+    IoBlock* io = nullptr;           // per-call pointers for graph replays
 };
 
 }  // namespace
@@ -111,6 +114,8 @@ struct tmae_handle {
     std::map<int, std::unique_ptr<Plan>> plans;
     PFN_encodeTiled encode = nullptr;
     std::vector<void*> weight_allocs;
+    bool use_graph = true;           // TMAE_NO_GRAPH=1 disables CUDA-graph replay
+    cudaStream_t cap_stream = nullptr;
     // profiling
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -400,7 +405,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     Workspace& w = h->ws;
     if (N <= w.cap_N) return TMAE_OK;
     // plans hold pointers into the workspace: drop them
-    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    for (auto& kv : h->plans) { if (kv.second->d_params) cudaFree(kv.second->d_params); if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph); }
     h->plans.clear();
     free_pool(w.allocs);
     w = Workspace();
@@ -452,6 +457,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.rate_sums, (size_t)2);
     WS_ALLOC(w.st_imgs, (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size);
     WS_ALLOC(w.st_scores, (size_t)N * h->L);
+    WS_ALLOC(w.io, (size_t)1);
 #undef WS_ALLOC
     w.cap_N = N;
     w.bytes = tot;
@@ -730,6 +736,7 @@ struct RunArgs {
     const float* scores = nullptr;
     const tmae_outputs* out = nullptr;
     int begin = 0, end = 0;
+    const IoBlock* io = nullptr;     // non-null: kernels read the per-call pointers from the device IoBlock
 };
 
 int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
@@ -777,19 +784,19 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_MASK:
                 CUDA_TRY(h, launch_mask_select(a.scores, N, h->L, K, h->cfg.softmax_isa == 8 ? 8 : 16, o.ids_shuffle,
-                                               o.ids_restore, w.ids_keep, st));
+                                               o.ids_restore, w.ids_keep, st, a.io));
                 break;
             case ST_GATHER:
                 CUDA_TRY(h, launch_gather_patches(a.imgs, w.ids_keep, w.patches, w.x, h->vecs["cls_token"],
                                                   h->vecs["encoder_pos_embed"], N, h->cfg.img_size, h->grid_w, K, T, C,
-                                                  h->cfg.in_chans, h->cfg.patch_size, st));
+                                                  h->cfg.in_chans, h->cfg.patch_size, st, a.io));
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, simt, st));
                 break;
             case ST_LN:
                 if (sp.ln_final)
-                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.enc, o.x_remain, N * T, C, T, 1, h->cfg.ln_eps, st));
+                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.enc, o.x_remain, N * T, C, T, 1, h->cfg.ln_eps, st, a.io));
                 else
                     CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.xn, nullptr, N * T, C, T, 0, h->cfg.ln_eps, st));
                 break;
@@ -798,15 +805,15 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_EB:
                 CUDA_TRY(h, launch_bottleneck(w.z, h->eb_tab, (long long)N * h->s4 * h->s4, h->Cz, o.z_likelihoods,
-                                              o.z_symbols, o.z_hat, w.zhat_pad, h->s4, w.rate_acc, h->s4 * h->s4, st));
+                                              o.z_symbols, o.z_hat, w.zhat_pad, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
                 break;
             case ST_GC:
                 CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc * sp.gc_slices,
-                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_pad, h->Cy, s, w.rate_acc, st));
+                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_pad, h->Cy, s, w.rate_acc, st, a.io));
                 break;
             case ST_RATE:
                 CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
-                                                 o.bpp ? o.bpp : w.bpp, o.rate_sums ? o.rate_sums : w.rate_sums, st));
+                                                 o.bpp ? o.bpp : w.bpp, o.rate_sums ? o.rate_sums : w.rate_sums, st, a.io));
                 break;
             case ST_Y_TO_PAD:
                 break;
@@ -829,6 +836,44 @@ int copy_outputs(tmae_handle* h, int N, const tmae_outputs* out, bool rate_half,
         if (out->sigma) CUDA_TRY(h, cudaMemcpyAsync(out->sigma, w.sigma, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
         if (out->y_hat) CUDA_TRY(h, cudaMemcpyAsync(out->y_hat, w.yhat, rk * h->Cy * 4, cudaMemcpyDeviceToDevice, st));
     }
+    return TMAE_OK;
+}
+
+// Whole forward as one CUDA-graph replay: the per-call pointers travel through the device IoBlock, so the graph is
+// captured once per batch size.  Returns TMAE_OK with *done = false when graphs are disabled / profiling is on.
+int run_full_graph(tmae_handle* h, Plan& pl, const float* imgs, const float* scores, const tmae_outputs* out,
+                   cudaStream_t st, bool* done) {
+    *done = false;
+    if (!h->use_graph || h->profiling) return TMAE_OK;
+    if (pl.calls++ == 0) return TMAE_OK;
+    Workspace& w = h->ws;
+    const int N = pl.N;
+    if (!pl.graph) {
+        if (!h->cap_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        RunArgs a;
+        a.begin = 0; a.end = (int)pl.steps.size(); a.io = w.io;
+        int rc = run_steps(h, pl, a, h->cap_stream);
+        if (rc == TMAE_OK) {
+            cudaError_t e = launch_copy_outputs(w.io, w.y, w.z, w.mu, w.sigma, w.yhat, w.ids_keep, (long long)N * h->K * h->Cy,
+                                                (long long)N * h->s4 * h->s4 * h->Cz, (long long)N * h->K, h->cap_stream);
+            if (e != cudaSuccess) rc = fail(h, TMAE_ECUDA, "copy_outputs capture: %s", cudaGetErrorString(e));
+        }
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(h->cap_stream, &g);
+        if (rc != TMAE_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess || !g) return fail(h, TMAE_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&pl.graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { pl.graph = nullptr; return fail(h, TMAE_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    }
+    IoBlock hio;
+    memset(&hio, 0, sizeof(hio));
+    hio.imgs = imgs; hio.scores = scores;
+    if (out) hio.out = *out;
+    CUDA_TRY(h, cudaMemcpyAsync(w.io, &hio, sizeof(hio), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    CUDA_TRY(h, cudaGraphLaunch(pl.graph, st));
+    *done = true;
     return TMAE_OK;
 }
 
@@ -881,6 +926,7 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gemm configure: %s", cudaGetErrorString(e));
     e = attention_configure(h->T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
+    h->use_graph = getenv("TMAE_NO_GRAPH") == nullptr;
     *out = h.release();
     return TMAE_OK;
 }
@@ -889,7 +935,8 @@ void tmae_destroy(tmae_handle* h) {
     if (!h) return;
     cudaDeviceSynchronize();
     for (auto& kv : h->raw) cudaFree(kv.second.ptr);
-    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    for (auto& kv : h->plans) { if (kv.second->d_params) cudaFree(kv.second->d_params); if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph); }
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     free_pool(h->ws.allocs);
     free_pool(h->weight_allocs);
     for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -921,7 +968,7 @@ int tmae_set_weight(tmae_handle* h, const char* name, const void* data, int dtyp
 int tmae_finalize_weights(tmae_handle* h) {
     if (!h) return TMAE_EINVAL;
     // re-finalize: drop previous packs
-    for (auto& kv : h->plans) if (kv.second->d_params) cudaFree(kv.second->d_params);
+    for (auto& kv : h->plans) { if (kv.second->d_params) cudaFree(kv.second->d_params); if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph); }
     h->plans.clear();
     free_pool(h->weight_allocs);
     h->layers.clear();
@@ -1036,6 +1083,9 @@ int tmae_forward(tmae_handle* h, const float* imgs, const float* scores, int N, 
     Plan* pl = nullptr;
     if ((rc = build_plan(h, N, &pl))) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    bool done = false;
+    if ((rc = run_full_graph(h, *pl, imgs, scores, out, st, &done))) return rc;
+    if (done) return TMAE_OK;
     RunArgs a;
     a.imgs = imgs; a.scores = scores; a.out = out; a.begin = 0; a.end = (int)pl->steps.size();
     if (h->profiling) h->prof_used = 0;
@@ -1092,11 +1142,15 @@ int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores
     tmae_outputs o = out ? *out : tmae_outputs{};
     if (!o.bpp) o.bpp = w.bpp;
     if (!o.rate_sums) o.rate_sums = w.rate_sums;
-    RunArgs a;
-    a.imgs = w.st_imgs; a.scores = w.st_scores; a.out = &o; a.begin = 0; a.end = (int)pl->steps.size();
-    if (h->profiling) h->prof_used = 0;
-    if ((rc = run_steps(h, *pl, a, st))) return rc;
-    if ((rc = copy_outputs(h, N, out, true, true, st))) return rc;
+    bool done = false;
+    if ((rc = run_full_graph(h, *pl, w.st_imgs, w.st_scores, &o, st, &done))) return rc;
+    if (!done) {
+        RunArgs a;
+        a.imgs = w.st_imgs; a.scores = w.st_scores; a.out = &o; a.begin = 0; a.end = (int)pl->steps.size();
+        if (h->profiling) h->prof_used = 0;
+        if ((rc = run_steps(h, *pl, a, st))) return rc;
+        if ((rc = copy_outputs(h, N, out, true, true, st))) return rc;
+    }
     if (h_bpp) CUDA_TRY(h, cudaMemcpyAsync(h_bpp, o.bpp, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (h_rate_sums) CUDA_TRY(h, cudaMemcpyAsync(h_rate_sums, o.rate_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     return TMAE_OK;
