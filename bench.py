@@ -170,7 +170,7 @@ def run_b200(args, kwargs, batch, desc, wl):
     S = max(1, args.streams)
     models = []
     for _ in range(S):
-        m_ = MCM(**kwargs, skip_dead_lrp=False)
+        m_ = MCM(**kwargs, skip_dead_lrp=False, share_sm=S > 1)
         m_.load_state_dict(sd)
         m_.cuda().eval()
         models.append(m_)

@@ -65,6 +65,8 @@ typedef struct {
 
 #define TMAE_FLAG_SKIP_DEAD_LRP 1u   /* rate-only: skip lrp_transform[6..11] (their y_hat feeds only g_s) */
 #define TMAE_FLAG_DEBUG_SIMT    2u   /* bring-up only: run GEMM/conv layers on the CUDA-core checker kernel */
+#define TMAE_FLAG_SHARE_SM      4u   /* several handles/streams run concurrently on this GPU: size every launch so that
+                                        CTAs of two kernels can share an SM (<= half the shared memory each) */
 
 /* Outputs of one forward; any pointer may be NULL (that output is skipped).
  * N = batch, L = (img/patch)^2, K = num_keep_patches, s = sqrt(K), Cy = latent_depth, Cz = hyperprior_depth. */

@@ -13,6 +13,7 @@ LIB_PATH = _PKG / "libtmae_b200.so"
 TMAE_OK, TMAE_EINVAL, TMAE_ECUDA, TMAE_ESTATE, TMAE_ENOMEM = 0, 1, 2, 3, 4
 FLAG_SKIP_DEAD_LRP = 1
 FLAG_DEBUG_SIMT = 2
+FLAG_SHARE_SM = 4
 
 
 class TmaeConfig(C.Structure):

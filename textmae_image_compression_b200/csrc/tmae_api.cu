@@ -792,7 +792,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                                                   h->cfg.in_chans, h->cfg.patch_size, st, a.io));
                 break;
             case ST_GEMM:
-                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, simt, st));
+                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st));
                 break;
             case ST_LN:
                 if (sp.ln_final)
@@ -1196,31 +1196,31 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
     const int ctas = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + p.block_n - 1) / p.block_n);
     long long* dticks = nullptr;
     if (timing) {
-        cudaMalloc(reinterpret_cast<void**>(&dticks), (size_t)ctas * 8 * sizeof(long long));
-        cudaMemset(dticks, 0, (size_t)ctas * 8 * sizeof(long long));
+        cudaMalloc(reinterpret_cast<void**>(&dticks), (size_t)ctas * 16 * sizeof(long long));
+        cudaMemset(dticks, 0, (size_t)ctas * 16 * sizeof(long long));
         p.dbg_ticks = dticks;
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
-    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, impl == 1, st);
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, impl == 1, false, st);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
         cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, st);
-        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, st);
+        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, st);
         cudaEventRecord(ev1, st);
         cudaStreamSynchronize(st);
         float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
-        std::vector<long long> t((size_t)ctas * 8);
+        std::vector<long long> t((size_t)ctas * 16);
         cudaMemcpy(t.data(), dticks, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
         long long tmin = t[0], tend = 0;
-        for (int c = 0; c < ctas; ++c) { if (t[c * 8] < tmin) tmin = t[c * 8]; if (t[c * 8 + 7] > tend) tend = t[c * 8 + 7]; }
-        double avg[8] = {0};
-        for (int c = 0; c < ctas; ++c) for (int k = 1; k < 8; ++k) avg[k] += (double)(t[c * 8 + k] - t[c * 8]) / ctas;
-        int smem = 0; const int stages = gemm_pick_stages(p.block_n, ctas, &smem);
+        for (int c = 0; c < ctas; ++c) { if (t[c * 16] < tmin) tmin = t[c * 16]; if (t[c * 16 + 6] > tend) tend = t[c * 16 + 6]; }
+        double avg[16] = {0};
+        for (int c = 0; c < ctas; ++c) for (int k = 1; k < 12; ++k) avg[k] += (double)(t[c * 16 + k] - t[c * 16]) / ctas;
+        int smem = 0; const int stages = gemm_pick_stages(p.block_n, ctas, false, &smem);
         fprintf(stderr, "[gemm timing] M=%d N=%d Kb=%d taps=%d bn=%d ctas=%d stages=%d smem=%d | kernel %.1f us (events), first-start..last-end %.1f us | "
-                "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f, exit %.0f\n",
+                "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f | first chunk: ldtm_done %.0f, staged %.0f, batch0 %.0f, batch1 %.0f\n",
                 p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, smem, ms * 1e3,
-                (tend - tmin) * 1e-3, avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[7]);
+                (tend - tmin) * 1e-3, avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[8], avg[9], avg[10], avg[11]);
         // steady-state cost of back-to-back dependent launches of this kernel: plain stream vs CUDA graph
         {
             p.dbg_ticks = nullptr;
@@ -1228,14 +1228,14 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
             const int reps = 50;
             cudaStreamSynchronize(st);
             cudaEventRecord(ev0, st);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, st);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, st);
             cudaEventRecord(ev1, st);
             cudaStreamSynchronize(st);
             float ms_plain = 0; cudaEventElapsedTime(&ms_plain, ev0, ev1);
             cudaStream_t cs; cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
             cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
             cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, cs);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, cs);
             cudaStreamEndCapture(cs, &graph);
             float ms_graph = -1;
             if (graph && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {

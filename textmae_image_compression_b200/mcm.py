@@ -32,7 +32,7 @@ class MCM(nn.Module):
                  encoder_num_heads=12, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, mlp_ratio=4.0,
                  norm_layer=None, norm_pix_loss=False, latent_depth=384, hyperprior_depth=192, num_slices=12,
                  num_keep_patches=144, *, skip_dead_lrp: bool = False, debug_simt: bool = False,
-                 softmax_isa: Optional[int] = None, extra_outputs: bool = False):
+                 softmax_isa: Optional[int] = None, extra_outputs: bool = False, share_sm: bool = False):
         super().__init__()
         self.cfg = PathConfig(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
                               encoder_embed_dim=encoder_embed_dim, encoder_depth=encoder_depth,
@@ -45,6 +45,7 @@ class MCM(nn.Module):
         self.norm_pix_loss = norm_pix_loss
         self.skip_dead_lrp = skip_dead_lrp
         self.debug_simt = debug_simt
+        self.share_sm = share_sm                 # several handles/streams in flight on this GPU (see TMAE_FLAG_SHARE_SM)
         self.extra_outputs = extra_outputs       # also return y, z, mu, sigma, x_remain (parity tests)
         if softmax_isa is None:
             # lane order of the ATen CPU softmax the reference's host routine would have used on this machine
@@ -114,7 +115,8 @@ class MCM(nn.Module):
         lib = _native.load()
         self._release()
         c = self.cfg
-        flags = (_native.FLAG_SKIP_DEAD_LRP if self.skip_dead_lrp else 0) | (_native.FLAG_DEBUG_SIMT if self.debug_simt else 0)
+        flags = ((_native.FLAG_SKIP_DEAD_LRP if self.skip_dead_lrp else 0) | (_native.FLAG_DEBUG_SIMT if self.debug_simt else 0)
+                 | (_native.FLAG_SHARE_SM if self.share_sm else 0))
         cfg = _native.TmaeConfig(c.img_size, c.patch_size, c.in_chans, c.encoder_embed_dim, c.encoder_depth,
                                  c.encoder_num_heads, c.decoder_embed_dim, c.mlp_ratio, c.latent_depth,
                                  c.hyperprior_depth, c.num_slices, c.num_keep_patches, c.ln_eps, self.softmax_isa, flags)
