@@ -105,6 +105,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// explicit shared-space vector accesses (a pointer derived from the manually aligned dynamic-smem base is a generic
+// pointer to the compiler, which would emit slower generic LD/ST for it)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // 32-bit shared-address variants for the hot loops (no generic->shared conversion per call)
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
     uint32_t ok;

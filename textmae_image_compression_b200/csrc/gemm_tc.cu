@@ -196,7 +196,13 @@ constexpr int kGemmThreads = 320;                     // warp 0 TMA, warp 1 MMA,
 constexpr int kEpiPitch = 36;                         // floats per staged accumulator row (32 + 4 pad)
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 
-template <int ACT>
+// EPI selects a compile-time specialisation of the store phase:
+//   EPI_GENERIC        any row map / two outputs / gathered residual (patch embed, g_a.6, strided, PixelShuffle, mu/sigma, LRP)
+//   EPI_BF16_SAME      one bf16 output at the accumulator's own row (QKV, fc1, g_a.0-4, every conv mid layer)
+//   EPI_F32_SAME_RESID one fp32 output at the accumulator's own row with an fp32 residual at the same row (proj, fc2)
+enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2 };
+
+template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     const GemmParams& p = params[blockIdx.z];
@@ -328,7 +334,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         const RowCtx r = decode_row(e, m);
         const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
         const int cq = e.N >> 2;
-        float* stage_tile = reinterpret_cast<float*>(smem) + (size_t)(warp - 2) * 32 * kEpiPitch;
+        const uint32_t stage_a = smem_base + (uint32_t)(warp - 2) * 32u * kEpiPitch * 4u;   // this warp's staging tile
         const int rsub = lane >> 3, c4 = (lane & 7) * 4;
         // mapped rows of THIS thread's accumulator row (quadrant-dependent ones are refreshed per chunk)
         int my_rrow = e.resid ? (int)map_row(e, e.resid_map, r, 0) : -1;
@@ -342,6 +348,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         };
         float4 bias_next = load_bias(half * 32);
         const bool has_resid = e.resid != nullptr;
+        const unsigned valid_mask = __ballot_sync(0xffffffffu, r.valid != 0);   // rows of this quarter that produce output
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
@@ -362,8 +369,8 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
             if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[8] = globaltimer_ns();
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4)
-                *reinterpret_cast<uint4*>(stage_tile + lane * kEpiPitch + g4 * 4) =
-                    make_uint4(acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2], acc[g4 * 4 + 3]);
+                sts128(stage_a + (uint32_t)(lane * kEpiPitch + g4 * 4) * 4u, acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2],
+                       acc[g4 * 4 + 3]);
             const int colbase = n0 + c0;
             int q = 0;
             if (shuf) {                                               // cq % 32 == 0 for PixelShuffle layers
@@ -376,6 +383,57 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
             const int col = colbase + c4;
             const bool col_ok = col < e.N && c0 + c4 < block_n;
             const int ocol = col - q * (shuf ? cq : 0);
+            if (EPI == EPI_BF16_SAME) {
+                if (col_ok) {
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) +
+                                         (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
+                    const long long step = 4ll * e.out[0].ld;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it, dst += step) {
+                        const int rr = it * 4 + rsub;
+                        if ((valid_mask >> rr) & 1u) {
+                            const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                            uint2 pk;
+                            pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
+                            pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
+                            *reinterpret_cast<uint2*>(dst) = pk;
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
+            if (EPI == EPI_F32_SAME_RESID) {
+                if (col_ok) {
+                    const long long off0 = (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
+                    const long long step = 4ll * e.out[0].ld;
+                    float* dst = reinterpret_cast<float*>(e.out[0].ptr) + off0;
+                    const float* src = e.resid + (long long)(m0 + quarter * 32 + rsub) * e.resid_ld + col;
+                    const long long rstep = 4ll * e.resid_ld;
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        float4 rs[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = (hb * 4 + j) * 4 + rsub;
+                            rs[j] = ((valid_mask >> rr) & 1u) ? *reinterpret_cast<const float4*>(src + (hb * 4 + j) * rstep)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int rr = (hb * 4 + j) * 4 + rsub;
+                            if ((valid_mask >> rr) & 1u) {
+                                const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                                *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) =
+                                    make_float4(act_fast<ACT>(t4.x + b4.x) + rs[j].x, act_fast<ACT>(t4.y + b4.y) + rs[j].y,
+                                                act_fast<ACT>(t4.z + b4.z) + rs[j].z, act_fast<ACT>(t4.w + b4.w) + rs[j].w);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                continue;
+            }
 #pragma unroll
             for (int hb = 0; hb < 2; ++hb) {                          // two batches of 4 row-groups: loads first, then math
                 int rrow[4], orow0[4], orow1[4];
@@ -393,7 +451,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
                         rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (has_resid)                                 // clamped row: always a valid address
                             rs[j] = *reinterpret_cast<const float4*>(e.resid + (long long)max(rrow[j], 0) * e.resid_ld + ocol);
-                        t4[j] = *reinterpret_cast<const float4*>(stage_tile + ((hb * 4 + j) * 4 + rsub) * kEpiPitch + c4);
+                        t4[j] = lds128(stage_a + (uint32_t)(((hb * 4 + j) * 4 + rsub) * kEpiPitch + c4) * 4u);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -477,20 +535,34 @@ int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes
     return stages;
 }
 
+template <int ACT, int EPI>
+static cudaError_t configure_one() {
+    prefer_max_smem_carveout(gemm_tc_kernel<ACT, EPI>);
+    return cudaFuncSetAttribute(gemm_tc_kernel<ACT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 cudaError_t gemm_tc_configure() {
-    prefer_max_smem_carveout(gemm_tc_kernel<ACT_NONE>);
-    prefer_max_smem_carveout(gemm_tc_kernel<ACT_GELU>);
-    prefer_max_smem_carveout(gemm_tc_kernel<ACT_HALF_TANH>);
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gemm_tc_kernel<ACT_HALF_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e;
+    if ((e = configure_one<ACT_NONE, EPI_GENERIC>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_GELU, EPI_GENERIC>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_HALF_TANH, EPI_GENERIC>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_NONE, EPI_BF16_SAME>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_GELU, EPI_BF16_SAME>()) != cudaSuccess) return e;
+    return configure_one<ACT_NONE, EPI_F32_SAME_RESID>();
+}
+
+// Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).
+int gemm_epi_kind(const GemmParams& p) {
+    const bool one_out = p.out[1].dtype == OUT_NONE && p.out[0].map == MAP_SAME;
+    if (one_out && p.out[0].dtype == OUT_BF16 && p.resid == nullptr && p.act != ACT_HALF_TANH) return EPI_BF16_SAME;
+    if (one_out && p.out[0].dtype == OUT_F32 && p.resid != nullptr && p.resid_map == MAP_SAME && p.act == ACT_NONE)
+        return EPI_F32_SAME_RESID;
+    return EPI_GENERIC;
 }
 
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
-cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, bool simt,
-                        bool share_sm, cudaStream_t stream) {
+cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
+                        bool simt, bool share_sm, cudaStream_t stream) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
         gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
@@ -499,11 +571,13 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem);
-    switch (act) {            // every member of a grouped launch shares the activation
-        case ACT_GELU: gemm_tc_kernel<ACT_GELU><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
-        case ACT_HALF_TANH: gemm_tc_kernel<ACT_HALF_TANH><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
-        default: gemm_tc_kernel<ACT_NONE><<<grid, kGemmThreads, smem, stream>>>(d_params, stages); break;
-    }
+    // every member of a grouped launch shares the activation and the store-phase specialisation
+    if (epi == EPI_BF16_SAME && act == ACT_GELU) gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    else if (epi == EPI_BF16_SAME && act == ACT_NONE) gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    else if (act == ACT_GELU) gemm_tc_kernel<ACT_GELU, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    else if (act == ACT_HALF_TANH) gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    else gemm_tc_kernel<ACT_NONE, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
     return cudaGetLastError();
 }
 

@@ -20,8 +20,9 @@ struct IoBlock {
 // gemm_tc.cu
 cudaError_t gemm_tc_configure();
 int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes);
-cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, bool simt,
-                        bool share_sm, cudaStream_t stream);
+int gemm_epi_kind(const GemmParams& p);
+cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
+                        bool simt, bool share_sm, cudaStream_t stream);
 
 // mask.cu
 cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int softmax_isa, int64_t* ids_shuffle,

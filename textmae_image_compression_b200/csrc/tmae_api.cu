@@ -50,7 +50,7 @@ struct Step {
     StepKind kind;
     int family = FAM_MISC;
     // GEMM
-    int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0;
+    int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0, epi = 0;
     double flops = 0, bytes = 0;
     // LN
     const float* ln_gamma = nullptr;
@@ -502,6 +502,8 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         GemmParams p;
         int rc = fill_params(h, descs[g], groups, &p, bn);
         if (rc) return rc;
+        const int ek = gemm_epi_kind(p);
+        if (g == 0) st.epi = ek; else if (ek != st.epi) st.epi = 0;     // mixed group -> generic store phase
         pl.host_params.push_back(p);
         st.flops += descs[g].flops;
     }
@@ -792,7 +794,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                                                   h->cfg.in_chans, h->cfg.patch_size, st, a.io));
                 break;
             case ST_GEMM:
-                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st));
+                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st));
                 break;
             case ST_LN:
                 if (sp.ln_final)
@@ -1201,12 +1203,12 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
         p.dbg_ticks = dticks;
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
-    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, impl == 1, false, st);
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
         cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, st);
-        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, st);
+        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st);
         cudaEventRecord(ev1, st);
         cudaStreamSynchronize(st);
         float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
@@ -1228,14 +1230,14 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
             const int reps = 50;
             cudaStreamSynchronize(st);
             cudaEventRecord(ev0, st);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, st);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st);
             cudaEventRecord(ev1, st);
             cudaStreamSynchronize(st);
             float ms_plain = 0; cudaEventElapsedTime(&ms_plain, ev0, ev1);
             cudaStream_t cs; cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
             cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
             cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, false, false, cs);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, cs);
             cudaStreamEndCapture(cs, &graph);
             float ms_graph = -1;
             if (graph && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
