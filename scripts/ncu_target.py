@@ -16,3 +16,7 @@ for _ in range(nfwd):
     out = m(imgs, scores)
 torch.cuda.synchronize()
 print("bpp", out["bpp"][:4].tolist())
+n = m.launch_count(batch)
+print("launches_per_forward", n - 1)          # every plan step is one kernel except the rate-accumulator memset
+m.profile(True); m(imgs, scores); torch.cuda.synchronize()
+print("gemm_per_forward", sum(1 for s_ in m.profile_read_steps() if s_["ctas"] > 0))

@@ -201,3 +201,22 @@ def test_error_classes_on_device(cuda_dev):
         m(torch.rand(1, 3, 32, 32).cuda(), torch.rand(1, 16).cuda())         # timm PatchEmbed size assert
     with pytest.raises(ValueError):
         m(torch.rand(1, 3, 64, 64).cuda(), torch.rand(1, 8).cuda())          # K > len(scores) (MCM.py:374-376)
+
+
+def test_vit_large_512_against_oracle(cuda_dev):
+    """BASELINE.json config 4 geometry (ViT-L/16, 512x512, K=256, L=1024, T=257) at batch 2 against the fp32 oracle."""
+    from textmae_image_compression_b200 import vit_large
+    cfg = vit_large(256, 512)
+    kwargs = dict(img_size=512, encoder_embed_dim=1024, encoder_depth=24, encoder_num_heads=16, num_keep_patches=256)
+    sd = make_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand(2, 3, 512, 512, generator=g)
+    scores = torch.rand(2, cfg.num_patches, generator=g)
+    scores[1] = torch.round(scores[1] * 40) / 40
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(kwargs, sd, cuda_dev)
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    _compare("vitL_K256_512", out, ref, cfg, bpp_tol=0.005)
+    del m
+    torch.cuda.empty_cache()
