@@ -202,6 +202,160 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 //   EPI_F32_SAME_RESID one fp32 output at the accumulator's own row with an fp32 residual at the same row (proj, fc2)
 enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2 };
 
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue of one 128 x block_n accumulator tile, executed by the 8 epilogue warps (warp index 2..9; TMEM lane
+// quarter = warp % 4, two warps per quarter alternate 32-column chunks).
+// Phase 1 (thread = accumulator row): TMEM -> registers -> smem staging tile (raw fp32 accumulators).
+// Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): + bias, activation, residual add,
+// coalesced 64 / 128-byte row segments to global memory.
+// ---------------------------------------------------------------------------------------------------------
+template <int ACT, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m0, int n0, int block_n, uint32_t tmem_acc,
+                                              uint32_t stage_base, int warp, int lane, uint64_t* wait_bar,
+                                              uint32_t wait_parity, long long* ticks, int nsub = 2) {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                  // which of the `nsub` warps of this TMEM lane quarter
+    const int cstride = 32 * nsub;
+    const int m = m0 + quarter * 32 + lane;
+    const RowCtx r = decode_row(e, m);
+    const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
+    const int cq = e.N >> 2;
+    const uint32_t stage_a = stage_base + (uint32_t)(warp - 2) * 32u * kEpiPitch * 4u;   // this warp's staging tile
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    // mapped rows of THIS thread's accumulator row (quadrant-dependent ones are refreshed per chunk)
+    int my_rrow = e.resid ? (int)map_row(e, e.resid_map, r, 0) : -1;
+    int my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, 0) : -1;
+    int my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, 0) : -1;
+    // bias of this lane's 4 channels for each of its (up to 4) column chunks: fetched before the accumulator wait
+    auto load_bias = [&](int c0) {
+        const int col = n0 + c0 + c4;
+        return (c0 + c4 < block_n && col < e.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 bias_next = load_bias(half * 32);
+    const bool has_resid = e.resid != nullptr;
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, r.valid != 0);   // rows of this quarter that produce output
+    mbar_wait(wait_bar, wait_parity);
+    tc_fence_after();
+    if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
+    const uint32_t lane_base = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = half * 32; c0 < block_n; c0 += cstride) {
+        const float4 b4 = bias_next;
+        bias_next = load_bias(c0 + cstride);                        // prefetch for the next chunk of this warp
+        uint32_t acc[32];
+        if (block_n - c0 >= 32) {
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
+        } else {                                  // block_n is a multiple of 16
+            uint32_t a16[16];
+            tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, a16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { acc[i] = a16[i]; acc[16 + i] = 0u; }
+        }
+        tmem_ld_wait();
+        if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[8] = globaltimer_ns();
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4)
+            sts128(stage_a + (uint32_t)(lane * kEpiPitch + g4 * 4) * 4u, acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2],
+                   acc[g4 * 4 + 3]);
+        const int colbase = n0 + c0;
+        int q = 0;
+        if (shuf) {                                               // cq % 32 == 0 for PixelShuffle layers
+            q = colbase / cq;
+            my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, q) : -1;
+            my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, q) : -1;
+        }
+        __syncwarp();
+        if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[9] = globaltimer_ns();
+        const int col = colbase + c4;
+        const bool col_ok = col < e.N && c0 + c4 < block_n;
+        const int ocol = col - q * (shuf ? cq : 0);
+        if (EPI == EPI_BF16_SAME) {
+            if (col_ok) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) +
+                                     (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
+                const long long step = 4ll * e.out[0].ld;
+#pragma unroll
+                for (int it = 0; it < 8; ++it, dst += step) {
+                    const int rr = it * 4 + rsub;
+                    if ((valid_mask >> rr) & 1u) {
+                        const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                        uint2 pk;
+                        pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
+                        pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
+                        *reinterpret_cast<uint2*>(dst) = pk;
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+        if (EPI == EPI_F32_SAME_RESID) {
+            if (col_ok) {
+                const long long off0 = (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
+                const long long step = 4ll * e.out[0].ld;
+                float* dst = reinterpret_cast<float*>(e.out[0].ptr) + off0;
+                const float* src = e.resid + (long long)(m0 + quarter * 32 + rsub) * e.resid_ld + col;
+                const long long rstep = 4ll * e.resid_ld;
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    float4 rs[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = (hb * 4 + j) * 4 + rsub;
+                        rs[j] = ((valid_mask >> rr) & 1u) ? *reinterpret_cast<const float4*>(src + (hb * 4 + j) * rstep)
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = (hb * 4 + j) * 4 + rsub;
+                        if ((valid_mask >> rr) & 1u) {
+                            const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                            *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) =
+                                make_float4(act_fast<ACT>(t4.x + b4.x) + rs[j].x, act_fast<ACT>(t4.y + b4.y) + rs[j].y,
+                                            act_fast<ACT>(t4.z + b4.z) + rs[j].z, act_fast<ACT>(t4.w + b4.w) + rs[j].w);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            continue;
+        }
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {                          // two batches of 4 row-groups: loads first, then math
+            int rrow[4], orow0[4], orow1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rr = (hb * 4 + j) * 4 + rsub;
+                rrow[j] = __shfl_sync(0xffffffffu, my_rrow, rr);
+                orow0[j] = __shfl_sync(0xffffffffu, my_orow0, rr);
+                orow1[j] = __shfl_sync(0xffffffffu, my_orow1, rr);
+            }
+            if (col_ok) {
+                float4 rs[4], t4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_resid)                                 // clamped row: always a valid address
+                        rs[j] = *reinterpret_cast<const float4*>(e.resid + (long long)max(rrow[j], 0) * e.resid_ld + ocol);
+                    t4[j] = lds128(stage_a + (uint32_t)(((hb * 4 + j) * 4 + rsub) * kEpiPitch + c4) * 4u);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[4];
+                    v[0] = act_fast<ACT>(t4[j].x + b4.x) + rs[j].x;
+                    v[1] = act_fast<ACT>(t4[j].y + b4.y) + rs[j].y;
+                    v[2] = act_fast<ACT>(t4[j].z + b4.z) + rs[j].z;
+                    v[3] = act_fast<ACT>(t4[j].w + b4.w) + rs[j].w;
+                    store_out4(e.out[0], orow0[j], ocol, v);
+                    store_out4(e.out[1], orow1[j], ocol, v);
+                }
+            }
+            if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[10 + hb] = globaltimer_ns();
+        }
+        __syncwarp();
+    }
+}
+
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
@@ -327,153 +481,150 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         // Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): + bias, activation,
         // residual add, coalesced 64 / 128-byte row segments to global memory.  The staging tiles reuse the (now
         // idle) pipeline buffers: accum_bar completes only after every MMA has finished reading them.
+        // The staging tiles reuse the (now idle) pipeline buffers: accum_bar completes only after every MMA has
+        // finished reading them.
         const EpiCtx e = load_epi(p);
-        const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
-        const int m = m0 + quarter * 32 + lane;
-        const RowCtx r = decode_row(e, m);
-        const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
-        const int cq = e.N >> 2;
-        const uint32_t stage_a = smem_base + (uint32_t)(warp - 2) * 32u * kEpiPitch * 4u;   // this warp's staging tile
-        const int rsub = lane >> 3, c4 = (lane & 7) * 4;
-        // mapped rows of THIS thread's accumulator row (quadrant-dependent ones are refreshed per chunk)
-        int my_rrow = e.resid ? (int)map_row(e, e.resid_map, r, 0) : -1;
-        int my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, 0) : -1;
-        int my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, 0) : -1;
-        // bias of this lane's 4 channels for each of its (up to 4) column chunks: fetched before the accumulator wait
-        auto load_bias = [&](int c0) {
-            const int col = n0 + c0 + c4;
-            return (c0 + c4 < block_n && col < e.N) ? __ldg(reinterpret_cast<const float4*>(e.bias + col))
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        float4 bias_next = load_bias(half * 32);
-        const bool has_resid = e.resid != nullptr;
-        const unsigned valid_mask = __ballot_sync(0xffffffffu, r.valid != 0);   // rows of this quarter that produce output
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        for (int c0 = half * 32; c0 < block_n; c0 += 64) {
-            const float4 b4 = bias_next;
-            bias_next = load_bias(c0 + 64);                             // prefetch for the next chunk of this warp
-            uint32_t acc[32];
-            if (block_n - c0 >= 32) {
-                tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
-            } else {                                  // block_n is a multiple of 16
-                uint32_t a16[16];
-                tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, a16);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { acc[i] = a16[i]; acc[16 + i] = 0u; }
-            }
-            tmem_ld_wait();
-            if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[8] = globaltimer_ns();
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4)
-                sts128(stage_a + (uint32_t)(lane * kEpiPitch + g4 * 4) * 4u, acc[g4 * 4], acc[g4 * 4 + 1], acc[g4 * 4 + 2],
-                       acc[g4 * 4 + 3]);
-            const int colbase = n0 + c0;
-            int q = 0;
-            if (shuf) {                                               // cq % 32 == 0 for PixelShuffle layers
-                q = colbase / cq;
-                my_orow0 = e.out[0].dtype != OUT_NONE ? (int)map_row(e, e.out[0].map, r, q) : -1;
-                my_orow1 = e.out[1].dtype != OUT_NONE ? (int)map_row(e, e.out[1].map, r, q) : -1;
-            }
-            __syncwarp();
-            if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[9] = globaltimer_ns();
-            const int col = colbase + c4;
-            const bool col_ok = col < e.N && c0 + c4 < block_n;
-            const int ocol = col - q * (shuf ? cq : 0);
-            if (EPI == EPI_BF16_SAME) {
-                if (col_ok) {
-                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) +
-                                         (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
-                    const long long step = 4ll * e.out[0].ld;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it, dst += step) {
-                        const int rr = it * 4 + rsub;
-                        if ((valid_mask >> rr) & 1u) {
-                            const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                            uint2 pk;
-                            pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
-                            pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
-                            *reinterpret_cast<uint2*>(dst) = pk;
-                        }
-                    }
-                }
-                __syncwarp();
-                continue;
-            }
-            if (EPI == EPI_F32_SAME_RESID) {
-                if (col_ok) {
-                    const long long off0 = (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
-                    const long long step = 4ll * e.out[0].ld;
-                    float* dst = reinterpret_cast<float*>(e.out[0].ptr) + off0;
-                    const float* src = e.resid + (long long)(m0 + quarter * 32 + rsub) * e.resid_ld + col;
-                    const long long rstep = 4ll * e.resid_ld;
-#pragma unroll
-                    for (int hb = 0; hb < 2; ++hb) {
-                        float4 rs[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int rr = (hb * 4 + j) * 4 + rsub;
-                            rs[j] = ((valid_mask >> rr) & 1u) ? *reinterpret_cast<const float4*>(src + (hb * 4 + j) * rstep)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int rr = (hb * 4 + j) * 4 + rsub;
-                            if ((valid_mask >> rr) & 1u) {
-                                const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                                *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) =
-                                    make_float4(act_fast<ACT>(t4.x + b4.x) + rs[j].x, act_fast<ACT>(t4.y + b4.y) + rs[j].y,
-                                                act_fast<ACT>(t4.z + b4.z) + rs[j].z, act_fast<ACT>(t4.w + b4.w) + rs[j].w);
-                            }
-                        }
-                    }
-                }
-                __syncwarp();
-                continue;
-            }
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {                          // two batches of 4 row-groups: loads first, then math
-                int rrow[4], orow0[4], orow1[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = (hb * 4 + j) * 4 + rsub;
-                    rrow[j] = __shfl_sync(0xffffffffu, my_rrow, rr);
-                    orow0[j] = __shfl_sync(0xffffffffu, my_orow0, rr);
-                    orow1[j] = __shfl_sync(0xffffffffu, my_orow1, rr);
-                }
-                if (col_ok) {
-                    float4 rs[4], t4[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        rs[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (has_resid)                                 // clamped row: always a valid address
-                            rs[j] = *reinterpret_cast<const float4*>(e.resid + (long long)max(rrow[j], 0) * e.resid_ld + ocol);
-                        t4[j] = lds128(stage_a + (uint32_t)(((hb * 4 + j) * 4 + rsub) * kEpiPitch + c4) * 4u);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[4];
-                        v[0] = act_fast<ACT>(t4[j].x + b4.x) + rs[j].x;
-                        v[1] = act_fast<ACT>(t4[j].y + b4.y) + rs[j].y;
-                        v[2] = act_fast<ACT>(t4[j].z + b4.z) + rs[j].z;
-                        v[3] = act_fast<ACT>(t4[j].w + b4.w) + rs[j].w;
-                        store_out4(e.out[0], orow0[j], ocol, v);
-                        store_out4(e.out[1], orow1[j], ocol, v);
-                    }
-                }
-                if (ticks && warp == 2 && lane == 0 && c0 == half * 32) ticks[10 + hb] = globaltimer_ns();
-            }
-            __syncwarp();
-        }
+        epilogue_tile<ACT, EPI>(e, m0, n0, block_n, tmem_base, smem_base, warp, lane, accum_bar, 0u, ticks);
         if (ticks && warp == 2 && lane == 0) ticks[6] = globaltimer_ns();
     }
     tc_fence_before();
     __syncthreads();
     if (ticks && threadIdx.x == 0) ticks[7] = globaltimer_ns();
     if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent variant for launches with several tiles per SM (encoder QKV / fc1): one CTA per SM walks a static
+// round-robin tile list; the smem pipeline runs straight across tile boundaries and the accumulator is double
+// buffered in TMEM (2 x 256 columns), so the epilogue of tile i overlaps the main loop of tile i+1.
+//   barriers: full/empty[stages] (TMA <-> MMA), tfull/tempty[2] (MMA <-> epilogue)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPersistEpiWarps = 16;                       // 4 warps per TMEM lane quarter: the GELU epilogue of fc1 is issue bound
+constexpr int kPersistThreads = 64 + 32 * kPersistEpiWarps;
+constexpr int kEpiStageBytes = kPersistEpiWarps * 32 * kEpiPitch * 4;   // dedicated staging tiles (the pipeline never idles here)
+
+template <int ACT, int EPI>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int m_tiles, int n_tiles) {
+    const GemmParams& p = params[0];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int block_n = p.block_n;
+    const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
+    uint8_t* pipe = smem + kEpiStageBytes;                    // a multiple of 1024 B: the stages keep their swizzle alignment
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(pipe + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tfull_bar = empty_bar + stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    int* sm_tap = reinterpret_cast<int*>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int kb_per_tap = 0;
+    for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
+    const int total_kb = kb_per_tap * p.num_taps;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kPersistEpiWarps); }
+        fence_barrier_init();
+        for (int sg = 0; sg < p.num_segs; ++sg) tma_prefetch_desc(&p.a_map[sg]);
+        tma_prefetch_desc(&p.b_map);
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+    if (warp == 2 && lane < kMaxTaps) sm_tap[lane] = lane < p.num_taps ? p.tap_off[lane] : 0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t pipe_base = smem_u32(pipe);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+
+    if (warp == 0) {
+        // ===== TMA producer (warp-uniform) =====
+        const int nseg = p.num_segs;
+        const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
+        const void* map0 = &p.a_map[0];
+        const void* map1 = &p.a_map[1];
+        const void* map2 = &p.a_map[2];
+        const void* mapb = &p.b_map;
+        const uint32_t tx_bytes = (uint32_t)stage_bytes;
+        int stage = 0;
+        uint32_t phase = 0, stage_off = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * block_n;
+            int sg = 0, k = 0, tap = 0, skb_cur = skb0;
+            const void* map_cur = map0;
+            int row = m0 + sm_tap[0];
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t fb = full_a + 8u * stage;
+                    mbar_arrive_expect_tx_a(fb, tx_bytes);
+                    tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
+                    tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
+                }
+                __syncwarp();
+                if (++k == skb_cur) {
+                    k = 0;
+                    if (++sg == nseg) { sg = 0; ++tap; row = m0 + sm_tap[tap < kMaxTaps ? tap : 0]; }
+                    skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+                    map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+                }
+                stage_off += (uint32_t)stage_bytes;
+                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (warp-uniform) =====
+        const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+        const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);
+        int stage = 0, it = 0;
+        uint32_t phase = 0, stage_off = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&tempty_bar[buf], acc_phase ^ 1u);           // epilogue has drained this accumulator buffer
+            tc_fence_after();
+            const uint32_t tmem_acc = tmem_base + (uint32_t)buf * 256u;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait_a(full_a + 8u * stage, phase);
+                tc_fence_after();
+                const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
+                const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_a(empty_a + 8u * stage);
+                    if (kb == total_kb - 1) umma_commit(&tfull_bar[buf]);
+                }
+                __syncwarp();
+                stage_off += (uint32_t)stage_bytes;
+                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+            }
+        }
+    } else {
+        // ===== epilogue warps =====
+        const EpiCtx e = load_epi(p);
+        const uint32_t stage_base = smem_u32(smem);
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * block_n;
+            epilogue_tile<ACT, EPI>(e, m0, n0, block_n, tmem_base + (uint32_t)buf * 256u, stage_base, warp, lane,
+                                    &tfull_bar[buf], acc_phase, nullptr, kPersistEpiWarps / 4);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[buf]);           // one arrival per epilogue warp frees the buffer
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -548,7 +699,17 @@ cudaError_t gemm_tc_configure() {
     if ((e = configure_one<ACT_HALF_TANH, EPI_GENERIC>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_NONE, EPI_BF16_SAME>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_GELU, EPI_BF16_SAME>()) != cudaSuccess) return e;
-    return configure_one<ACT_NONE, EPI_F32_SAME_RESID>();
+    if ((e = configure_one<ACT_NONE, EPI_F32_SAME_RESID>()) != cudaSuccess) return e;
+    prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>);
+    prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>);
+    if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// Persistent launch qualifies: one group, bf16 same-row output, more tiles than 2 per SM.
+bool gemm_use_persistent(int groups, int epi, int act, int tiles) {
+    static const bool off = getenv("TMAE_NO_PERSISTENT") != nullptr;
+    return !off && groups == 1 && epi == EPI_BF16_SAME && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
 }
 
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).
@@ -570,6 +731,18 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     }
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
+    if (gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y))) {
+        const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
+        const int overhead = 1024 + 256 + kEpiStageBytes;
+        int pst = (226 * 1024 - overhead) / stage_bytes;
+        if (pst > 8) pst = 8;
+        const int psmem = overhead + pst * stage_bytes;
+        const int tiles = (int)(grid.x * grid.y);
+        const int ctas = tiles < 148 ? tiles : 148;
+        if (act == ACT_GELU) gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME><<<ctas, kPersistThreads, psmem, stream>>>(d_params, pst, (int)grid.x, (int)grid.y);
+        else gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME><<<ctas, kPersistThreads, psmem, stream>>>(d_params, pst, (int)grid.x, (int)grid.y);
+        return cudaGetLastError();
+    }
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem);
     // every member of a grouped launch shares the activation and the store-phase specialisation
     if (epi == EPI_BF16_SAME && act == ACT_GELU) gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);

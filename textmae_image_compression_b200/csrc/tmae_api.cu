@@ -496,6 +496,16 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     }
     const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
     int bn = pick_block_n(m_tiles, max_N, groups);
+    if (groups == 1 && m_tiles * ((max_N + 255) / 256) > 2 * 148 - 1 && descs[0].out0.dtype == OUT_BF16 && descs[0].out0.map == MAP_SAME &&
+        descs[0].out1.dtype == OUT_NONE && descs[0].resid == nullptr) {
+        // persistent-kernel candidate: tiles are dealt round-robin to 148 CTAs -> minimise rounds x (tile width + fixed cost)
+        long long best_cost = -1;
+        for (int cand = 256; cand >= 128; cand -= 16) {
+            const int tiles = m_tiles * ((max_N + cand - 1) / cand);
+            const long long cost = (long long)((tiles + 147) / 148) * (cand + 48);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = cand; }
+        }
+    }
     for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
         if (descs[g].out0.map == MAP_SHUF_PAD || descs[g].out1.map == MAP_SHUF_PAD) bn = (bn + 31) / 32 * 32;
     for (int g = 0; g < groups; ++g) {
