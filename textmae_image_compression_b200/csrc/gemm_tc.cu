@@ -525,6 +525,8 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
     for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
     const int total_kb = kb_per_tap * p.num_taps;
     const int total_tiles = m_tiles * n_tiles;
+    long long* ticks = p.dbg_ticks ? p.dbg_ticks + (size_t)blockIdx.x * 16 : nullptr;
+    if (ticks && threadIdx.x == 0) ticks[0] = globaltimer_ns();
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -588,6 +590,7 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&tempty_bar[buf], acc_phase ^ 1u);           // epilogue has drained this accumulator buffer
             tc_fence_after();
+            if (ticks && lane == 0 && it < 3) ticks[1 + 4 * it] = globaltimer_ns();
             const uint32_t tmem_acc = tmem_base + (uint32_t)buf * 256u;
             for (int kb = 0; kb < total_kb; ++kb) {
                 mbar_wait_a(full_a + 8u * stage, phase);
@@ -599,7 +602,7 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
                     for (int k = 0; k < kBlockK / 16; ++k)
                         umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit_a(empty_a + 8u * stage);
-                    if (kb == total_kb - 1) umma_commit(&tfull_bar[buf]);
+                    if (kb == total_kb - 1) { umma_commit(&tfull_bar[buf]); if (ticks && it < 3) ticks[2 + 4 * it] = globaltimer_ns(); }
                 }
                 __syncwarp();
                 stage_off += (uint32_t)stage_bytes;
@@ -615,8 +618,10 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
             const int buf = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * block_n;
+            long long tk[16];
             epilogue_tile<ACT, EPI>(e, m0, n0, block_n, tmem_base + (uint32_t)buf * 256u, stage_base, warp, lane,
-                                    &tfull_bar[buf], acc_phase, nullptr, kPersistEpiWarps / 4);
+                                    &tfull_bar[buf], acc_phase, (ticks && warp == 2 && it < 3) ? tk : nullptr, kPersistEpiWarps / 4);
+            if (ticks && warp == 2 && lane == 0 && it < 3) { ticks[3 + 4 * it] = tk[5]; ticks[4 + 4 * it] = globaltimer_ns(); }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[buf]);           // one arrival per epilogue warp frees the buffer
@@ -707,9 +712,11 @@ cudaError_t gemm_tc_configure() {
 }
 
 // Persistent launch qualifies: one group, bf16 same-row output, more tiles than 2 per SM.
-bool gemm_use_persistent(int groups, int epi, int act, int tiles) {
+// Not used when several streams share the GPU: a persistent launch owns every SM (one CTA, all of its shared memory),
+// which removes the cross-stream overlap that mode relies on (measured: 26.5k vs 25.9k images/s at 3 streams).
+bool gemm_use_persistent(int groups, int epi, int act, int tiles, bool share_sm) {
     static const bool off = getenv("TMAE_NO_PERSISTENT") != nullptr;
-    return !off && groups == 1 && epi == EPI_BF16_SAME && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
+    return !off && !share_sm && groups == 1 && epi == EPI_BF16_SAME && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
 }
 
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).
@@ -731,7 +738,7 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     }
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
-    if (gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y))) {
+    if (gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y), share_sm)) {
         const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
         const int overhead = 1024 + 256 + kEpiStageBytes;
         int pst = (226 * 1024 - overhead) / stage_bytes;

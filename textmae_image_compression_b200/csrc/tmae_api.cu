@@ -496,7 +496,7 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     }
     const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
     int bn = pick_block_n(m_tiles, max_N, groups);
-    if (groups == 1 && m_tiles * ((max_N + 255) / 256) > 2 * 148 - 1 && descs[0].out0.dtype == OUT_BF16 && descs[0].out0.map == MAP_SAME &&
+    if (!(h->cfg.flags & TMAE_FLAG_SHARE_SM) && groups == 1 && m_tiles * ((max_N + 255) / 256) > 2 * 148 - 1 && descs[0].out0.dtype == OUT_BF16 && descs[0].out0.map == MAP_SAME &&
         descs[0].out1.dtype == OUT_NONE && descs[0].resid == nullptr) {
         // persistent-kernel candidate: tiles are dealt round-robin to 148 CTAs -> minimise rounds x (tile width + fixed cost)
         long long best_cost = -1;
@@ -1205,6 +1205,12 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
     if (cudaMalloc(reinterpret_cast<void**>(&dp), sizeof(GemmParams)) != cudaSuccess) return fail(tmp, TMAE_ENOMEM, "cudaMalloc params");
     // bring-up aid: TMAE_GEMM_TIMING=1 prints the per-phase globaltimer profile of the tensor-core kernel
     const bool timing = getenv("TMAE_GEMM_TIMING") != nullptr && impl == 0;
+    __nv_bfloat16* bf16_out = nullptr;
+    if (timing && getenv("TMAE_TIMING_BF16")) {      // time the bf16 same-row store path (persistent kernel for big grids); output discarded
+        cudaMalloc(reinterpret_cast<void**>(&bf16_out), (size_t)p.M * p.N * 2);
+        p.out[0].ptr = bf16_out; p.out[0].dtype = OUT_BF16; p.out[0].map = MAP_SAME; p.out[0].ld = p.N;
+        if (getenv("TMAE_TIMING_GELU")) p.act = ACT_GELU;
+    }
     const int ctas = ((p.M + kBlockM - 1) / kBlockM) * ((p.N + p.block_n - 1) / p.block_n);
     long long* dticks = nullptr;
     if (timing) {
@@ -1261,6 +1267,14 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
             cudaStreamDestroy(cs);
             fprintf(stderr, "[gemm timing]   back-to-back x%d: %.2f us/launch (stream), %.2f us/launch (graph)\n", reps,
                     ms_plain * 1e3 / reps, ms_graph * 1e3 / reps);
+        }
+        if (bf16_out) {
+            double a2[16] = {0};
+            const int pc = ctas < 148 ? ctas : 148;
+            for (int c = 0; c < pc; ++c) for (int k = 1; k < 13; ++k) a2[k] += (double)(t[c * 16 + k] - t[c * 16]) / pc;
+            fprintf(stderr, "[gemm timing]   persistent tiles (ns since CTA entry): t0 mma %.0f-%.0f epi %.0f-%.0f | t1 mma %.0f-%.0f epi %.0f-%.0f | t2 mma %.0f-%.0f epi %.0f-%.0f\n",
+                    a2[1], a2[2], a2[3], a2[4], a2[5], a2[6], a2[7], a2[8], a2[9], a2[10], a2[11], a2[12]);
+            cudaFree(bf16_out);
         }
         cudaFree(dticks);
         cudaEventDestroy(ev0); cudaEventDestroy(ev1);
