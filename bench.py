@@ -265,12 +265,21 @@ def run_b200(args, kwargs, batch, desc, wl):
     tot_ms = sum(f["ms"] for f in fams) or 1.0
     gemm = next((f for f in fams if f["name"] == "gemm_tc"), None)
     roofline = None
+    traffic = None
+    tr_path = ROOT / "profiles" / f"r01_launches_{wl}.json"      # ncu dram__bytes_read+write per launch (cold cache)
+    if tr_path.exists():
+        try:
+            traffic = json.loads(tr_path.read_text())["families"]["gemm_tc_kernel"]["dram_MB_per_launch"] * 1e6
+        except Exception:
+            traffic = None
     if gemm and gemm["ms"] > 0:
         achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
         roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained (of measured)",
+                    "traffic": traffic, "traffic_note": "bytes per launch, ncu dram__bytes_read+write averaged over the gemm_tc "
+                    "launches of one forward (profiles/r01_launches_*.json); algorithmic_flops_per_launch below",
+                    "algorithmic_flops_per_launch": gemm["flops"] / gemm["launches"], "peak_source": f"{peaks['source']} bf16_tflops_sustained (of measured)",
                     "launches_per_step": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / gemm["launches"],
                     "share_of_step": gemm["ms"] / tot_ms,
                     "families": {f["name"]: {"ms": round(f["ms"], 4), "launches": f["launches"]} for f in fams}}
