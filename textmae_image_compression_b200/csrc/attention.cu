@@ -29,6 +29,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 __global__ void __launch_bounds__(kAttnThreads, 6)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
                  float scale_log2e) {
+    pdl_wait();
+    pdl_launch_dependents();
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);            // [Tp][KPITCH]
     __nv_bfloat16* sVt = sK + (size_t)Tp * KPITCH;                               // [HD][Tp + 8]
@@ -170,9 +172,8 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
     if (C != H * HD) return cudaErrorInvalidValue;
     const int Tp = attn_tp(T);
     TMAE_CARVEOUT_ONCE(attention_kernel);
-    attention_kernel<<<N * H, kAttnThreads, attn_smem(T), st>>>(qkv, out, T, Tp, H, C,
-                                                                scale * 1.4426950408889634f);
-    return cudaGetLastError();
+    return launch_k(attention_kernel, dim3(N * H), dim3(kAttnThreads), attn_smem(T), st, true, qkv, out, T, Tp, H, C,
+                    scale * 1.4426950408889634f);
 }
 
 }  // namespace tmae

@@ -20,6 +20,8 @@ gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict_
                       __nv_bfloat16* __restrict__ patches, float* __restrict__ x, const float* __restrict__ cls_token,
                       const float* __restrict__ pos_embed, int S, int grid_w, int K, int T, int C, int in_chans,
                       int patch, const IoBlock* __restrict__ io) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (io) imgs = io->imgs;
     const int j = blockIdx.x, n = blockIdx.y;
     if (j == K) {
@@ -50,9 +52,8 @@ cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __
                                   int T, int C, int in_chans, int patch, cudaStream_t st, const IoBlock* io) {
     dim3 grid(K + 1, N);
     TMAE_CARVEOUT_ONCE(gather_patches_kernel);
-    gather_patches_kernel<<<grid, 192, 0, st>>>(imgs, ids_keep, patches, x, cls_token, pos_embed, S, grid_w, K, T, C,
-                                                in_chans, patch, io);
-    return cudaGetLastError();
+    return launch_k(gather_patches_kernel, grid, dim3(192), 0, st, true, imgs, ids_keep, patches, x, cls_token, pos_embed, S,
+                    grid_w, K, T, C, in_chans, patch, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -66,6 +67,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int rows, int C, int T, int drop_cls,
                  float eps, const IoBlock* __restrict__ io) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (io) out_f32 = io->out.x_remain;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -114,13 +117,13 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
     const int blocks = (rows * 32 + 255) / 256;
     if (C % 128 != 0) return cudaErrorInvalidValue;
     switch (C / 128) {
-        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); layernorm_kernel<6><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); layernorm_kernel<10><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); layernorm_kernel<1><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
-        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io); break;
+        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); return launch_k(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); return launch_k(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); return launch_k(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); return launch_k(layernorm_kernel<1>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); return launch_k(layernorm_kernel<2>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); return launch_k(layernorm_kernel<3>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); return launch_k(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -165,6 +168,8 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
                   float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
                   __nv_bfloat16* __restrict__ zhat_pad, int s4, double* __restrict__ rate_acc, int rows_per_image,
                   const IoBlock* __restrict__ io) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (io) { lik_out = io->out.z_likelihoods; sym_out = io->out.z_symbols; zhat_out = io->out.z_hat; }
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float lg = 0.f;
@@ -214,9 +219,8 @@ cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long row
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(bottleneck_kernel);
-    bottleneck_kernel<<<blocks, 256, 0, st>>>(z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4, rate_acc,
-                                              rows_per_image, io);
-    return cudaGetLastError();
+    return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4,
+                    rate_acc, rows_per_image, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -241,6 +245,8 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
                       int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_pad,
                       int ld_pad, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; }
     const int vec_per_row = cs >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -294,9 +300,8 @@ cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* 
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
-    gaussian_slice_kernel<<<blocks, 256, 0, st>>>(y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat, yhat_pad, ld_pad, s,
-                                                  rate_acc, io);
-    return cudaGetLastError();
+    return launch_k(gaussian_slice_kernel, dim3(blocks), dim3(256), 0, st, true, y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat,
+                    yhat_pad, ld_pad, s, rate_acc, io);
 }
 
 // flat variant for the stand-alone operator (n elements, no layout)
@@ -325,6 +330,8 @@ cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* s
 __global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N, double pixels_per_image,
                                      float* __restrict__ bpp, double* __restrict__ rate_sums,
                                      const IoBlock* __restrict__ io) {
+    pdl_wait();
+    pdl_launch_dependents();
     if (io) {                                  // caller buffers when given, else the workspace defaults passed in
         if (io->out.bpp) bpp = io->out.bpp;
         if (io->out.rate_sums) rate_sums = io->out.rate_sums;
@@ -349,8 +356,7 @@ __global__ void rate_finalize_kernel(const double* __restrict__ rate_acc, int N,
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
                                  double* rate_sums, cudaStream_t st, const IoBlock* io) {
     TMAE_CARVEOUT_ONCE(rate_finalize_kernel);
-    rate_finalize_kernel<<<1, 256, 0, st>>>(rate_acc, N, pixels_per_image, bpp, rate_sums, io);
-    return cudaGetLastError();
+    return launch_k(rate_finalize_kernel, dim3(1), dim3(256), 0, st, true, rate_acc, N, pixels_per_image, bpp, rate_sums, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -360,6 +366,8 @@ __global__ void copy_outputs_kernel(const IoBlock* __restrict__ io, const float4
                                     const float4* __restrict__ mu, const float4* __restrict__ sigma,
                                     const float4* __restrict__ yhat, const int64_t* __restrict__ ids_keep, long long n_y4,
                                     long long n_z4, long long n_ids) {
+    pdl_wait();
+    pdl_launch_dependents();
     const tmae_outputs o = io->out;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_y4; i += stride) {
@@ -375,10 +383,9 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
                                 const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
                                 cudaStream_t st) {
     TMAE_CARVEOUT_ONCE(copy_outputs_kernel);
-    copy_outputs_kernel<<<296, 256, 0, st>>>(io, reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(z),
-                                             reinterpret_cast<const float4*>(mu), reinterpret_cast<const float4*>(sigma),
-                                             reinterpret_cast<const float4*>(yhat), ids_keep, n_y / 4, n_z / 4, n_ids);
-    return cudaGetLastError();
+    return launch_k(copy_outputs_kernel, dim3(296), dim3(256), 0, st, true, io, reinterpret_cast<const float4*>(y),
+                    reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(mu), reinterpret_cast<const float4*>(sigma),
+                    reinterpret_cast<const float4*>(yhat), ids_keep, n_y / 4, n_z / 4, n_ids);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -359,6 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m0, int n0, i
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
+    pdl_launch_dependents();
     const GemmParams& p = params[blockIdx.z];
     const int m0 = blockIdx.x * kBlockM;
     const int n0 = blockIdx.y * p.block_n;
@@ -407,6 +408,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (ticks && threadIdx.x == 0) ticks[1] = globaltimer_ns();
+    pdl_wait();                 // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
     // Producer and MMA loops are WARP-UNIFORM (all 32 lanes run the loop on identical values, only the TMA / MMA /
     // commit instructions are elect-predicated), so the compiler keeps addresses and descriptors in uniform registers
@@ -506,6 +508,7 @@ constexpr int kEpiStageBytes = kPersistEpiWarps * 32 * kEpiPitch * 4;   // dedic
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int m_tiles, int n_tiles) {
+    pdl_launch_dependents();
     const GemmParams& p = params[0];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -541,6 +544,7 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
     const uint32_t pipe_base = smem_u32(pipe);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
 
@@ -637,6 +641,7 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 gemm_simt_kernel(const GemmParams* __restrict__ params) {
+    pdl_wait();
     const GemmParams& p = params[blockIdx.z];
     const int m = blockIdx.x;
     if (m >= p.M) return;
@@ -746,18 +751,17 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         const int psmem = overhead + pst * stage_bytes;
         const int tiles = (int)(grid.x * grid.y);
         const int ctas = tiles < 148 ? tiles : 148;
-        if (act == ACT_GELU) gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME><<<ctas, kPersistThreads, psmem, stream>>>(d_params, pst, (int)grid.x, (int)grid.y);
-        else gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME><<<ctas, kPersistThreads, psmem, stream>>>(d_params, pst, (int)grid.x, (int)grid.y);
-        return cudaGetLastError();
+        if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
+        return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
     }
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem);
     // every member of a grouped launch shares the activation and the store-phase specialisation
-    if (epi == EPI_BF16_SAME && act == ACT_GELU) gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
-    else if (epi == EPI_BF16_SAME && act == ACT_NONE) gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
-    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
-    else if (act == ACT_GELU) gemm_tc_kernel<ACT_GELU, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
-    else if (act == ACT_HALF_TANH) gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
-    else gemm_tc_kernel<ACT_NONE, EPI_GENERIC><<<grid, kGemmThreads, smem, stream>>>(d_params, stages);
+    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
     return cudaGetLastError();
 }
 

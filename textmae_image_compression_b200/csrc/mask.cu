@@ -125,6 +125,7 @@ __device__ int block_exclusive_scan(int* a, int len, int* warp_tmp) {
 __global__ void __launch_bounds__(kThreads)
 mask_select_kernel(const float* __restrict__ scores, int L, int Lp2, int K, int isa, int64_t* __restrict__ ids_shuffle,
                    int64_t* __restrict__ ids_restore, int64_t* __restrict__ ids_keep, const IoBlock* __restrict__ io) {
+    pdl_launch_dependents();                     // first kernel of the forward (follows a memset): launched without PDL itself
     if (io) { scores = io->scores; ids_shuffle = io->out.ids_shuffle; ids_restore = io->out.ids_restore; }
     extern __shared__ float smf[];
     float* s = smf;                                   // scores in index order
