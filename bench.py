@@ -319,6 +319,7 @@ def run_b200(args, kwargs, batch, desc, wl):
             "gpu_launches": launches * args.steps,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "model_tflops": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3,
+            "model_tflops_frac_of_peak": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3 / peaks["bf16_tflops_sustained"],
             "bpp_mean_last_step": out["bpp"].mean().item(),
         }
         print(json.dumps(line), flush=True)
@@ -335,7 +336,7 @@ def main():
     ap.add_argument("--workload", default="B64", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="batches in flight per GPU (independent handles/streams)")
+    ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (independent handles/streams)")
     args = ap.parse_args()
     kwargs, batch, desc = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -78,6 +78,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is None:
         if not LIB_PATH.exists():
+            try:                                      # same image on the GPU box: nvcc is there, build in-tree
+                from . import build as _build
+                _build.build()
+            except Exception as e:                    # noqa: BLE001
+                raise RuntimeError(f"{LIB_PATH} is missing and could not be built ({e}); there is no CPU fallback") from e
+        if not LIB_PATH.exists():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -m textmae_image_compression_b200.build` "
                 "(there is no CPU fallback for this path)")

@@ -131,34 +131,36 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
 
 // ---------------------------------------------------------------------------------------------------------
 // Factorized-prior likelihood of z + quantisation (compressai EntropyBottleneck eval forward, MCM.py:741-744).
-// eb_tab: [Cz][64] fp32 per channel: softplus(matrix0)[3] bias0[3] tanh(factor0)[3] | softplus(matrix1)[9] bias1[3]
+// eb_tab: [64][Cz] fp32, parameter-major (coalesced across channels); per channel the 64 entries are: softplus(matrix0)[3] bias0[3] tanh(factor0)[3] | softplus(matrix1)[9] bias1[3]
 // tanh(factor1)[3] | (x2 more 3x3 layers) | softplus(matrix4)[3] bias4[1] | median at [60].
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float eb_logits(const float* __restrict__ t, float x) {
+// t: this channel's column of the parameter-major table (entry k at t[k * cs], cs = Cz): consecutive lanes handle
+// consecutive channels, so every table read of a warp is one coalesced 128-byte line.
+__device__ __forceinline__ float eb_logits(const float* __restrict__ t, int cs, float x) {
     float h[3], g[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        float v = t[i] * x + t[3 + i];
-        h[i] = v + t[6 + i] * tanhf(v);
+        float v = t[i * cs] * x + t[(3 + i) * cs];
+        h[i] = v + t[(6 + i) * cs] * tanhf(v);
     }
-    const float* tt = t + 9;
+    const float* tt = t + 9 * cs;
 #pragma unroll
     for (int l = 0; l < 3; ++l) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            float v = tt[i * 3 + 0] * h[0];
-            v += tt[i * 3 + 1] * h[1];
-            v += tt[i * 3 + 2] * h[2];
-            v += tt[9 + i];
-            g[i] = v + tt[12 + i] * tanhf(v);
+            float v = tt[(i * 3 + 0) * cs] * h[0];
+            v += tt[(i * 3 + 1) * cs] * h[1];
+            v += tt[(i * 3 + 2) * cs] * h[2];
+            v += tt[(9 + i) * cs];
+            g[i] = v + tt[(12 + i) * cs] * tanhf(v);
         }
         h[0] = g[0]; h[1] = g[1]; h[2] = g[2];
-        tt += 15;
+        tt += 15 * cs;
     }
     float v = tt[0] * h[0];
-    v += tt[1] * h[1];
-    v += tt[2] * h[2];
-    return v + tt[3];
+    v += tt[1 * cs] * h[1];
+    v += tt[2 * cs] * h[2];
+    return v + tt[3 * cs];
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -177,12 +179,12 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
     if (idx < total) {
         const long long row = idx / Cz;
         const int c = (int)(idx - row * Cz);
-        const float* t = eb_tab + (size_t)c * 64;
-        const float med = t[60];
+        const float* t = eb_tab + c;
+        const float med = t[60 * Cz];
         const float sym = rintf(z[idx] - med);
         const float zh = sym + med;
-        const float lower = eb_logits(t, zh - 0.5f);
-        const float upper = eb_logits(t, zh + 0.5f);
+        const float lower = eb_logits(t, Cz, zh - 0.5f);
+        const float upper = eb_logits(t, Cz, zh + 0.5f);
         const float sum = lower + upper;
         const float sgn = sum > 0.f ? -1.f : (sum < 0.f ? 1.f : 0.f);
         float lik = fabsf(sigmoidf_(sgn * upper) - sigmoidf_(sgn * lower));
@@ -484,30 +486,30 @@ __global__ void eb_table_kernel(const float* m0, const float* b0, const float* f
                                 const float* quantiles, float* tab, int Cz) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cz) return;
-    float* t = tab + (size_t)c * 64;
+    float* t = tab + c;                                   // parameter-major: entry k of channel c at tab[k * Cz + c]
     auto softplus = [](float x) { return x > 20.f ? x : log1pf(expf(x)); };   // F.softplus(beta=1, threshold=20)
     for (int i = 0; i < 3; ++i) {
-        t[i] = softplus(m0[c * 3 + i]);
-        t[3 + i] = b0[c * 3 + i];
-        t[6 + i] = tanhf(f0[c * 3 + i]);
+        t[i * Cz] = softplus(m0[c * 3 + i]);
+        t[(3 + i) * Cz] = b0[c * 3 + i];
+        t[(6 + i) * Cz] = tanhf(f0[c * 3 + i]);
     }
     const float* mm[3] = {m1, m2, m3};
     const float* bb[3] = {b1, b2, b3};
     const float* ff[3] = {f1, f2, f3};
     for (int l = 0; l < 3; ++l) {
-        float* tt = t + 9 + 15 * l;
-        for (int i = 0; i < 9; ++i) tt[i] = softplus(mm[l][c * 9 + i]);
+        float* tt = t + (9 + 15 * l) * Cz;
+        for (int i = 0; i < 9; ++i) tt[i * Cz] = softplus(mm[l][c * 9 + i]);
         for (int i = 0; i < 3; ++i) {
-            tt[9 + i] = bb[l][c * 3 + i];
-            tt[12 + i] = tanhf(ff[l][c * 3 + i]);
+            tt[(9 + i) * Cz] = bb[l][c * 3 + i];
+            tt[(12 + i) * Cz] = tanhf(ff[l][c * 3 + i]);
         }
     }
-    float* tl = t + 54;
-    for (int i = 0; i < 3; ++i) tl[i] = softplus(m4[c * 3 + i]);
-    tl[3] = b4[c];
-    t[58] = 0.f; t[59] = 0.f;
-    t[60] = quantiles[c * 3 + 1];
-    t[61] = 0.f; t[62] = 0.f; t[63] = 0.f;
+    float* tl = t + 54 * Cz;
+    for (int i = 0; i < 3; ++i) tl[i * Cz] = softplus(m4[c * 3 + i]);
+    tl[3 * Cz] = b4[c];
+    t[58 * Cz] = 0.f; t[59 * Cz] = 0.f;
+    t[60 * Cz] = quantiles[c * 3 + 1];
+    t[61 * Cz] = 0.f; t[62 * Cz] = 0.f; t[63 * Cz] = 0.f;
 }
 cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st) {
     eb_table_kernel<<<(Cz + 127) / 128, 128, 0, st>>>(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], ptrs[6],
