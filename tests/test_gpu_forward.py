@@ -220,3 +220,30 @@ def test_vit_large_512_against_oracle(cuda_dev):
     _compare("vitL_K256_512", out, ref, cfg, bpp_tol=0.005)
     del m
     torch.cuda.empty_cache()
+
+
+def test_graph_replay_matches_direct_launches(cuda_dev, monkeypatch):
+    """From its second call per batch size, tmae_forward replays a captured CUDA graph (per-call pointers travel through a
+    device IoBlock, kernels overlap through programmatic dependent launch).  Replays must reproduce the plain-launch
+    results for fresh inputs and fresh output buffers, call after call."""
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(21)
+    batches = [(torch.rand(6, 3, 64, 64, generator=g).cuda(), torch.rand(6, cfg.num_patches, generator=g).cuda()) for _ in range(4)]
+    m_graph = _build(SMALL, sd, cuda_dev)
+    monkeypatch.setenv("TMAE_NO_GRAPH", "1")
+    monkeypatch.setenv("TMAE_NO_PDL", "1")
+    m_plain = _build(SMALL, sd, cuda_dev)
+    m_plain._ensure_handle()                      # the environment is read when the handle is created
+    monkeypatch.delenv("TMAE_NO_GRAPH")
+    outs_g = [m_graph(i, s) for i, s in batches]  # call 0 plain, calls 1..3 graph replays
+    outs_p = [m_plain(i, s) for i, s in batches]
+    torch.cuda.synchronize()
+    for k, (a, b) in enumerate(zip(outs_g, outs_p)):
+        assert torch.equal(a["ids_restore"], b["ids_restore"]), k
+        assert torch.equal(a["latents"]["y_sym"], b["latents"]["y_sym"]), k
+        assert torch.equal(a["latents"]["z_sym"], b["latents"]["z_sym"]), k
+        assert torch.equal(a["likelihoods"]["y"], b["likelihoods"]["y"]), k
+        assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["y"], b["y"]), k
+        assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6), k      # fp64 atomics: order may differ in the last bit
+    assert not torch.equal(outs_g[1]["latents"]["y_sym"], outs_g[2]["latents"]["y_sym"])   # really different inputs
