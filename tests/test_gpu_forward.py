@@ -247,3 +247,27 @@ def test_graph_replay_matches_direct_launches(cuda_dev, monkeypatch):
         assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["y"], b["y"]), k
         assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6), k      # fp64 atomics: order may differ in the last bit
     assert not torch.equal(outs_g[1]["latents"]["y_sym"], outs_g[2]["latents"]["y_sym"])   # really different inputs
+
+
+def test_fused_chain_kernel_matches_per_layer_launches(cuda_dev, monkeypatch):
+    """TMAE_CHAIN=1 runs each serial cc / lrp net (5 conv layers) as one cooperative launch with grid barriers between
+    layers; it must reproduce the per-layer launches bit for bit (same tiles, same accumulation order)."""
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(31)
+    imgs = torch.rand(5, 3, 64, 64, generator=g).cuda()
+    scores = torch.rand(5, cfg.num_patches, generator=g).cuda()
+    m_plain = _build(SMALL, sd, cuda_dev)
+    m_plain._ensure_handle()
+    monkeypatch.setenv("TMAE_CHAIN", "1")
+    m_chain = _build(SMALL, sd, cuda_dev)
+    m_chain._ensure_handle()
+    monkeypatch.delenv("TMAE_CHAIN")
+    assert m_chain.launch_count(5) < m_plain.launch_count(5) - 40
+    for _ in range(2):                                  # second call = graph replay with the cooperative nodes
+        a, b = m_chain(imgs, scores), m_plain(imgs, scores)
+        torch.cuda.synchronize()
+        assert torch.equal(a["latents"]["y_sym"], b["latents"]["y_sym"])
+        assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["sigma"], b["sigma"])
+        assert torch.equal(a["latents"]["y_hat"], b["latents"]["y_hat"])
+        assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6)

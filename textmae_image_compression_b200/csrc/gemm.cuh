@@ -71,6 +71,20 @@ struct alignas(64) GemmParams {
     long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)
 };
 
+// A chain = consecutive layers of one net (or of several independent nets, grouped) that all work on the same pixel
+// grid: executed by ONE cooperative launch with a grid-wide barrier between layers instead of one launch per layer.
+constexpr int kMaxChainLayers = 6;
+struct ChainDesc {
+    int num_layers;
+    int first[kMaxChainLayers];      // index of the layer's first GemmParams in the plan's parameter array
+    int groups[kMaxChainLayers];     // independent members of the layer (grouped nets / slices)
+    int m_tiles[kMaxChainLayers];
+    int n_tiles[kMaxChainLayers];
+    int kind[kMaxChainLayers];       // ChainKind: activation + store-phase specialisation of the layer
+    unsigned int* bar;               // [2] device words: arrival counter, generation (sense-reversing grid barrier)
+};
+enum ChainKind : int { CHAIN_GELU_BF16_SAME = 0, CHAIN_NONE_GENERIC = 1, CHAIN_HALF_TANH_GENERIC = 2 };
+
 // haloed layout: per image (s+1) x (s+1) rows; pixel (y, x) at y*(s+1)+x; column s and row s are zero.
 __host__ __device__ inline int halo_rows_per_image(int s) { return (s + 1) * (s + 1); }
 

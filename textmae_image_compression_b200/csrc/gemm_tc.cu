@@ -640,6 +640,161 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Chain kernel: the 5 conv layers of a cc_transform / lrp_transform net (all members of a grouped launch) in ONE
+// cooperative launch.  Every CTA keeps its barriers / TMEM / role warps alive across layers; between layers the grid
+// meets at a sense-reversing barrier in global memory (the next layer's TMA loads read what other CTAs just stored, so
+// the barrier is followed by a generic->async proxy fence).  Replaces 5 launches + 5 prologues / pipeline drains of a
+// latency-bound dependency chain by 1 launch + 4 grid barriers.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int num_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int* gen_p = bar + 1;
+        const unsigned int gen = *gen_p;
+        __threadfence();                                        // this CTA's stores (cumulative over bar.sync) before arrival
+        if (atomicAdd(bar, 1u) == num_ctas - 1u) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);                             // release everybody
+        } else {
+            const long long t0 = clock64();
+            while (*gen_p == gen) {
+                if (clock64() - t0 > 4000000000LL) { printf("tmae: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    asm volatile("fence.proxy.async;\n" ::: "memory");          // generic-proxy stores of other CTAs -> this CTA's TMA loads
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_chain_kernel(const GemmParams* __restrict__ params, const ChainDesc cd, int stages, int stage_bytes) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kStaging = 8 * 32 * kEpiPitch * 4;            // dedicated epilogue staging (36 KB, multiple of 1024)
+    uint8_t* pipe = smem + kStaging;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(pipe + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tfull_bar = empty_bar + stages;                    // accumulator ready   (MMA -> epilogue)
+    uint64_t* tempty_bar = tfull_bar + 1;                        // accumulator drained (epilogue -> MMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 8);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t pipe_base = smem_u32(pipe);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    const uint32_t stage_base = smem_u32(smem);
+
+    // pipeline / accumulator bookkeeping persists across tiles and layers (each role tracks its own copy)
+    int stage = 0;
+    uint32_t phase = 0, stage_off = 0;
+    int tile_it = 0;                                             // accumulator uses so far (parity of tfull / tempty)
+
+    for (int l = 0; l < cd.num_layers; ++l) {
+        const int mt = cd.m_tiles[l], nt = cd.n_tiles[l];
+        const int total_tiles = mt * nt * cd.groups[l];
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+            const int g = t / (mt * nt);
+            const int rem = t - g * mt * nt;
+            const GemmParams& p = params[cd.first[l] + g];
+            const int block_n = p.block_n;
+            const int m0 = (rem / nt) * kBlockM, n0 = (rem % nt) * block_n;
+            int kb_per_tap = 0;
+            for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
+            const int total_kb = kb_per_tap * p.num_taps;
+            const uint32_t acc_phase = (uint32_t)tile_it & 1u;
+            if (m0 >= p.M || n0 >= p.N) {                        // member smaller than the group's grid: keep parities in step
+                if (warp >= 2) { /* nothing to drain */ }
+                --tile_it;
+                continue;
+            }
+            if (warp == 0) {
+                // ===== TMA producer (warp-uniform) =====
+                const int nseg = p.num_segs;
+                const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
+                const void* map0 = &p.a_map[0];
+                const void* map1 = &p.a_map[1];
+                const void* map2 = &p.a_map[2];
+                const void* mapb = &p.b_map;
+                const uint32_t tx_bytes = (uint32_t)(kAStageBytes + block_n * kBlockK * 2);
+                int sg = 0, k = 0, tap = 0, skb_cur = skb0;
+                const void* map_cur = map0;
+                int row = m0 + p.tap_off[0];
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+                    if (elect_one()) {
+                        const uint32_t fb = full_a + 8u * stage;
+                        mbar_arrive_expect_tx_a(fb, tx_bytes);
+                        tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
+                        tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
+                    }
+                    __syncwarp();
+                    if (++k == skb_cur) {
+                        k = 0;
+                        if (++sg == nseg) { sg = 0; ++tap; row = m0 + p.tap_off[tap < kMaxTaps ? tap : 0]; }
+                        skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+                        map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+                    }
+                    stage_off += (uint32_t)stage_bytes;
+                    if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+                }
+            } else if (warp == 1) {
+                // ===== MMA issuer (warp-uniform) =====
+                const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+                const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);
+                mbar_wait(tempty_bar, acc_phase ^ 1u);             // previous tile's accumulator has been drained
+                tc_fence_after();
+                for (int kb = 0; kb < total_kb; ++kb) {
+                    mbar_wait_a(full_a + 8u * stage, phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
+                    const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                            umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_a(empty_a + 8u * stage);
+                        if (kb == total_kb - 1) umma_commit(tfull_bar);
+                    }
+                    __syncwarp();
+                    stage_off += (uint32_t)stage_bytes;
+                    if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+                }
+            } else {
+                // ===== epilogue warps =====
+                const EpiCtx e = load_epi(p);
+                const int kind = cd.kind[l];
+                if (kind == CHAIN_GELU_BF16_SAME)
+                    epilogue_tile<ACT_GELU, EPI_BF16_SAME>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                else if (kind == CHAIN_HALF_TANH_GENERIC)
+                    epilogue_tile<ACT_HALF_TANH, EPI_GENERIC>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                else
+                    epilogue_tile<ACT_NONE, EPI_GENERIC>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar);
+            }
+        }
+        if (l + 1 < cd.num_layers) grid_barrier(cd.bar, gridDim.x);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // CUDA-core checker: same parameter block, same epilogue, plain loads.  Bring-up / tests only.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -725,6 +880,28 @@ cudaError_t gemm_tc_configure() {
 bool gemm_use_persistent(int groups, int epi, int act, int tiles, bool share_sm) {
     static const bool off = getenv("TMAE_NO_PERSISTENT") != nullptr;
     return !off && !share_sm && groups == 1 && epi == EPI_BF16_SAME && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
+}
+
+cudaError_t gemm_chain_configure() {
+    prefer_max_smem_carveout(gemm_tc_chain_kernel);
+    return cudaFuncSetAttribute(gemm_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
+// One cooperative launch for a whole chain.  max_block_n = widest N tile of any layer (sizes the pipeline stages).
+cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream) {
+    const int stage_bytes = kAStageBytes + max_block_n * kBlockK * 2;
+    const int overhead = 1024 + 256 + 8 * 32 * kEpiPitch * 4;
+    int stages = (226 * 1024 - overhead) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) return cudaErrorInvalidValue;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid_ctas); cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = overhead + stages * stage_bytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tc_chain_kernel, d_params, cd, stages, stage_bytes);
 }
 
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).

@@ -21,6 +21,8 @@ struct IoBlock {
 cudaError_t gemm_tc_configure();
 int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes);
 int gemm_epi_kind(const GemmParams& p);
+cudaError_t gemm_chain_configure();
+cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream);
 

@@ -41,7 +41,7 @@ struct Layer {                      // one prepacked linear / conv
     int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
 };
 
-enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE, ST_Y_TO_PAD };
+enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_CHAIN, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE, ST_Y_TO_PAD };
 enum Family { FAM_GEMM = 0, FAM_ATTN, FAM_LN, FAM_MASK, FAM_GATHER, FAM_ENTROPY, FAM_MISC, FAM_COUNT };
 const char* kFamilyNames[FAM_COUNT] = {"gemm_tc", "attention", "layernorm", "mask_select", "gather_patches",
                                        "entropy_elementwise", "misc"};
@@ -52,6 +52,9 @@ struct Step {
     // GEMM
     int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0, epi = 0;
     double flops = 0, bytes = 0;
+    // fused chain of layers (ST_CHAIN)
+    ChainDesc chain;
+    int chain_grid = 0, chain_max_bn = 0;
     // LN
     const float* ln_gamma = nullptr;
     const float* ln_beta = nullptr;
@@ -96,6 +99,7 @@ struct Workspace {
     // host-buffer entry staging
     float *st_imgs = nullptr, *st_scores = nullptr;
     IoBlock* io = nullptr;           // per-call pointers for graph replays
+    unsigned int* grid_bar = nullptr; // [2] counter + generation of the chain kernels' grid barrier
 };
 
 }  // namespace
@@ -115,6 +119,9 @@ struct tmae_handle {
     PFN_encodeTiled encode = nullptr;
     std::vector<void*> weight_allocs;
     bool use_graph = true;           // TMAE_NO_GRAPH=1 disables CUDA-graph replay
+    bool use_chain = false;          // TMAE_CHAIN=1: fuse each serial cc/lrp net (5 conv layers) into one cooperative launch.
+                                     // Measured on B200: per-launch roofline 0.29 -> 0.32, but end-to-end it loses to the
+                                     // PDL + CUDA-graph path (22.5k vs 23.4k img/s, and it blocks cross-stream overlap), so off.
     cudaStream_t cap_stream = nullptr;
     // profiling
     bool profiling = false;
@@ -458,6 +465,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.st_imgs, (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size);
     WS_ALLOC(w.st_scores, (size_t)N * h->L);
     WS_ALLOC(w.io, (size_t)1);
+    WS_ALLOC(w.grid_bar, (size_t)2);
 #undef WS_ALLOC
     w.cap_N = N;
     w.bytes = tot;
@@ -519,6 +527,62 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     }
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
     for (int g = 1; g < groups; ++g) if (descs[g].act != descs[0].act) return fail(h, TMAE_EINVAL, "grouped GEMM members must share the activation");
+    pl.steps.push_back(st);
+    return TMAE_OK;
+}
+
+// layers[l] = the (grouped) members of layer l; all layers share the pixel grid.  One cooperative launch.
+int add_chain(tmae_handle* h, Plan& pl, const std::vector<std::vector<GemmDesc>>& layers, const char* tag) {
+    Step st;
+    st.kind = ST_CHAIN;
+    st.family = FAM_GEMM;
+    st.tag = tag;
+    memset(&st.chain, 0, sizeof(st.chain));
+    st.chain.num_layers = (int)layers.size();
+    if (st.chain.num_layers > kMaxChainLayers) return fail(h, TMAE_EINVAL, "chain too long");
+    int grid = 1, max_bn = 32;
+    for (size_t l = 0; l < layers.size(); ++l) {
+        const std::vector<GemmDesc>& mem = layers[l];
+        const int groups = (int)mem.size();
+        int max_M = 0, max_N = 0;
+        for (const GemmDesc& d : mem) { if (d.M > max_M) max_M = d.M; if (d.layer->Cout > max_N) max_N = d.layer->Cout; }
+        const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
+        // column tiles: as many as keep the layer within one wave of 148 CTAs (each >= 32 wide), at least ceil(N / 256)
+        int nt = 148 / (m_tiles * groups);
+        if (nt < 1) nt = 1;
+        while (nt > 1 && round16((max_N + nt - 1) / nt) < 32) --nt;
+        if (nt < (max_N + 255) / 256) nt = (max_N + 255) / 256;
+        const int bn = round16((max_N + nt - 1) / nt);
+        const int n_tiles = (max_N + bn - 1) / bn;
+        st.chain.first[l] = (int)pl.host_params.size();
+        st.chain.groups[l] = groups;
+        st.chain.m_tiles[l] = m_tiles;
+        st.chain.n_tiles[l] = n_tiles;
+        int kind = -1;
+        for (int g = 0; g < groups; ++g) {
+            GemmParams p;
+            int rc = fill_params(h, mem[g], groups, &p, bn);
+            if (rc) return rc;
+            const int ek = gemm_epi_kind(p);
+            int k = -1;
+            if (p.act == ACT_GELU && ek == 1 /*EPI_BF16_SAME*/) k = CHAIN_GELU_BF16_SAME;
+            else if (p.act == ACT_NONE) k = CHAIN_NONE_GENERIC;
+            else if (p.act == ACT_HALF_TANH) k = CHAIN_HALF_TANH_GENERIC;
+            if (k < 0 || (kind >= 0 && k != kind)) return fail(h, TMAE_EINVAL, "chain layer %zu: unsupported epilogue mix", l);
+            kind = k;
+            pl.host_params.push_back(p);
+            st.flops += mem[g].flops;
+        }
+        st.chain.kind[l] = kind;
+        const int tiles = m_tiles * n_tiles * groups;
+        if (tiles > grid) grid = tiles;
+        if (bn > max_bn) max_bn = bn;
+    }
+    st.chain.bar = h->ws.grid_bar;
+    st.chain_grid = grid < 148 ? grid : 148;
+    st.chain_max_bn = max_bn;
+    st.param_index = st.chain.first[0];
+    st.groups = 1; st.max_M = 0; st.max_N = 0; st.block_n = max_bn;
     pl.steps.push_back(st);
     return TMAE_OK;
 }
@@ -673,6 +737,8 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         const int sup = i0 < half_sl ? i0 : half_sl;
         int ch[6];
         cc_channels(h, ch, i0, false);
+        const bool fuse = h->use_chain && cnt == 1 && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT);
+        std::vector<std::vector<GemmDesc>> chain_layers;
         for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i] of every member, grouped
             std::vector<GemmDesc> d((size_t)cnt * 2);
             for (int j = 0; j < cnt; ++j)
@@ -694,12 +760,15 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                     g.flops = conv_flops(rk, ch[l], ch[l + 1], 9);
                 }
             snprintf(tag, sizeof(tag), "cc.%d.%d", i0, 2 * l);
-            rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc;
+            if (fuse) chain_layers.push_back(d);
+            else { rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc; }
         }
+        if (fuse) { snprintf(tag, sizeof(tag), "cc.%d.chain", i0); rc = add_chain(h, pl, chain_layers, tag); if (rc) return rc; }
         { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i0; g.gc_slices = cnt; g.tag = "gaussian." + std::to_string(i0); pl.steps.push_back(g); }
         if (!(skip_dead && i0 >= half_sl)) {
             int lch[6];
             cc_channels(h, lch, i0, true);
+            chain_layers.clear();
             for (int l = 0; l < 5; ++l) {    // lrp_transform[i] (MCM.py:780-783)
                 std::vector<GemmDesc> d((size_t)cnt);
                 for (int j = 0; j < cnt; ++j) {
@@ -724,8 +793,10 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                     g.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
                 }
                 snprintf(tag, sizeof(tag), "lrp.%d.%d", i0, 2 * l);
-                rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc;
+                if (fuse) chain_layers.push_back(d);
+                else { rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc; }
             }
+            if (fuse) { snprintf(tag, sizeof(tag), "lrp.%d.chain", i0); rc = add_chain(h, pl, chain_layers, tag); if (rc) return rc; }
         }
         i0 += cnt;
     }
@@ -770,8 +841,8 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
     h->prof_flops[h->prof_used] = st.flops;
     h->prof_bytes[h->prof_used] = st.bytes;
     h->prof_tag[h->prof_used] = st.tag;
-    h->prof_ctas[h->prof_used] = st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
-    h->prof_bn[h->prof_used] = st.kind == ST_GEMM ? st.block_n : 0;
+    h->prof_ctas[h->prof_used] = st.kind == ST_CHAIN ? st.chain_grid : st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
+    h->prof_bn[h->prof_used] = (st.kind == ST_GEMM || st.kind == ST_CHAIN) ? st.block_n : 0;
     ++h->prof_used;
     return TMAE_OK;
 }
@@ -805,6 +876,9 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st));
+                break;
+            case ST_CHAIN:
+                CUDA_TRY(h, gemm_chain_launch(pl.d_params, sp.chain, sp.chain_grid, sp.chain_max_bn, st));
                 break;
             case ST_LN:
                 if (sp.ln_final)
@@ -936,9 +1010,12 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     e = gemm_tc_configure();
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gemm configure: %s", cudaGetErrorString(e));
+    e = gemm_chain_configure();
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "chain configure: %s", cudaGetErrorString(e));
     e = attention_configure(h->T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
     h->use_graph = getenv("TMAE_NO_GRAPH") == nullptr;
+    h->use_chain = getenv("TMAE_CHAIN") != nullptr;
     *out = h.release();
     return TMAE_OK;
 }
