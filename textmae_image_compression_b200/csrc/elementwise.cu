@@ -164,11 +164,11 @@ __device__ __forceinline__ float eb_logits(const float* __restrict__ t, int cs, 
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// z: [rows, Cz] compact channels-last.  zhat_pad (optional): bf16 haloed layout of side s4 for h_s.
+// z: [rows, Cz] compact channels-last.  zhat_bf (optional): bf16 copy, same layout, the input of h_s.
 __global__ void __launch_bounds__(256)
 bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab, long long total, int Cz,
                   float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
-                  __nv_bfloat16* __restrict__ zhat_pad, int s4, double* __restrict__ rate_acc, int rows_per_image,
+                  __nv_bfloat16* __restrict__ zhat_bf, int s4, double* __restrict__ rate_acc, int rows_per_image,
                   const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
@@ -193,12 +193,7 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
         if (sym_out) sym_out[idx] = (int32_t)sym;
         if (zhat_out) zhat_out[idx] = zh;
         n = (int)(row / rows_per_image);
-        if (zhat_pad) {
-            const int j = (int)(row - (long long)n * rows_per_image);
-            const int y = j / s4, x = j - y * s4;
-            const long long prow = (long long)n * (s4 + 1) * (s4 + 1) + y * (s4 + 1) + x;
-            zhat_pad[prow * Cz + c] = __float2bfloat16(zh);
-        }
+        if (zhat_bf) zhat_bf[idx] = __float2bfloat16(zh);
         lg = log2f(lik);
     }
     if (rate_acc) {
@@ -215,13 +210,13 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
 }
 
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
-                              float* zhat, __nv_bfloat16* zhat_pad, int s4, double* rate_acc, int rows_per_image,
+                              float* zhat, __nv_bfloat16* zhat_bf, int s4, double* rate_acc, int rows_per_image,
                               cudaStream_t st, const IoBlock* io) {
     const long long total = rows * Cz;
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(bottleneck_kernel);
-    return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_pad, s4,
+    return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_bf, s4,
                     rate_acc, rows_per_image, io);
 }
 
@@ -229,7 +224,7 @@ cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long row
 // Gaussian conditional likelihood + quantisation of one latent slice (compressai GaussianConditional eval
 // forward + quantize_ste, MCM.py:771-776).  Each thread handles 4 consecutive channels (128-bit accesses).
 //   y, mu, sigma, lik, sym, y_hat : fp32 / int32 [rows, ld] with channel offset col0, `cs` channels in the slice.
-//   yhat_pad (optional) : bf16 haloed layout [N*P, ld_pad], same channel offset: support for later slices.
+//   yhat_bf (optional) : bf16 copy [rows, ld_bf], same channel offset: support for later slices.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void gaussian_elem(float y, float mu, float sigma, float& lik, float& sym, float& yhat) {
     const float kNegInvSqrt2 = -0.70710678118654752440f;        // float(-(2 ** -0.5))
@@ -245,8 +240,8 @@ __device__ __forceinline__ void gaussian_elem(float y, float mu, float sigma, fl
 __global__ void __launch_bounds__(256)
 gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
-                      int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_pad,
-                      int ld_pad, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
+                      int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_bf,
+                      int ld_bf, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
     if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; }
@@ -272,14 +267,11 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
         if (yhat_out) *reinterpret_cast<float4*>(yhat_out + off) = yh;
         const int K = s * s;
         n = (int)(row / K);
-        if (yhat_pad) {
-            const int j = (int)(row - (long long)n * K);
-            const int py = j / s, px = j - py * s;
-            const long long prow = (long long)n * (s + 1) * (s + 1) + py * (s + 1) + px;
+        if (yhat_bf) {
             uint2 pk;
             pk.x = pack_bf16x2(yh.x, yh.y);
             pk.y = pack_bf16x2(yh.z, yh.w);
-            *reinterpret_cast<uint2*>(yhat_pad + prow * ld_pad + c) = pk;
+            *reinterpret_cast<uint2*>(yhat_bf + (size_t)row * ld_bf + c) = pk;
         }
         lg = (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
     }
@@ -296,14 +288,14 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
 }
 
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
-                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_pad, int ld_pad,
+                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, int ld_bf,
                                   int s, double* rate_acc, cudaStream_t st, const IoBlock* io) {
     const long long total = rows * (cs / 4);
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
     return launch_k(gaussian_slice_kernel, dim3(blocks), dim3(256), 0, st, true, y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat,
-                    yhat_pad, ld_pad, s, rate_acc, io);
+                    yhat_bf, ld_bf, s, rate_acc, io);
 }
 
 // flat variant for the stand-alone operator (n elements, no layout)
@@ -390,33 +382,6 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
                     reinterpret_cast<const float4*>(yhat), ids_keep, n_y / 4, n_z / 4, n_ids);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// fp32 compact [N*K, C] -> bf16 haloed layout (teacher-forced entry: y supplied by the caller)
-// ---------------------------------------------------------------------------------------------------------
-__global__ void compact_to_pad_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows,
-                                      int C, int s) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int vec = C >> 2;
-    if (idx >= rows * vec) return;
-    const long long row = idx / vec;
-    const int c = (int)(idx - row * vec) * 4;
-    const int K = s * s;
-    const int n = (int)(row / K);
-    const int j = (int)(row - (long long)n * K);
-    const int y = j / s, x = j - y * s;
-    const long long prow = (long long)n * (s + 1) * (s + 1) + y * (s + 1) + x;
-    const float4 v = *reinterpret_cast<const float4*>(src + row * C + c);
-    uint2 pk;
-    pk.x = pack_bf16x2(v.x, v.y);
-    pk.y = pack_bf16x2(v.z, v.w);
-    *reinterpret_cast<uint2*>(dst + prow * C + c) = pk;
-}
-cudaError_t launch_compact_to_pad(const float* src, __nv_bfloat16* dst, long long rows, int C, int s, cudaStream_t st) {
-    const long long total = rows * (C / 4);
-    if (total == 0) return cudaSuccess;
-    compact_to_pad_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(src, dst, rows, C, s);
-    return cudaGetLastError();
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // Weight prepack: fp32 [Cout, Cin_total, kh, kw] (or [Cout, Cin] linear) -> bf16 [Cout, Kp], K index =

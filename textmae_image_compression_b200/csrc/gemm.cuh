@@ -13,15 +13,18 @@ constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one 128B-swizzle atom row
 constexpr int kMaxSegs = 3;
 constexpr int kMaxTaps = 9;
 
-enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_PADDED = 2 };
+// Row spaces.  Every activation matrix is COMPACT channels-last: pixel (n, y, x) of an s x s grid is row n*s*s + y*s + x.
+//   IN_LINEAR  plain GEMM rows (tokens)
+//   IN_COMPACT plain GEMM rows that are pixels of an s x s grid (g_a, patch embed): only the token remap needs (n, j)
+//   IN_CONV    3x3 convolution: the A tile of a CTA is a 4-D TMA box [64 ch, s (x), box_y, box_n images] of the
+//              compact tensor; a tap (dy, dx) shifts the box coordinates and TMA zero-fills what falls outside the
+//              image, so there is no halo / im2col buffer and no wasted rows when s*box_y*box_n == 128.
+enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_CONV = 2 };
 enum RowMap : int {
-    MAP_SAME = 0,        // out row = m
-    MAP_TO_PAD,          // compact (n, j) -> zero-haloed layout of side s
-    MAP_TO_COMPACT,      // haloed (n, y, x) -> n*s*s + y*s + x
+    MAP_SAME = 0,        // out row = the pixel's / token's own compact row
     MAP_TO_TOKEN,        // compact (n, j) -> token row n*T + 1 + j
-    MAP_S2_PAD,          // stride-2 subsample -> haloed layout of side s/2
-    MAP_S2_COMPACT,      // stride-2 subsample -> compact layout of side s/2
-    MAP_SHUF_PAD,        // PixelShuffle(2): column quadrant q -> haloed layout of side 2s
+    MAP_S2,              // stride-2 subsample -> compact grid of side s/2
+    MAP_SHUF,            // PixelShuffle(2): column quadrant q -> compact grid of side 2s
     MAP_GATHER1          // row = gather_ids[m] + 1 (pos-embed lookup)
 };
 enum Act : int { ACT_NONE = 0, ACT_GELU = 1, ACT_HALF_TANH = 2 };
@@ -35,7 +38,7 @@ struct OutSpec {
 };
 
 struct alignas(64) GemmParams {
-    CUtensorMap a_map[kMaxSegs];      // [rows, C_seg] bf16, box 64 x 128, SWIZZLE_128B
+    CUtensorMap a_map[kMaxSegs];      // linear: [rows, C_seg] box 64 x 128; conv: [C_seg, s, s, n_img] box 64 x s x box_y x box_n
     CUtensorMap b_map;                // [N, Kpacked] bf16, box 64 x block_n, SWIZZLE_128B
     // raw views of the same operands (CUDA-core checker kernel)
     const __nv_bfloat16* a_ptr[kMaxSegs];
@@ -47,20 +50,22 @@ struct alignas(64) GemmParams {
     // K loop
     int num_segs;
     int seg_kblocks[kMaxSegs];        // ceil(C_seg / 64)
-    int num_taps;
-    int tap_off[kMaxTaps];            // row shift of each tap
+    int num_taps;                     // 1, or 9 for IN_CONV: taps in (kh, kw) row-major order, shift (kw - 1, kh - 1)
     // problem
-    int M;                            // rows of the input row space covered by this launch
+    int M;                            // linear: rows; conv: m_tiles * 128 (virtual rows of the tile grid)
     int N;                            // output channels
     int block_n;
     // input row space geometry
     int in_mode;
     int s;                            // side of the pixel grid
-    int P;                            // (s+1)^2 rows per image in the haloed layout
     int K;                            // s*s
     int T;                            // tokens per image (K + 1)
+    int n_img;                        // conv: images
+    int box_y, box_n;                 // conv: image rows / images per CTA tile
+    int rows_used;                    // conv: s * box_y * box_n (<= 128) accumulator rows that hold pixels
+    int y_tiles;                      // conv: ceil(s / box_y)
     // epilogue
-    const float* bias;                // [N] (already permuted for MAP_SHUF_PAD)
+    const float* bias;                // [N] (already permuted for MAP_SHUF)
     int act;
     const float* resid;               // optional fp32 addend, read at row map `resid_map`
     int resid_ld;
@@ -85,7 +90,5 @@ struct ChainDesc {
 };
 enum ChainKind : int { CHAIN_GELU_BF16_SAME = 0, CHAIN_NONE_GENERIC = 1, CHAIN_HALF_TANH_GENERIC = 2 };
 
-// haloed layout: per image (s+1) x (s+1) rows; pixel (y, x) at y*(s+1)+x; column s and row s are zero.
-__host__ __device__ inline int halo_rows_per_image(int s) { return (s + 1) * (s + 1); }
 
 }  // namespace tmae

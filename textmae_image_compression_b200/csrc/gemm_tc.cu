@@ -27,7 +27,7 @@ struct EpiCtx {
     const float* resid;
     const int64_t* gather_ids;
     OutSpec out[2];
-    int act, resid_ld, resid_map, M, N, in_mode, s, P, K, T;
+    int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used;
 };
 
 __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
@@ -35,33 +35,49 @@ __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
     e.bias = p.bias; e.resid = p.resid; e.gather_ids = p.gather_ids;
     e.out[0] = p.out[0]; e.out[1] = p.out[1];
     e.act = p.act; e.resid_ld = p.resid_ld; e.resid_map = p.resid_map;
-    e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.P = p.P; e.K = p.K; e.T = p.T;
+    e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.K = p.K; e.T = p.T;
+    e.n_img = p.n_img; e.box_y = p.box_y; e.box_n = p.box_n; e.y_tiles = p.y_tiles; e.rows_used = p.rows_used;
     return e;
+}
+
+// Conv tiles: CTA tile `m_tile` covers image rows [y0, y0 + box_y) of images [n0, n0 + box_n).
+__device__ __forceinline__ void conv_tile_origin(int m_tile, int y_tiles, int box_y, int box_n, int& y0, int& n0) {
+    const int nt = m_tile / y_tiles;
+    y0 = (m_tile - nt * y_tiles) * box_y;
+    n0 = nt * box_n;
 }
 
 struct RowCtx {
     int valid, n, y, x, lin;
 };
 
-__device__ __forceinline__ RowCtx decode_row(const EpiCtx& p, int m) {
-    RowCtx r;
-    r.lin = m;
-    r.valid = m < p.M;
-    r.n = r.y = r.x = 0;
-    if (p.in_mode == IN_PADDED) {
-        const int w = p.s + 1;
-        r.n = m / p.P;
-        const int rem = m - r.n * p.P;
-        r.y = rem / w;
-        r.x = rem - r.y * w;
-        r.valid = r.valid && (r.y < p.s) && (r.x < p.s);
-    } else if (p.in_mode == IN_COMPACT) {
-        r.n = m / p.K;
-        const int j = m - r.n * p.K;
-        r.y = j / p.s;
-        r.x = j - r.y * p.s;
+// r = accumulator row (0..127) of CTA tile `m_tile`.  Linear row spaces: row m_tile*128 + r.  Conv: the A tile is the
+// TMA box [x][yl][nl] flattened, r = (nl * box_y + yl) * s + x, and the row it stands for is pixel (n0+nl, y0+yl, x).
+__device__ __forceinline__ RowCtx decode_row(const EpiCtx& p, int m_tile, int r) {
+    RowCtx c;
+    c.n = c.y = c.x = 0;
+    if (p.in_mode == IN_CONV) {
+        int y0, n0;
+        conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, n0);
+        const int per_img = p.s * p.box_y;
+        const int nl = r / per_img, rem = r - nl * per_img;
+        const int yl = rem / p.s;
+        c.x = rem - yl * p.s;
+        c.y = y0 + yl;
+        c.n = n0 + nl;
+        c.valid = (r < p.rows_used) && (c.n < p.n_img) && (c.y < p.s);
+        c.lin = c.n * p.K + c.y * p.s + c.x;
+    } else {
+        c.lin = m_tile * kBlockM + r;
+        c.valid = c.lin < p.M;
+        if (p.in_mode == IN_COMPACT) {
+            c.n = c.lin / p.K;
+            const int j = c.lin - c.n * p.K;
+            c.y = j / p.s;
+            c.x = j - c.y * p.s;
+        }
     }
-    return r;
+    return c;
 }
 
 // q = PixelShuffle quadrant (dy*2+dx) of the column group; returns -1 when this row produces no output.
@@ -69,22 +85,15 @@ __device__ __forceinline__ long long map_row(const EpiCtx& p, int map, const Row
     if (!r.valid) return -1;
     switch (map) {
         case MAP_SAME: return r.lin;
-        case MAP_TO_PAD: return (long long)r.n * p.P + r.y * (p.s + 1) + r.x;
-        case MAP_TO_COMPACT: return (long long)r.n * p.K + r.y * p.s + r.x;
         case MAP_TO_TOKEN: return (long long)r.n * p.T + 1 + r.y * p.s + r.x;
-        case MAP_S2_PAD: {
-            if ((r.y | r.x) & 1) return -1;
-            const int s2 = p.s >> 1;
-            return (long long)r.n * (s2 + 1) * (s2 + 1) + (r.y >> 1) * (s2 + 1) + (r.x >> 1);
-        }
-        case MAP_S2_COMPACT: {
+        case MAP_S2: {
             if ((r.y | r.x) & 1) return -1;
             const int s2 = p.s >> 1;
             return (long long)r.n * s2 * s2 + (r.y >> 1) * s2 + (r.x >> 1);
         }
-        case MAP_SHUF_PAD: {
+        case MAP_SHUF: {
             const int s2 = p.s << 1;
-            return (long long)r.n * (s2 + 1) * (s2 + 1) + (2 * r.y + (q >> 1)) * (s2 + 1) + 2 * r.x + (q & 1);
+            return (long long)r.n * s2 * s2 + (2 * r.y + (q >> 1)) * s2 + 2 * r.x + (q & 1);
         }
         case MAP_GATHER1: return p.gather_ids[r.lin] + 1;
     }
@@ -183,7 +192,7 @@ __device__ __forceinline__ void epilogue8(const EpiCtx& p, const RowCtx& r, int 
     for (int i = 0; i < 8; ++i) v[i] = apply_act(v[i], p.act);
     // PixelShuffle bookkeeping: weights are packed quadrant-major, so consecutive columns share (dy,dx).
     int q = 0, ocol = col;
-    if (p.out[0].map == MAP_SHUF_PAD || p.out[1].map == MAP_SHUF_PAD) {
+    if (p.out[0].map == MAP_SHUF || p.out[1].map == MAP_SHUF) {
         const int cq = p.N >> 2;
         q = col / cq;
         ocol = col - q * cq;
@@ -213,15 +222,16 @@ enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2 
 // coalesced 64 / 128-byte row segments to global memory.
 // ---------------------------------------------------------------------------------------------------------
 template <int ACT, int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m0, int n0, int block_n, uint32_t tmem_acc,
+__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n0, int block_n, uint32_t tmem_acc,
                                               uint32_t stage_base, int warp, int lane, uint64_t* wait_bar,
                                               uint32_t wait_parity, long long* ticks, int nsub = 2) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;                  // which of the `nsub` warps of this TMEM lane quarter
     const int cstride = 32 * nsub;
-    const int m = m0 + quarter * 32 + lane;
-    const RowCtx r = decode_row(e, m);
-    const bool shuf = e.out[0].map == MAP_SHUF_PAD || e.out[1].map == MAP_SHUF_PAD;
+    const int m0 = m_tile * kBlockM;                   // first row of the tile in a linear row space
+    const RowCtx r = decode_row(e, m_tile, quarter * 32 + lane);
+    const bool conv = e.in_mode == IN_CONV;            // conv tiles: output rows come from the decoded pixel, not m0 + r
+    const bool shuf = e.out[0].map == MAP_SHUF || e.out[1].map == MAP_SHUF;
     const int cq = e.N >> 2;
     const uint32_t stage_a = stage_base + (uint32_t)(warp - 2) * 32u * kEpiPitch * 4u;   // this warp's staging tile
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;
@@ -272,6 +282,22 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m0, int n0, i
         const int col = colbase + c4;
         const bool col_ok = col < e.N && c0 + c4 < block_n;
         const int ocol = col - q * (shuf ? cq : 0);
+        if (EPI == EPI_BF16_SAME && conv) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rsub;
+                const int orow = __shfl_sync(0xffffffffu, r.lin, rr);
+                if (col_ok && ((valid_mask >> rr) & 1u)) {
+                    const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                    uint2 pk;
+                    pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
+                    pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) + (long long)orow * e.out[0].ld + col) = pk;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         if (EPI == EPI_BF16_SAME) {
             if (col_ok) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) +
@@ -359,14 +385,60 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m0, int n0, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA producer of one CTA tile (called by a whole warp; WARP-UNIFORM: all 32 lanes run the loop on identical values and
+// only the TMA instructions are elect-predicated, so addresses and descriptors stay in uniform registers).
+// Linear row spaces: A tile = 2-D box [64 ch, 128 rows].  Conv: 4-D box [64 ch, s, box_y, box_n] at pixel offset (dx, dy)
+// of the tap; TMA zero-fills whatever falls outside the image (and images >= n_img), which IS the conv's zero padding.
+// The pipeline position (stage / phase / stage_off) is carried across tiles by the caller.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages,
+                                             int stage_bytes, uint32_t pipe_base, uint32_t full_a, uint32_t empty_a,
+                                             int& stage, uint32_t& phase, uint32_t& stage_off, long long* ticks) {
+    const int nseg = p.num_segs;
+    const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
+    const void* map0 = &p.a_map[0];
+    const void* map1 = &p.a_map[1];
+    const void* map2 = &p.a_map[2];
+    const void* mapb = &p.b_map;
+    const bool conv = p.in_mode == IN_CONV;
+    int y0 = 0, img0 = 0;
+    if (conv) conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, img0);
+    const int row = m_tile * kBlockM;
+    const uint32_t tx_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2 + p.block_n * kBlockK * 2);
+    int sg = 0, k = 0, skb_cur = skb0;
+    int dx = -1, cy = y0 - 1;                              // taps in (kh, kw) row-major order = the weight packing order
+    const void* map_cur = map0;
+    for (int kb = 0; kb < total_kb; ++kb) {
+        mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+        if (elect_one()) {
+            const uint32_t fb = full_a + 8u * stage;
+            mbar_arrive_expect_tx_a(fb, tx_bytes);
+            if (conv) tma_load_4d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, dx, cy, img0);
+            else tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
+            tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
+            if (ticks && kb == 0) ticks[2] = globaltimer_ns();
+        }
+        __syncwarp();
+        if (++k == skb_cur) {
+            k = 0;
+            if (++sg == nseg) { sg = 0; if (++dx > 1) { dx = -1; ++cy; } }
+            skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+            map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+        }
+        stage_off += (uint32_t)stage_bytes;
+        if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+    }
+}
+
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     pdl_launch_dependents();
     const GemmParams& p = params[blockIdx.z];
-    const int m0 = blockIdx.x * kBlockM;
+    const int m_tile = blockIdx.x;
     const int n0 = blockIdx.y * p.block_n;
-    if (m0 >= p.M || n0 >= p.N) return;   // grouped launches: grid is sized for the largest member
+    if (m_tile * kBlockM >= p.M || n0 >= p.N) return;   // grouped launches: grid is sized for the largest member
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -377,7 +449,6 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* accum_bar = empty_bar + stages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-    int* sm_tap = reinterpret_cast<int*>(tmem_slot + 2);                 // [kMaxTaps] row shift per conv tap
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -405,7 +476,6 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         tmem_alloc(tmem_slot, tmem_cols);
         tmem_relinquish();
     }
-    if (warp == 2 && lane < kMaxTaps) sm_tap[lane] = lane < p.num_taps ? p.tap_off[lane] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -420,37 +490,9 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     if (warp == 0) {
         // ===== TMA producer =====
-        const int nseg = p.num_segs;
-        const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
-        const void* map0 = &p.a_map[0];
-        const void* map1 = &p.a_map[1];
-        const void* map2 = &p.a_map[2];
-        const void* mapb = &p.b_map;
-        const uint32_t tx_bytes = (uint32_t)stage_bytes;
-        int stage = 0, sg = 0, k = 0, tap = 0;
-        int skb_cur = skb0;
-        const void* map_cur = map0;
-        int row = m0 + sm_tap[0];
+        int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        for (int kb = 0; kb < total_kb; ++kb) {
-            mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
-            if (elect_one()) {
-                const uint32_t fb = full_a + 8u * stage;
-                mbar_arrive_expect_tx_a(fb, tx_bytes);
-                tma_load_2d_a(smem_base + stage_off, map_cur, fb, k * kBlockK, row);
-                tma_load_2d_a(smem_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
-                if (ticks && kb == 0) ticks[2] = globaltimer_ns();
-            }
-            __syncwarp();
-            if (++k == skb_cur) {
-                k = 0;
-                if (++sg == nseg) { sg = 0; ++tap; row = m0 + sm_tap[tap < kMaxTaps ? tap : 0]; }
-                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
-            }
-            stage_off += (uint32_t)stage_bytes;
-            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-        }
+        produce_tile(p, m_tile, n0, total_kb, stages, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, ticks);
     } else if (warp == 1) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
@@ -489,7 +531,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         // The staging tiles reuse the (now idle) pipeline buffers: accum_bar completes only after every MMA has
         // finished reading them.
         const EpiCtx e = load_epi(p);
-        epilogue_tile<ACT, EPI>(e, m0, n0, block_n, tmem_base, smem_base, warp, lane, accum_bar, 0u, ticks);
+        epilogue_tile<ACT, EPI>(e, m_tile, n0, block_n, tmem_base, smem_base, warp, lane, accum_bar, 0u, ticks);
         if (ticks && warp == 2 && lane == 0) ticks[6] = globaltimer_ns();
     }
     tc_fence_before();
@@ -523,7 +565,6 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
     uint64_t* tfull_bar = empty_bar + stages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    int* sm_tap = reinterpret_cast<int*>(tmem_slot + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -542,7 +583,6 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
         tma_prefetch_desc(&p.b_map);
     }
     if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-    if (warp == 2 && lane < kMaxTaps) sm_tap[lane] = lane < p.num_taps ? p.tap_off[lane] : 0;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -553,39 +593,11 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
 
     if (warp == 0) {
         // ===== TMA producer (warp-uniform) =====
-        const int nseg = p.num_segs;
-        const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
-        const void* map0 = &p.a_map[0];
-        const void* map1 = &p.a_map[1];
-        const void* map2 = &p.a_map[2];
-        const void* mapb = &p.b_map;
-        const uint32_t tx_bytes = (uint32_t)stage_bytes;
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * block_n;
-            int sg = 0, k = 0, tap = 0, skb_cur = skb0;
-            const void* map_cur = map0;
-            int row = m0 + sm_tap[0];
-            for (int kb = 0; kb < total_kb; ++kb) {
-                mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
-                if (elect_one()) {
-                    const uint32_t fb = full_a + 8u * stage;
-                    mbar_arrive_expect_tx_a(fb, tx_bytes);
-                    tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
-                    tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
-                }
-                __syncwarp();
-                if (++k == skb_cur) {
-                    k = 0;
-                    if (++sg == nseg) { sg = 0; ++tap; row = m0 + sm_tap[tap < kMaxTaps ? tap : 0]; }
-                    skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-                    map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
-                }
-                stage_off += (uint32_t)stage_bytes;
-                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-            }
-        }
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x)
+            produce_tile(p, t / n_tiles, (t % n_tiles) * block_n, total_kb, stages, stage_bytes, pipe_base, full_a, empty_a,
+                         stage, phase, stage_off, nullptr);
     } else if (warp == 1) {
         // ===== MMA issuer (warp-uniform) =====
         const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
@@ -624,9 +636,9 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int buf = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int m0 = (t / n_tiles) * kBlockM, n0 = (t % n_tiles) * block_n;
+            const int m_tile = t / n_tiles, n0 = (t % n_tiles) * block_n;
             long long tk[16];
-            epilogue_tile<ACT, EPI>(e, m0, n0, block_n, tmem_base + (uint32_t)buf * 256u, stage_base, warp, lane,
+            epilogue_tile<ACT, EPI>(e, m_tile, n0, block_n, tmem_base + (uint32_t)buf * 256u, stage_base, warp, lane,
                                     &tfull_bar[buf], acc_phase, (ticks && warp == 2 && it < 3) ? tk : nullptr, kPersistEpiWarps / 4);
             if (ticks && warp == 2 && lane == 0 && it < 3) { ticks[3 + 4 * it] = tk[5]; ticks[4 + 4 * it] = globaltimer_ns(); }
             tc_fence_before();
@@ -710,46 +722,20 @@ gemm_tc_chain_kernel(const GemmParams* __restrict__ params, const ChainDesc cd, 
             const int rem = t - g * mt * nt;
             const GemmParams& p = params[cd.first[l] + g];
             const int block_n = p.block_n;
-            const int m0 = (rem / nt) * kBlockM, n0 = (rem % nt) * block_n;
+            const int m_tile = rem / nt, n0 = (rem % nt) * block_n;
             int kb_per_tap = 0;
             for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
             const int total_kb = kb_per_tap * p.num_taps;
             const uint32_t acc_phase = (uint32_t)tile_it & 1u;
-            if (m0 >= p.M || n0 >= p.N) {                        // member smaller than the group's grid: keep parities in step
+            if (m_tile * kBlockM >= p.M || n0 >= p.N) {          // member smaller than the group's grid: keep parities in step
                 if (warp >= 2) { /* nothing to drain */ }
                 --tile_it;
                 continue;
             }
             if (warp == 0) {
                 // ===== TMA producer (warp-uniform) =====
-                const int nseg = p.num_segs;
-                const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
-                const void* map0 = &p.a_map[0];
-                const void* map1 = &p.a_map[1];
-                const void* map2 = &p.a_map[2];
-                const void* mapb = &p.b_map;
-                const uint32_t tx_bytes = (uint32_t)(kAStageBytes + block_n * kBlockK * 2);
-                int sg = 0, k = 0, tap = 0, skb_cur = skb0;
-                const void* map_cur = map0;
-                int row = m0 + p.tap_off[0];
-                for (int kb = 0; kb < total_kb; ++kb) {
-                    mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
-                    if (elect_one()) {
-                        const uint32_t fb = full_a + 8u * stage;
-                        mbar_arrive_expect_tx_a(fb, tx_bytes);
-                        tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
-                        tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
-                    }
-                    __syncwarp();
-                    if (++k == skb_cur) {
-                        k = 0;
-                        if (++sg == nseg) { sg = 0; ++tap; row = m0 + p.tap_off[tap < kMaxTaps ? tap : 0]; }
-                        skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-                        map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
-                    }
-                    stage_off += (uint32_t)stage_bytes;
-                    if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-                }
+                produce_tile(p, m_tile, n0, total_kb, stages, stage_bytes, pipe_base, full_a, empty_a, stage, phase,
+                             stage_off, nullptr);
             } else if (warp == 1) {
                 // ===== MMA issuer (warp-uniform) =====
                 const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
@@ -777,11 +763,11 @@ gemm_tc_chain_kernel(const GemmParams* __restrict__ params, const ChainDesc cd, 
                 const EpiCtx e = load_epi(p);
                 const int kind = cd.kind[l];
                 if (kind == CHAIN_GELU_BF16_SAME)
-                    epilogue_tile<ACT_GELU, EPI_BF16_SAME>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                    epilogue_tile<ACT_GELU, EPI_BF16_SAME>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
                 else if (kind == CHAIN_HALF_TANH_GENERIC)
-                    epilogue_tile<ACT_HALF_TANH, EPI_GENERIC>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                    epilogue_tile<ACT_HALF_TANH, EPI_GENERIC>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
                 else
-                    epilogue_tile<ACT_NONE, EPI_GENERIC>(e, m0, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
+                    epilogue_tile<ACT_NONE, EPI_GENERIC>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar);
@@ -804,14 +790,19 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
     const int m = blockIdx.x;
     if (m >= p.M) return;
     const EpiCtx e = load_epi(p);
-    const RowCtx r = decode_row(e, m);
+    const RowCtx r = decode_row(e, m / kBlockM, m % kBlockM);
     if (!r.valid) return;
+    const bool conv = p.in_mode == IN_CONV;
     int kp_per_tap = 0;
     for (int sg = 0; sg < p.num_segs; ++sg) kp_per_tap += p.seg_kblocks[sg] * kBlockK;
     for (int col = threadIdx.x * 8; col < p.N; col += blockDim.x * 8) {
         float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int tap = 0; tap < p.num_taps; ++tap) {
-            const long long row = (long long)m + p.tap_off[tap];
+            long long row = r.lin;
+            if (conv) {                                          // zero padding: taps outside the image contribute nothing
+                const int yy = r.y + tap / 3 - 1, xx = r.x + tap % 3 - 1;
+                row = (yy >= 0 && yy < p.s && xx >= 0 && xx < p.s) ? (long long)r.n * p.K + yy * p.s + xx : -1;
+            }
             int kbase = tap * kp_per_tap;
             for (int sg = 0; sg < p.num_segs; ++sg) {
                 if (row >= 0 && row < p.a_rows[sg]) {
@@ -908,7 +899,7 @@ cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, i
 int gemm_epi_kind(const GemmParams& p) {
     const bool one_out = p.out[1].dtype == OUT_NONE && p.out[0].map == MAP_SAME;
     if (one_out && p.out[0].dtype == OUT_BF16 && p.resid == nullptr && p.act != ACT_HALF_TANH) return EPI_BF16_SAME;
-    if (one_out && p.out[0].dtype == OUT_F32 && p.resid != nullptr && p.resid_map == MAP_SAME && p.act == ACT_NONE)
+    if (one_out && p.in_mode != IN_CONV && p.out[0].dtype == OUT_F32 && p.resid != nullptr && p.resid_map == MAP_SAME && p.act == ACT_NONE)
         return EPI_F32_SAME_RESID;
     return EPI_GENERIC;
 }

@@ -42,10 +42,10 @@ cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
                              int rows, int C, int T, int drop_cls, float eps, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
-                              float* zhat, __nv_bfloat16* zhat_pad, int s4, double* rate_acc, int rows_per_image,
+                              float* zhat, __nv_bfloat16* zhat_bf, int s4, double* rate_acc, int rows_per_image,
                               cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
-                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_pad, int ld_pad,
+                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, int ld_bf,
                                   int s, double* rate_acc, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* sigma, long long n, float* lik,
                                  int32_t* sym, float* yhat, cudaStream_t st);
@@ -55,7 +55,6 @@ cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_pe
 cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* z, const float* mu, const float* sigma,
                                 const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
                                 cudaStream_t st);
-cudaError_t launch_compact_to_pad(const float* src, __nv_bfloat16* dst, long long rows, int C, int s, cudaStream_t st);
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
                                   const int* segc, int shuffle, cudaStream_t st);
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st);

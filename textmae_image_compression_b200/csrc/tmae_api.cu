@@ -85,13 +85,13 @@ struct Workspace {
     __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *h1 = nullptr, *enc = nullptr;
     float* x = nullptr;
     // g_a
-    __nv_bfloat16 *ga1 = nullptr, *ga2 = nullptr, *ga3 = nullptr, *y_pad = nullptr;
+    __nv_bfloat16 *ga1 = nullptr, *ga2 = nullptr, *ga3 = nullptr, *y_bf = nullptr;
     float *y = nullptr, *z = nullptr, *mu = nullptr, *sigma = nullptr, *yhat = nullptr;
     // h_a / h_s
-    __nv_bfloat16 *ha1 = nullptr, *ha2 = nullptr, *ha3 = nullptr, *ha4 = nullptr, *zhat_pad = nullptr;
+    __nv_bfloat16 *ha1 = nullptr, *ha2 = nullptr, *ha3 = nullptr, *ha4 = nullptr, *zhat_bf = nullptr;
     __nv_bfloat16 *hs1[2] = {nullptr, nullptr}, *hs2[2] = {nullptr, nullptr}, *hs3[2] = {nullptr, nullptr},
                   *hs4[2] = {nullptr, nullptr}, *lat[2] = {nullptr, nullptr};     // 0 = means, 1 = scales
-    __nv_bfloat16* yhat_pad = nullptr;
+    __nv_bfloat16* yhat_bf = nullptr;
     __nv_bfloat16* t[18][4] = {{nullptr}};     // [slice-group member j (0..5) * 3 + net (mean, scale, lrp)][layer]
     double* rate_acc = nullptr;
     float* bpp = nullptr;
@@ -106,7 +106,7 @@ struct Workspace {
 
 struct tmae_handle {
     tmae_config cfg;
-    int L, K, T, s, C, H, hd, mlp, Cy, Cz, nsl, sc, grid_w, patch_dim, P, s2, P2, s4, P4;
+    int L, K, T, s, C, H, hd, mlp, Cy, Cz, nsl, sc, grid_w, patch_dim, s2, s4;
     int ga_ch[5];
     std::string err;
     std::map<std::string, RawTensor> raw;
@@ -202,9 +202,8 @@ int derive_geometry(tmae_handle* h) {
     h->patch_dim = c.in_chans * c.patch_size * c.patch_size;
     if (c.patch_size % 4 != 0 || h->C % 128 != 0)
         return fail(nullptr, TMAE_EINVAL, "patch_size %% 4 and embed_dim %% 128 required");
-    h->P = (h->s + 1) * (h->s + 1);
-    h->s2 = h->s / 2; h->P2 = (h->s2 + 1) * (h->s2 + 1);
-    h->s4 = h->s / 4; h->P4 = (h->s4 + 1) * (h->s4 + 1);
+    h->s2 = h->s / 2;
+    h->s4 = h->s / 4;
     const int e = h->C, d = c.decoder_embed_dim;
     h->ga_ch[0] = e;
     h->ga_ch[1] = (int)(d + (e - d) * 3 / 4.0);
@@ -322,6 +321,46 @@ int make_map(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, 
     return TMAE_OK;
 }
 
+// Conv A operand: the compact channels-last tensor [n_img, s, s, C] seen as a 4-D tensor (C, x, y, n); one box is
+// [64 ch, s, box_y, box_n] = rows_used rows of 128 B in smem (row = (nl * box_y + yl) * s + x), SWIZZLE_128B.
+int make_map4d(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, int s, int n_img, uint64_t ld_elems,
+               int box_y, int box_n) {
+    cuuint64_t gdim[4] = {cols, (cuuint64_t)s, (cuuint64_t)s, (cuuint64_t)n_img};
+    cuuint64_t gstr[3] = {ld_elems * 2, (cuuint64_t)s * ld_elems * 2, (cuuint64_t)s * s * ld_elems * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)s, (cuuint32_t)box_y, (cuuint32_t)box_n};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (cols == 0 || s <= 0 || n_img <= 0) return fail(h, TMAE_EINVAL, "empty tensor map");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstr[0] & 15) != 0)
+        return fail(h, TMAE_EINVAL, "tensor map base/stride not 16-byte aligned");
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(4d) failed (%d): cols %llu s %d n %d ld %llu box %d x %d", (int)r,
+                    (unsigned long long)cols, s, n_img, (unsigned long long)ld_elems, box_y, box_n);
+    return TMAE_OK;
+}
+
+// Tiling of a conv layer over an s x s grid: a CTA tile is box_y image rows of box_n images (s * box_y * box_n <= 128
+// accumulator rows).  Pick the pair with the fewest tiles; ties go to whole images (contiguous output rows).
+struct ConvGeom { int box_y = 0, box_n = 0, y_tiles = 0, m_tiles = 0, rows_used = 0; };
+bool conv_geom(int s, int n_img, ConvGeom* g) {
+    if (s <= 0 || s > kBlockM || n_img <= 0) return false;
+    long long best = -1;
+    for (int by = (s < kBlockM / s ? s : kBlockM / s); by >= 1; --by) {
+        int bn = kBlockM / (s * by);
+        if (bn > n_img) bn = n_img;
+        if (bn > 256) bn = 256;
+        const int yt = (s + by - 1) / by;
+        const long long tiles = (long long)((n_img + bn - 1) / bn) * yt;
+        if (best < 0 || tiles < best) {
+            best = tiles;
+            g->box_y = by; g->box_n = bn; g->y_tiles = yt; g->m_tiles = (int)tiles; g->rows_used = s * by * bn;
+        }
+    }
+    return true;
+}
+
 // Choose the N tile: fewest column tiles that still give the machine >= ~120 CTAs (148 SMs), multiple of 16.
 int pick_block_n(int m_tiles, int N, int groups) {
     int best = round16(N) > 256 ? 256 : round16(N);
@@ -347,7 +386,8 @@ struct GemmDesc {
     long long a_rows = 0;       // rows of the A matrices
     int M = 0;                  // rows to compute
     int in_mode = IN_LINEAR;
-    int side = 0;               // grid side for IN_COMPACT / IN_PADDED
+    int side = 0;               // grid side for IN_COMPACT / IN_CONV
+    int n_img = 0;              // IN_CONV: images
     bool conv3 = false;
     int act = ACT_NONE;
     const float* resid = nullptr; int resid_ld = 0; int resid_map = MAP_SAME;
@@ -361,6 +401,14 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     memset(p, 0, sizeof(*p));
     const Layer& L = *d.layer;
     if (d.nseg != L.nseg) return fail(h, TMAE_EINVAL, "segment count mismatch");
+    const bool conv = d.in_mode == IN_CONV;
+    if (conv != (L.taps == 9)) return fail(h, TMAE_EINVAL, "3x3 layers need IN_CONV inputs (and only they)");
+    ConvGeom cg;
+    if (conv) {
+        if (!conv_geom(d.side, d.n_img, &cg)) return fail(h, TMAE_EINVAL, "conv grid side %d unsupported (1..128)", d.side);
+        if (d.M != cg.m_tiles * kBlockM || d.a_rows != (long long)d.n_img * d.side * d.side)
+            return fail(h, TMAE_EINVAL, "conv descriptor rows inconsistent with its geometry");
+    }
     p->num_segs = d.nseg;
     for (int i = 0; i < d.nseg; ++i) {
         if (d.seg[i].cols != L.segc[i]) return fail(h, TMAE_EINVAL, "segment %d width %d != packed %d", i, d.seg[i].cols, L.segc[i]);
@@ -369,22 +417,17 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
         p->a_cols[i] = d.seg[i].cols;
         p->a_rows[i] = d.a_rows;
         p->seg_kblocks[i] = pad64(d.seg[i].cols) / 64;
-        int rc = make_map(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
+        int rc = conv ? make_map4d(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_y, cg.box_n)
+                      : make_map(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
         if (rc) return rc;
     }
     p->b_ptr = L.w;
     p->b_ld = L.Kp;
     p->num_taps = L.taps;
     p->s = d.side;
-    p->P = (d.side + 1) * (d.side + 1);
     p->K = d.side * d.side;
     p->T = p->K + 1;
-    if (L.taps == 9) {
-        for (int kh = 0; kh < 3; ++kh)
-            for (int kw = 0; kw < 3; ++kw) p->tap_off[kh * 3 + kw] = (kh - 1) * (d.side + 1) + (kw - 1);
-    } else {
-        p->tap_off[0] = 0;
-    }
+    p->n_img = d.n_img; p->box_y = cg.box_y; p->box_n = cg.box_n; p->y_tiles = cg.y_tiles; p->rows_used = cg.rows_used;
     p->M = d.M;
     p->N = L.Cout;
     const int m_tiles = (d.M + kBlockM - 1) / kBlockM;
@@ -417,8 +460,8 @@ int ensure_workspace(tmae_handle* h, int N) {
     free_pool(w.allocs);
     w = Workspace();
     size_t tot = 0;
-    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rp = (size_t)N * h->P, rp2 = (size_t)N * h->P2,
-                 rp4 = (size_t)N * h->P4, rz = (size_t)N * h->s4 * h->s4;
+    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rz = (size_t)N * h->s4 * h->s4;
+    const size_t rp = rk, rp2 = (size_t)N * h->s2 * h->s2, rp4 = rz;      // every activation is compact: no halo rows
     const int C = h->C, Cy = h->Cy, Cz = h->Cz;
     int ci[5], co[5], aux[5];
 #define WS_ALLOC(field, count)                                                        \
@@ -434,7 +477,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.ga1, rk * h->ga_ch[1]);
     WS_ALLOC(w.ga2, rk * h->ga_ch[2]);
     WS_ALLOC(w.ga3, rk * h->ga_ch[3]);
-    WS_ALLOC(w.y_pad, rp * Cy);
+    WS_ALLOC(w.y_bf, rp * Cy);
     WS_ALLOC(w.y, rk * Cy);
     WS_ALLOC(w.z, rz * Cz);
     WS_ALLOC(w.mu, rk * Cy);
@@ -445,7 +488,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.ha2, rp * co[1]);
     WS_ALLOC(w.ha3, rp2 * co[2]);
     WS_ALLOC(w.ha4, rp2 * co[3]);
-    WS_ALLOC(w.zhat_pad, rp4 * Cz);
+    WS_ALLOC(w.zhat_bf, rp4 * Cz);
     hs_layers(h, ci, co, aux);
     for (int net = 0; net < 2; ++net) {
         WS_ALLOC(w.hs1[net], rp4 * co[0]);
@@ -454,7 +497,7 @@ int ensure_workspace(tmae_handle* h, int N) {
         WS_ALLOC(w.hs4[net], rp * co[3]);
         WS_ALLOC(w.lat[net], rp * Cy);
     }
-    WS_ALLOC(w.yhat_pad, rp * Cy);
+    WS_ALLOC(w.yhat_bf, rp * Cy);
     int ch[6];
     cc_channels(h, ch, 0, false);
     for (int net = 0; net < 18; ++net)
@@ -473,8 +516,8 @@ int ensure_workspace(tmae_handle* h, int N) {
 }
 
 size_t workspace_bytes_estimate(const tmae_handle* h, int N) {
-    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rp = (size_t)N * h->P, rp2 = (size_t)N * h->P2,
-                 rp4 = (size_t)N * h->P4;
+    const size_t rt = (size_t)N * h->T, rk = (size_t)N * h->K, rp = rk, rp2 = (size_t)N * h->s2 * h->s2,
+                 rp4 = (size_t)N * h->s4 * h->s4;
     const size_t C = h->C;
     size_t b = rk * 8 + rk * h->patch_dim * 2 + rt * C * 4 + rt * C * 2 * 2 + rt * 3 * C * 2 + rt * h->mlp * 2 + rk * C * 2;
     b += rk * (h->ga_ch[1] + h->ga_ch[2] + h->ga_ch[3]) * 2 + rp * h->Cy * 2 + rk * h->Cy * 4 * 4 + rk / 16 * h->Cz * 4;
@@ -515,7 +558,7 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         }
     }
     for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
-        if (descs[g].out0.map == MAP_SHUF_PAD || descs[g].out1.map == MAP_SHUF_PAD) bn = (bn + 31) / 32 * 32;
+        if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF) bn = (bn + 31) / 32 * 32;
     for (int g = 0; g < groups; ++g) {
         GemmParams p;
         int rc = fill_params(h, descs[g], groups, &p, bn);
@@ -606,9 +649,15 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     pl.N = N;
     Workspace& w = h->ws;
     const int C = h->C, T = h->T, K = h->K, s = h->s, Cy = h->Cy, Cz = h->Cz;
-    const long long rt = (long long)N * T, rk = (long long)N * K, rp = (long long)N * h->P, rp2 = (long long)N * h->P2,
-                    rp4 = (long long)N * h->P4;
+    const long long rt = (long long)N * T, rk = (long long)N * K;
     char tag[96];
+    // 3x3 conv input over a `side` x `side` grid of all N images (compact rows; the tile grid covers box_y x box_n blocks)
+    auto conv_in = [&](GemmDesc& d, int side) {
+        ConvGeom cg;
+        conv_geom(side, N, &cg);
+        d.in_mode = IN_CONV; d.side = side; d.n_img = N;
+        d.a_rows = (long long)N * side * side; d.M = cg.m_tiles * kBlockM;
+    };
     auto simple = [&](StepKind k, int fam, const char* t) { Step st; st.kind = k; st.family = fam; st.tag = t; pl.steps.push_back(st); };
 
     simple(ST_ZERO_RATE, FAM_MISC, "zero_rate");
@@ -678,7 +727,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
             d.seg[0] = seg(srcs[l], h->ga_ch[l], h->ga_ch[l]); d.a_rows = rk; d.M = (int)rk;
             d.in_mode = IN_COMPACT; d.side = s;
             if (l < 3) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], h->ga_ch[l + 1], OUT_BF16, MAP_SAME); }
-            else { d.out0 = outspec(w.y, Cy, OUT_F32, MAP_SAME); d.out1 = outspec(w.y_pad, Cy, OUT_BF16, MAP_TO_PAD); }
+            else { d.out0 = outspec(w.y, Cy, OUT_F32, MAP_SAME); d.out1 = outspec(w.y_bf, Cy, OUT_BF16, MAP_SAME); }
             d.flops = 2.0 * rk * h->ga_ch[l] * (double)h->ga_ch[l + 1];
             snprintf(tag, sizeof(tag), "g_a.%d", 2 * l);
             rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
@@ -688,17 +737,16 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     {   // h_a (MCM.py:115-129, 739)
         int ci[5], co[5], st[5];
         ha_layers(h, ci, co, st);
-        const __nv_bfloat16* srcs[5] = {w.y_pad, w.ha1, w.ha2, w.ha3, w.ha4};
+        const __nv_bfloat16* srcs[5] = {w.y_bf, w.ha1, w.ha2, w.ha3, w.ha4};
         __nv_bfloat16* dsts[4] = {w.ha1, w.ha2, w.ha3, w.ha4};
         const int sides[5] = {s, s, s, h->s2, h->s2};
-        const long long rows[5] = {rp, rp, rp, rp2, rp2};
         for (int l = 0; l < 5; ++l) {
             GemmDesc d;
             d.layer = get_layer(h, "h_a." + std::to_string(2 * l));
-            d.seg[0] = seg(srcs[l], ci[l], ci[l]); d.a_rows = rows[l]; d.M = (int)rows[l];
-            d.in_mode = IN_PADDED; d.side = sides[l];
-            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], co[l], OUT_BF16, st[l] == 2 ? MAP_S2_PAD : MAP_SAME); }
-            else d.out0 = outspec(w.z, Cz, OUT_F32, MAP_S2_COMPACT);
+            d.seg[0] = seg(srcs[l], ci[l], ci[l]);
+            conv_in(d, sides[l]);
+            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], co[l], OUT_BF16, st[l] == 2 ? MAP_S2 : MAP_SAME); }
+            else d.out0 = outspec(w.z, Cz, OUT_F32, st[l] == 2 ? MAP_S2 : MAP_SAME);
             const long long outpos = (long long)N * (sides[l] / st[l]) * (sides[l] / st[l]);
             d.flops = conv_flops(outpos, ci[l], co[l], 9);
             snprintf(tag, sizeof(tag), "h_a.%d", 2 * l);
@@ -710,18 +758,17 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         int ci[5], co[5], up[5];
         hs_layers(h, ci, co, up);
         const int sides[5] = {h->s4, h->s4, h->s2, h->s2, s};
-        const long long rows[5] = {rp4, rp4, rp2, rp2, rp};
         const char* nets[2] = {"h_s_mean", "h_s_scale"};
         for (int l = 0; l < 5; ++l) {
             GemmDesc d[2];
             for (int net = 0; net < 2; ++net) {
-                const __nv_bfloat16* srcs[5] = {w.zhat_pad, w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net]};
+                const __nv_bfloat16* srcs[5] = {w.zhat_bf, w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net]};
                 __nv_bfloat16* dsts[5] = {w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net], w.lat[net]};
                 d[net].layer = get_layer(h, std::string(nets[net]) + "." + std::to_string(2 * l));
-                d[net].seg[0] = seg(srcs[l], ci[l], ci[l]); d[net].a_rows = rows[l]; d[net].M = (int)rows[l];
-                d[net].in_mode = IN_PADDED; d[net].side = sides[l];
+                d[net].seg[0] = seg(srcs[l], ci[l], ci[l]);
+                conv_in(d[net], sides[l]);
                 d[net].act = l < 4 ? ACT_GELU : ACT_NONE;
-                d[net].out0 = outspec(dsts[l], co[l], OUT_BF16, up[l] == 2 ? MAP_SHUF_PAD : MAP_SAME);
+                d[net].out0 = outspec(dsts[l], co[l], OUT_BF16, up[l] == 2 ? MAP_SHUF : MAP_SAME);
                 d[net].flops = conv_flops((long long)N * sides[l] * sides[l], ci[l], co[l] * up[l] * up[l], 9);
             }
             snprintf(tag, sizeof(tag), "h_s.%d", 2 * l);
@@ -750,13 +797,13 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                     if (l == 0) {
                         g.seg[0] = seg(w.lat[net], Cy, Cy);
                         g.nseg = 1;
-                        if (sup > 0) { g.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); g.nseg = 2; }
+                        if (sup > 0) { g.seg[1] = seg(w.yhat_bf, h->sc * sup, Cy); g.nseg = 2; }
                     } else {
                         g.seg[0] = seg(w.t[j * 3 + net][l - 1], ch[l], ch[l]);
                     }
-                    g.a_rows = rp; g.M = (int)rp; g.in_mode = IN_PADDED; g.side = s;
+                    conv_in(g, s);
                     if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + net][l], ch[l + 1], OUT_BF16, MAP_SAME); }
-                    else g.out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
+                    else g.out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_SAME);
                     g.flops = conv_flops(rk, ch[l], ch[l + 1], 9);
                 }
             snprintf(tag, sizeof(tag), "cc.%d.%d", i0, 2 * l);
@@ -777,18 +824,18 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                     g.layer = get_layer(h, "lrp_transform." + std::to_string(i) + "." + std::to_string(2 * l));
                     if (l == 0) {
                         g.seg[0] = seg(w.lat[0], Cy, Cy);
-                        if (i < half_sl) { g.seg[1] = seg(w.yhat_pad, h->sc * (i + 1), Cy); g.nseg = 2; }
-                        else { g.seg[1] = seg(w.yhat_pad, h->sc * sup, Cy); g.seg[2] = seg(w.yhat_pad + i * h->sc, h->sc, Cy); g.nseg = 3; }
+                        if (i < half_sl) { g.seg[1] = seg(w.yhat_bf, h->sc * (i + 1), Cy); g.nseg = 2; }
+                        else { g.seg[1] = seg(w.yhat_bf, h->sc * sup, Cy); g.seg[2] = seg(w.yhat_bf + i * h->sc, h->sc, Cy); g.nseg = 3; }
                     } else {
                         g.seg[0] = seg(w.t[j * 3 + 2][l - 1], lch[l], lch[l]);
                     }
-                    g.a_rows = rp; g.M = (int)rp; g.in_mode = IN_PADDED; g.side = s;
+                    conv_in(g, s);
                     if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + 2][l], lch[l + 1], OUT_BF16, MAP_SAME); }
                     else {
                         g.act = ACT_HALF_TANH;
-                        g.resid = w.yhat + i * h->sc; g.resid_ld = Cy; g.resid_map = MAP_TO_COMPACT;
-                        g.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_TO_COMPACT);
-                        g.out1 = outspec(w.yhat_pad + i * h->sc, Cy, OUT_BF16, MAP_SAME);
+                        g.resid = w.yhat + i * h->sc; g.resid_ld = Cy; g.resid_map = MAP_SAME;
+                        g.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_SAME);
+                        g.out1 = outspec(w.yhat_bf + i * h->sc, Cy, OUT_BF16, MAP_SAME);
                     }
                     g.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
                 }
@@ -891,11 +938,11 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_EB:
                 CUDA_TRY(h, launch_bottleneck(w.z, h->eb_tab, (long long)N * h->s4 * h->s4, h->Cz, o.z_likelihoods,
-                                              o.z_symbols, o.z_hat, w.zhat_pad, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
+                                              o.z_symbols, o.z_hat, w.zhat_bf, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
                 break;
             case ST_GC:
                 CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc * sp.gc_slices,
-                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_pad, h->Cy, s, w.rate_acc, st, a.io));
+                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_bf, h->Cy, s, w.rate_acc, st, a.io));
                 break;
             case ST_RATE:
                 CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
@@ -1208,7 +1255,7 @@ int tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_o
     const size_t rk = (size_t)N * h->K;
     CUDA_TRY(h, cudaMemsetAsync(w.rate_acc, 0, sizeof(double) * N, st));
     CUDA_TRY(h, cudaMemcpyAsync(w.y, y, rk * h->Cy * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(h, launch_compact_to_pad(w.y, w.y_pad, (long long)rk, h->Cy, h->s, st));
+    CUDA_TRY(h, launch_f32_to_bf16(w.y, w.y_bf, (long long)rk * h->Cy, st));
     RunArgs a;
     a.out = out; a.begin = pl->first_rate_step; a.end = (int)pl->steps.size();
     if (h->profiling) h->prof_used = 0;
@@ -1414,32 +1461,27 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
     int rc = make_tmp_handle(tmp);
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const int P = (s + 1) * (s + 1), Kp = pad64(Cin) * 9;
+    const int Kp = pad64(Cin) * 9;
     std::vector<void*> pool;
-    __nv_bfloat16 *wp = nullptr, *xpad = nullptr;
-    float *bz = nullptr, *xf = nullptr;
-    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout)) ||
-        (rc = dev_alloc(tmp.get(), pool, &xpad, (size_t)N * P * Cin))) {
+    __nv_bfloat16* wp = nullptr;
+    float* bz = nullptr;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout))) {
         g_create_error = tmp->err; free_pool(pool); return rc;
     }
-    (void)xf;
     int sg[1] = {Cin};
     cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, st);
     if (bias) cudaMemcpyAsync(bz, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st);
-    // x bf16 compact NHWC -> haloed layout: one strided 2-D copy per image (s rows of s*Cin elements)
-    for (int n = 0; n < N && e == cudaSuccess; ++n)
-        e = cudaMemcpy2DAsync(xpad + (size_t)n * P * Cin, (size_t)(s + 1) * Cin * 2,
-                              reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)n * s * s * Cin, (size_t)s * Cin * 2,
-                              (size_t)s * Cin * 2, s, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "conv3x3 staging: %s", cudaGetErrorString(e)); }
     Layer L;
     L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.Kp = Kp;
+    ConvGeom cg;
+    if (!conv_geom(s, N, &cg)) { free_pool(pool); return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_bf16: grid side %d unsupported (1..128)", s); }
     GemmDesc d;
     d.layer = &L;
-    d.seg[0] = seg(xpad, Cin, Cin);
-    d.a_rows = (long long)N * P; d.M = N * P; d.in_mode = IN_PADDED; d.side = s;
+    d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(x), Cin, Cin);      // compact NHWC, read in place by 4-D TMA boxes
+    d.a_rows = (long long)N * s * s; d.M = cg.m_tiles * kBlockM; d.in_mode = IN_CONV; d.side = s; d.n_img = N;
     d.act = gelu ? ACT_GELU : ACT_NONE;
-    d.out0 = outspec(out, Cout, OUT_F32, MAP_TO_COMPACT);
+    d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);
     rc = engine_common(tmp.get(), d, 0, impl, st);
     if (rc) g_create_error = tmp->err;
     free_pool(pool);
