@@ -386,13 +386,20 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Pipeline stage = `kgroup` consecutive k-blocks (1, 2 or 4) behind ONE full / empty barrier pair:
+//   [A atom 0 .. A atom G-1][B atom 0 .. B atom G-1],  A atom = 128 rows x 128 B, B atom = block_n rows x 128 B.
+// Why: one producer <-> MMA handshake (wait, expect_tx / commit, wait) costs ~270-300 cycles per stage no matter how
+// many stages there are (scripts/ubench_sync.cu: 2..16 stages, blocking or probing waits, acquire or relaxed), while the
+// four MMAs of a k-block take 128 x block_n / 64 cycles: below block_n ~ 128 the handshake, not the tensor pipe, set the
+// pace.  Grouping k-blocks divides the handshakes per k-block by G at the same number of bytes in flight.
+// ---------------------------------------------------------------------------------------------------------
+
 // TMA producer of one CTA tile (called by a whole warp; WARP-UNIFORM: all 32 lanes run the loop on identical values and
 // only the TMA instructions are elect-predicated, so addresses and descriptors stay in uniform registers).
-// Linear row spaces: A tile = 2-D box [64 ch, 128 rows].  Conv: 4-D box [64 ch, s, box_y, box_n] at pixel offset (dx, dy)
+// Linear row spaces: A atom = 2-D box [64 ch, 128 rows].  Conv: 4-D box [64 ch, s, box_y, box_n] at pixel offset (dx, dy)
 // of the tap; TMA zero-fills whatever falls outside the image (and images >= n_img), which IS the conv's zero padding.
 // The pipeline position (stage / phase / stage_off) is carried across tiles by the caller.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages,
+__device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages, int kgroup,
                                              int stage_bytes, uint32_t pipe_base, uint32_t full_a, uint32_t empty_a,
                                              int& stage, uint32_t& phase, uint32_t& stage_off, long long* ticks) {
     const int nseg = p.num_segs;
@@ -405,27 +412,72 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     int y0 = 0, img0 = 0;
     if (conv) conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, img0);
     const int row = m_tile * kBlockM;
-    const uint32_t tx_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2 + p.block_n * kBlockK * 2);
+    const uint32_t b_atom = (uint32_t)(p.block_n * kBlockK * 2);
+    const uint32_t kb_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2) + b_atom;
+    const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
     int sg = 0, k = 0, skb_cur = skb0;
     int dx = -1, cy = y0 - 1;                              // taps in (kh, kw) row-major order = the weight packing order
     const void* map_cur = map0;
-    for (int kb = 0; kb < total_kb; ++kb) {
+    for (int kb = 0; kb < total_kb;) {
+        const int nk = min(kgroup, total_kb - kb);
         mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+        const uint32_t fb = full_a + 8u * stage;
+        if (elect_one()) mbar_arrive_expect_tx_a(fb, kb_bytes * (uint32_t)nk);
+        __syncwarp();
+        for (int j = 0; j < nk; ++j, ++kb) {
+            if (elect_one()) {
+                const uint32_t a_dst = pipe_base + stage_off + (uint32_t)(j * kAStageBytes);
+                if (conv) tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, cy, img0);
+                else tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
+                tma_load_2d_a(pipe_base + stage_off + b_base + (uint32_t)j * b_atom, mapb, fb, kb * kBlockK, n0);
+                if (ticks && kb == 0) ticks[2] = globaltimer_ns();
+            }
+            __syncwarp();
+            if (++k == skb_cur) {
+                k = 0;
+                if (++sg == nseg) { sg = 0; if (++dx > 1) { dx = -1; ++cy; } }
+                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+            }
+        }
+        stage_off += (uint32_t)stage_bytes;
+        if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+    }
+}
+
+// MMA issuer of one CTA tile (whole warp, warp-uniform like the producer): accumulates total_kb k-blocks into
+// tmem_acc, frees each pipeline stage with a tcgen05.commit and finally commits to `done_bar` (accumulator complete).
+__device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, int kgroup, int stage_bytes,
+                                         uint32_t pipe_base, uint32_t full_a, uint32_t empty_a, uint32_t tmem_acc,
+                                         uint32_t done_bar, int& stage, uint32_t& phase, uint32_t& stage_off,
+                                         long long* ticks, int tick_issue, int tick_done) {
+    const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+    const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);       // + (byte offset >> 4) selects stage / atom / k-slice
+    const uint32_t b_atom = (uint32_t)(block_n * kBlockK * 2);
+    const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
+    for (int kb = 0; kb < total_kb;) {
+        const int nk = min(kgroup, total_kb - kb);
+        mbar_wait_a(full_a + 8u * stage, phase);
+        tc_fence_after();
         if (elect_one()) {
-            const uint32_t fb = full_a + 8u * stage;
-            mbar_arrive_expect_tx_a(fb, tx_bytes);
-            if (conv) tma_load_4d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, dx, cy, img0);
-            else tma_load_2d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, row);
-            tma_load_2d_a(pipe_base + stage_off + kAStageBytes, mapb, fb, kb * kBlockK, n0);
-            if (ticks && kb == 0) ticks[2] = globaltimer_ns();
+            if (ticks && kb == 0 && tick_issue >= 0) ticks[tick_issue] = globaltimer_ns();
+            for (int j = 0; j < nk; ++j) {
+                const uint64_t a_desc = desc0 + (uint64_t)((stage_off + (uint32_t)(j * kAStageBytes)) >> 4);
+                const uint64_t b_desc = desc0 + (uint64_t)((stage_off + b_base + (uint32_t)j * b_atom) >> 4);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
+                    umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb + j) | k) != 0 ? 1u : 0u);
+                }
+            }
+            umma_commit_a(empty_a + 8u * stage);          // smem stage reusable once these MMAs retire
+            if (kb + nk == total_kb) {
+                umma_commit_a(done_bar);                  // accumulator complete
+                if (ticks && tick_done >= 0) ticks[tick_done] = globaltimer_ns();
+            }
         }
         __syncwarp();
-        if (++k == skb_cur) {
-            k = 0;
-            if (++sg == nseg) { sg = 0; if (++dx > 1) { dx = -1; ++cy; } }
-            skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-            map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
-        }
+        kb += nk;
         stage_off += (uint32_t)stage_bytes;
         if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
     }
@@ -433,7 +485,7 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
 
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
+gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup) {
     pdl_launch_dependents();
     const GemmParams& p = params[blockIdx.z];
     const int m_tile = blockIdx.x;
@@ -443,8 +495,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int block_n = p.block_n;
-    const int b_stage_bytes = block_n * kBlockK * 2;
-    const int stage_bytes = kAStageBytes + b_stage_bytes;
+    const int stage_bytes = kgroup * (kAStageBytes + block_n * kBlockK * 2);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* accum_bar = empty_bar + stages;
@@ -492,36 +543,13 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages) {
         // ===== TMA producer =====
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        produce_tile(p, m_tile, n0, total_kb, stages, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, ticks);
+        produce_tile(p, m_tile, n0, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, ticks);
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
-        const uint64_t desc0 = umma_smem_desc_sw128(smem_base);       // + (byte offset >> 4) selects stage / k-slice
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        for (int kb = 0; kb < total_kb; ++kb) {
-            mbar_wait_a(full_a + 8u * stage, phase);
-            tc_fence_after();
-            const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
-            const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
-            if (elect_one()) {
-                if (ticks && kb == 0) ticks[3] = globaltimer_ns();
-#pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
-                              (kb | k) != 0 ? 1u : 0u);
-                }
-                umma_commit_a(empty_a + 8u * stage);      // smem stage reusable once these MMAs retire
-                if (kb == total_kb - 1) {
-                    umma_commit(accum_bar);                // accumulator complete
-                    if (ticks) ticks[4] = globaltimer_ns();
-                }
-            }
-            __syncwarp();
-            stage_off += (uint32_t)stage_bytes;
-            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-        }
+        mma_tile(block_n, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, tmem_base, smem_u32(accum_bar),
+                 stage, phase, stage_off, ticks, 3, 4);
     } else {
         // ===== epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter alternate 32-column chunks) =====
         // Phase 1 (thread = accumulator row): TMEM -> registers -> smem staging tile (raw fp32 accumulators).
@@ -596,12 +624,10 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x)
-            produce_tile(p, t / n_tiles, (t % n_tiles) * block_n, total_kb, stages, stage_bytes, pipe_base, full_a, empty_a,
+            produce_tile(p, t / n_tiles, (t % n_tiles) * block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a,
                          stage, phase, stage_off, nullptr);
     } else if (warp == 1) {
         // ===== MMA issuer (warp-uniform) =====
-        const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
-        const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);
         int stage = 0, it = 0;
         uint32_t phase = 0, stage_off = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -609,24 +635,8 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&tempty_bar[buf], acc_phase ^ 1u);           // epilogue has drained this accumulator buffer
             tc_fence_after();
-            if (ticks && lane == 0 && it < 3) ticks[1 + 4 * it] = globaltimer_ns();
-            const uint32_t tmem_acc = tmem_base + (uint32_t)buf * 256u;
-            for (int kb = 0; kb < total_kb; ++kb) {
-                mbar_wait_a(full_a + 8u * stage, phase);
-                tc_fence_after();
-                const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
-                const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_a(empty_a + 8u * stage);
-                    if (kb == total_kb - 1) { umma_commit(&tfull_bar[buf]); if (ticks && it < 3) ticks[2 + 4 * it] = globaltimer_ns(); }
-                }
-                __syncwarp();
-                stage_off += (uint32_t)stage_bytes;
-                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-            }
+            mma_tile(block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, tmem_base + (uint32_t)buf * 256u,
+                     smem_u32(&tfull_bar[buf]), stage, phase, stage_off, it < 3 ? ticks : nullptr, 1 + 4 * it, 2 + 4 * it);
         }
     } else {
         // ===== epilogue warps =====
@@ -734,30 +744,14 @@ gemm_tc_chain_kernel(const GemmParams* __restrict__ params, const ChainDesc cd, 
             }
             if (warp == 0) {
                 // ===== TMA producer (warp-uniform) =====
-                produce_tile(p, m_tile, n0, total_kb, stages, stage_bytes, pipe_base, full_a, empty_a, stage, phase,
+                produce_tile(p, m_tile, n0, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, stage, phase,
                              stage_off, nullptr);
             } else if (warp == 1) {
                 // ===== MMA issuer (warp-uniform) =====
-                const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
-                const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);
                 mbar_wait(tempty_bar, acc_phase ^ 1u);             // previous tile's accumulator has been drained
                 tc_fence_after();
-                for (int kb = 0; kb < total_kb; ++kb) {
-                    mbar_wait_a(full_a + 8u * stage, phase);
-                    tc_fence_after();
-                    const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
-                    const uint64_t b_desc = a_desc + (uint64_t)(kAStageBytes >> 4);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k)
-                            umma_bf16(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                        umma_commit_a(empty_a + 8u * stage);
-                        if (kb == total_kb - 1) umma_commit(tfull_bar);
-                    }
-                    __syncwarp();
-                    stage_off += (uint32_t)stage_bytes;
-                    if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-                }
+                mma_tile(block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, tmem_base, smem_u32(tfull_bar),
+                         stage, phase, stage_off, nullptr, -1, -1);
             } else {
                 // ===== epilogue warps =====
                 const EpiCtx e = load_epi(p);
@@ -824,24 +818,28 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
-int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes) {
-    // The main loop is latency bound for small tiles (one TMA round trip per stage), so bytes in flight per SM is
-    // what matters.  A single wave (<= 148 CTAs) gets the whole shared memory of its SM; larger grids run two CTAs
-    // per SM so that one CTA's epilogue overlaps the other's main loop.
-    const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
-    const int overhead = 1024 + 256;
-    int stages;
+int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes, int* kgroup) {
+    // Small tiles are bound by (a) the TMA round trip: bytes in flight per SM is what matters, and (b) the ~300-cycle
+    // producer <-> MMA handshake per pipeline stage: see produce_tile.  A single wave (<= 148 CTAs) gets the whole
+    // shared memory of its SM; larger grids run two CTAs per SM so that one CTA's epilogue overlaps the other's loop.
     // share_sm: several handles / streams are in flight on this GPU, so even a single-wave launch keeps to half the
     // shared memory and lets a CTA of another stream's kernel co-reside (measured +9 % throughput at 3 streams).
-    if (total_ctas <= 148 && !share_sm) {
-        stages = (226 * 1024 - overhead) / stage_bytes;
-        if (stages > 10) stages = 10;
-    } else {
-        stages = (113 * 1024 - overhead) / stage_bytes;
-        if (stages > 6) stages = 6;
-    }
+    static const int force_g = getenv("TMAE_KGROUP") ? atoi(getenv("TMAE_KGROUP")) : 0;
+    const int atom = kAStageBytes + block_n * kBlockK * 2;
+    const int overhead = 1024 + 256;
+    const bool whole_sm = total_ctas <= 148 && !share_sm;
+    const int budget = (whole_sm ? 226 : 113) * 1024 - overhead;
+    const int max_kb_in_flight = whole_sm ? 10 : 6;
+    // two k-blocks per handshake once their 8 MMAs (128 x block_n / 32 cycles) no longer cover it, if >= 3 (whole SM) /
+    // >= 2 (half SM, the co-resident CTA fills the bubbles) such stages still fit
+    int g = 1;
+    if (block_n <= 128 && budget / (2 * atom) >= (whole_sm ? 3 : 2)) g = 2;
+    if (force_g == 1 || force_g == 2 || force_g == 4) { g = force_g; while (g > 1 && budget / (g * atom) < 2) g >>= 1; }
+    int stages = budget / (g * atom);
+    if (stages * g > max_kb_in_flight) stages = max_kb_in_flight / g;
     if (stages < 2) stages = 2;
-    *smem_bytes = overhead + stages * stage_bytes;
+    *kgroup = g;
+    *smem_bytes = overhead + stages * g * atom;
     return stages;
 }
 
@@ -925,14 +923,15 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
         return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
     }
-    const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem);
+    int kgroup = 1;
+    const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
     // every member of a grouped launch shares the activation and the store-phase specialisation
-    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
-    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
-    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
-    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
-    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
-    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages);
+    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ struct IoBlock {
 
 // gemm_tc.cu
 cudaError_t gemm_tc_configure();
-int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes);
+int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes, int* kgroup);
 int gemm_epi_kind(const GemmParams& p);
 cudaError_t gemm_chain_configure();
 cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream);

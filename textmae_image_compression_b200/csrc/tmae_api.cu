@@ -1358,10 +1358,10 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
         for (int c = 0; c < ctas; ++c) { if (t[c * 16] < tmin) tmin = t[c * 16]; if (t[c * 16 + 6] > tend) tend = t[c * 16 + 6]; }
         double avg[16] = {0};
         for (int c = 0; c < ctas; ++c) for (int k = 1; k < 12; ++k) avg[k] += (double)(t[c * 16 + k] - t[c * 16]) / ctas;
-        int smem = 0; const int stages = gemm_pick_stages(p.block_n, ctas, false, &smem);
-        fprintf(stderr, "[gemm timing] M=%d N=%d Kb=%d taps=%d bn=%d ctas=%d stages=%d smem=%d | kernel %.1f us (events), first-start..last-end %.1f us | "
+        int smem = 0, kgroup = 1; const int stages = gemm_pick_stages(p.block_n, ctas, false, &smem, &kgroup);
+        fprintf(stderr, "[gemm timing] M=%d N=%d Kb=%d taps=%d bn=%d ctas=%d stages=%d x%d smem=%d | kernel %.1f us (events), first-start..last-end %.1f us | "
                 "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f | first chunk: ldtm_done %.0f, staged %.0f, batch0 %.0f, batch1 %.0f\n",
-                p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, smem, ms * 1e3,
+                p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, kgroup, smem, ms * 1e3,
                 (tend - tmin) * 1e-3, avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[8], avg[9], avg[10], avg[11]);
         // steady-state cost of back-to-back dependent launches of this kernel: plain stream vs CUDA graph
         {
