@@ -1,6 +1,6 @@
 // Fused softmax attention over the visible tokens of one image and one head (timm 0.4.5 Attention.forward as
 // used by the encoder blocks, MCM.py:313-322, 629-630):  softmax((q k^T) * hd^-0.5) v, head_dim = 64, T <= ~300.
-// One CTA per (image, head); K and V^T of all T keys stay in shared memory, each warp owns 16-query tiles and runs
+// One CTA per (image, head); K and V of all T keys stay in shared memory, each warp owns 16-query tiles and runs
 // an online-softmax loop over 16-key chunks; S and P never leave registers.  bf16 tensor-core math
 // (mma.sync m16n8k16, fp32 accumulate): this op is 1.7-3 % of the path's FLOPs, so it uses the legacy
 // warp-level MMA; the GEMM / conv engine (gemm_tc.cu) is where tcgen05 is spent.
@@ -24,7 +24,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
 // qkv: bf16 [N*T, 3C] with columns [3][H][64] (timm reshape (B,T,3,H,hd)); out: bf16 [N*T, C] columns [H][64].
+// K and V of all keys are staged ROW-major (pitch 72 elements: the 8 rows of an ldmatrix tile fall in distinct bank
+// groups); B fragments come from ldmatrix (K: plain, V: .trans), so there is no transposed copy of V and no scalar
+// shared-memory traffic in the loop.
 // 6 CTAs/SM (<= 85 registers): N*H = 768 CTAs at batch 64 fit one wave of 888 slots instead of 1.04 waves of 740
 __global__ void __launch_bounds__(kAttnThreads, 6)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
@@ -33,16 +45,15 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     pdl_launch_dependents();
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);            // [Tp][KPITCH]
-    __nv_bfloat16* sVt = sK + (size_t)Tp * KPITCH;                               // [HD][Tp + 8]
-    const int vpitch = Tp + 8;
+    __nv_bfloat16* sV = sK + (size_t)Tp * KPITCH;                                // [Tp][KPITCH]
     const int n = blockIdx.x / H, h = blockIdx.x - n * H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const size_t ld = (size_t)3 * C;
     const __nv_bfloat16* base = qkv + (size_t)n * T * ld + (size_t)h * HD;
 
-    // ---- stage K (row-major) and V (transposed) for all keys; zero the padding ----
-#pragma unroll 2
+    // ---- stage K and V for all keys (16-byte chunks, coalesced: 8 threads per key row); zero the padding ----
+#pragma unroll 4
     for (int e = tid; e < Tp * (HD / 8); e += kAttnThreads) {
         const int key = e / (HD / 8), c8 = (e - key * (HD / 8)) * 8;
         uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
@@ -51,11 +62,16 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
             vv = *reinterpret_cast<const uint4*>(base + (size_t)key * ld + 2 * C + c8);
         }
         *reinterpret_cast<uint4*>(sK + (size_t)key * KPITCH + c8) = kv;
-        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sVt[(size_t)(c8 + i) * vpitch + key] = ve[i];
+        *reinterpret_cast<uint4*>(sV + (size_t)key * KPITCH + c8) = vv;
     }
     __syncthreads();
+
+    const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+    // per-lane ldmatrix row addresses (bytes) relative to the first key of a chunk
+    //   K (plain):  matrix j = lane >> 3 covers d columns [8j, 8j+8) of keys (lane & 7)           (+32 columns for the 2nd load)
+    //   V (.trans): matrices (keys 0-7, d0) (keys 8-15, d0) (keys 0-7, d0+8) (keys 8-15, d0+8)
+    const uint32_t k_lane = (uint32_t)(((lane & 7) * KPITCH + (lane >> 3) * 8) * 2);
+    const uint32_t v_lane = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * KPITCH + (lane >> 4) * 8) * 2);
 
     const int q_tiles = Tp / 16;
     for (int qt = warp; qt < q_tiles; qt += kAttnThreads / 32) {
@@ -84,13 +100,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
                 sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-                const __nv_bfloat16* krow = sK + (size_t)(k0 + nt * 8 + g) * KPITCH + 2 * t;
-#pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
-                    mma_bf16_16816(sacc[nt], qa[ks], b0, b1);
-                }
+                const uint32_t ka = sK_a + (uint32_t)((k0 + nt * 8) * KPITCH * 2) + k_lane;
+                uint32_t kb0[4], kb1[4];
+                ldmatrix_x4(kb0, ka);              // d 0..31 : (b0, b1) of k-steps 0 and 1
+                ldmatrix_x4(kb1, ka + 64);         // d 32..63: k-steps 2 and 3
+                mma_bf16_16816(sacc[nt], qa[0], kb0[0], kb0[1]);
+                mma_bf16_16816(sacc[nt], qa[1], kb0[2], kb0[3]);
+                mma_bf16_16816(sacc[nt], qa[2], kb1[0], kb1[1]);
+                mma_bf16_16816(sacc[nt], qa[3], kb1[2], kb1[3]);
             }
             // scale (log2 domain), mask padded keys
             float cmax0 = -INFINITY, cmax1 = -INFINITY;
@@ -129,13 +146,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
             for (int dt = 0; dt < 8; ++dt) {
                 o[dt][0] *= corr0; o[dt][1] *= corr0; o[dt][2] *= corr1; o[dt][3] *= corr1;
             }
-            // O += P (16 x 16 keys) * V[k0..k0+16) (16 keys x 64)
+            // O += P (16 x 16 keys) * V[k0..k0+16) (16 keys x 64): one transposing ldmatrix per pair of 8-wide d tiles
+            const uint32_t va = sV_a + (uint32_t)(k0 * KPITCH * 2) + v_lane;
 #pragma unroll
-            for (int dt = 0; dt < 8; ++dt) {
-                const __nv_bfloat16* vrow = sVt + (size_t)(dt * 8 + g) * vpitch + k0 + 2 * t;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vrow);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vrow + 8);
-                mma_bf16_16816(o[dt], pa, b0, b1);
+            for (int dp = 0; dp < 4; ++dp) {
+                uint32_t vb[4];
+                ldmatrix_x4_trans(vb, va + (uint32_t)(dp * 32));
+                mma_bf16_16816(o[2 * dp], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[2 * dp + 1], pa, vb[2], vb[3]);
             }
         }
         // row sums live per quad: reduce across the 4 lanes that share a row
@@ -158,7 +176,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 inline int attn_tp(int T) { return (T + 15) / 16 * 16; }
 inline size_t attn_smem(int T) {
     const int Tp = attn_tp(T);
-    return ((size_t)Tp * KPITCH + (size_t)HD * (Tp + 8)) * sizeof(__nv_bfloat16);
+    return (size_t)2 * Tp * KPITCH * sizeof(__nv_bfloat16);
 }
 
 }  // namespace

@@ -483,10 +483,27 @@ __device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, 
     }
 }
 
+// Weights are read once per forward (350 MB per step > L2), so the first touch of every B tile would pay the HBM round
+// trip inside a latency-bound main loop.  Each launch therefore pulls the weight matrices of the NEXT GEMM step of the
+// plan into L2 while it computes: every CTA prefetches its 1/ctas slice of each matrix (one bulk-prefetch instruction
+// per matrix, issued by one otherwise idle epilogue lane before the dependency wait - weights never change).
+__device__ __forceinline__ void prefetch_next_weights(const GemmParams* __restrict__ next, int next_groups, int cta, int nctas) {
+    for (int g = 0; g < next_groups; ++g) {
+        const size_t bytes = (size_t)next[g].N * (size_t)next[g].b_ld * 2;
+        size_t chunk = ((bytes + nctas - 1) / nctas + 127) & ~(size_t)127;
+        const size_t off = (size_t)cta * chunk;
+        if (off >= bytes) continue;
+        if (off + chunk > bytes) chunk = (bytes - off) & ~(size_t)15;
+        if (chunk) l2_prefetch_bulk(reinterpret_cast<const char*>(next[g].b_ptr) + off, (uint32_t)chunk);
+    }
+}
+
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup) {
+gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, const GemmParams* __restrict__ next, int next_groups) {
     pdl_launch_dependents();
+    if (next != nullptr && threadIdx.x == 64)
+        prefetch_next_weights(next, next_groups, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z);
     const GemmParams& p = params[blockIdx.z];
     const int m_tile = blockIdx.x;
     const int n0 = blockIdx.y * p.block_n;
@@ -580,8 +597,9 @@ constexpr int kEpiStageBytes = kPersistEpiWarps * 32 * kEpiPitch * 4;   // dedic
 
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kPersistThreads, 1)
-gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int m_tiles, int n_tiles) {
+gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int m_tiles, int n_tiles, const GemmParams* __restrict__ next, int next_groups) {
     pdl_launch_dependents();
+    if (next != nullptr && threadIdx.x == 64) prefetch_next_weights(next, next_groups, blockIdx.x, gridDim.x);
     const GemmParams& p = params[0];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -904,7 +922,7 @@ int gemm_epi_kind(const GemmParams& p) {
 
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
-                        bool simt, bool share_sm, cudaStream_t stream) {
+                        bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
         gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
@@ -920,18 +938,18 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         const int psmem = overhead + pst * stage_bytes;
         const int tiles = (int)(grid.x * grid.y);
         const int ctas = tiles < 148 ? tiles : 148;
-        if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
-        return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y);
+        if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
+        return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
     }
     int kgroup = 1;
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
     // every member of a grouped launch shares the activation and the store-phase specialisation
-    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
-    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
-    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
-    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
-    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
-    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup);
+    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,7 @@ struct Step {
     int family = FAM_MISC;
     // GEMM
     int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0, epi = 0;
+    int next_index = -1, next_groups = 0;      // parameter blocks of the next GEMM step (weight prefetch target)
     double flops = 0, bytes = 0;
     // fused chain of layers (ST_CHAIN)
     ChainDesc chain;
@@ -851,6 +852,15 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
 
     for (const Step& st : pl.steps)
         if (st.kind == ST_GEMM && pl.host_params[st.param_index].num_segs < 1) return fail(h, TMAE_EINVAL, "bad plan");
+    if (!getenv("TMAE_NO_WEIGHT_PREFETCH")) {      // each GEMM step prefetches the weights of the next one (cyclically)
+        std::vector<int> gemm_steps;
+        for (size_t i = 0; i < pl.steps.size(); ++i) if (pl.steps[i].kind == ST_GEMM) gemm_steps.push_back((int)i);
+        for (size_t k = 0; k < gemm_steps.size(); ++k) {
+            const Step& nx = pl.steps[gemm_steps[(k + 1) % gemm_steps.size()]];
+            pl.steps[gemm_steps[k]].next_index = nx.param_index;
+            pl.steps[gemm_steps[k]].next_groups = nx.groups;
+        }
+    }
     void* dp = nullptr;
     CUDA_TRY(h, cudaMalloc(&dp, pl.host_params.size() * sizeof(GemmParams)));
     pl.d_params = reinterpret_cast<GemmParams*>(dp);
@@ -922,7 +932,8 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                                                   h->cfg.in_chans, h->cfg.patch_size, st, a.io));
                 break;
             case ST_GEMM:
-                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st));
+                CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
+                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups));
                 break;
             case ST_CHAIN:
                 CUDA_TRY(h, gemm_chain_launch(pl.d_params, sp.chain, sp.chain_grid, sp.chain_max_bn, st));
