@@ -34,6 +34,6 @@ with open(dst + ".csv", "w") as fo:
     fo.write("launch,kernel,grid,duration_us,dram_read_bytes,dram_write_bytes,tensor_pipe_active_pct\n")
     for i in sorted(launch):
         d = launch[i]
-        fo.write(f'{i},{d["kernel"]},"{d["grid"]}",{d.get("gpu__time_duration.sum", 0) / 1e3:.2f},{d.get("dram__bytes_read.sum", 0):.0f},'
+        fo.write(f'{i},"{d["kernel"]}","{d["grid"]}",{d.get("gpu__time_duration.sum", 0) / 1e3:.2f},{d.get("dram__bytes_read.sum", 0):.0f},'
                  f'{d.get("dram__bytes_write.sum", 0):.0f},{d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", 0):.2f}\n')
 print(json.dumps(out, indent=1))

@@ -24,7 +24,12 @@ def test_gemm_matches_torch(cuda_dev, M, N, K, bn, impl):
 
 
 @pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (2, 4, 192, 240, True),
-                                                  (5, 8, 80, 32, False), (1, 16, 576, 224, True)])
+                                                  (5, 8, 80, 32, False), (1, 16, 576, 224, True),
+                                                  # tile geometries of the compact 4-D TMA conv: ragged image groups (box_n
+                                                  # tails), row tiles of one image, tiny and odd grids, the B64 slice shape
+                                                  (7, 12, 64, 48, False), (9, 6, 128, 64, True), (20, 3, 64, 32, False),
+                                                  (40, 2, 192, 96, False), (1, 8, 64, 32, False), (2, 32, 64, 32, False),
+                                                  (64, 8, 352, 224, True)])
 @pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
 def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin)
