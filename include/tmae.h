@@ -147,8 +147,9 @@ TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, fl
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
                        int Cin, int Cout, int gelu, int impl, void* stream);
 
-/* Per-kernel-family device timing (bench.py roofline): when enabled every launch of tmae_forward is bracketed
- * by CUDA events on `stream`; read after synchronising. */
+/* Per-kernel-family device timing (bench.py roofline): enable = 1 brackets every launch of tmae_forward with CUDA
+ * events on `stream`; enable = 2 brackets every RUN of consecutive launches of one kernel family (keeps the
+ * launch-to-launch overlap inside a run, no event gap between its members); 0 = off.  Read after synchronising. */
 typedef struct {
     char   name[32];
     int32_t launches;

@@ -126,6 +126,8 @@ struct tmae_handle {
     cudaStream_t cap_stream = nullptr;
     // profiling
     bool profiling = false;
+    bool prof_by_run = false;        // one event pair per run of consecutive same-family launches instead of per launch
+    std::vector<int> prof_launches;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     std::vector<int> prof_family;
     std::vector<double> prof_flops, prof_bytes;
@@ -891,6 +893,7 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
         h->prof_tag.push_back("");
         h->prof_ctas.push_back(0);
         h->prof_bn.push_back(0);
+        h->prof_launches.push_back(0);
     }
     *a = h->prof_events[h->prof_used].first;
     *b = h->prof_events[h->prof_used].second;
@@ -900,6 +903,7 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
     h->prof_tag[h->prof_used] = st.tag;
     h->prof_ctas[h->prof_used] = st.kind == ST_CHAIN ? st.chain_grid : st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
     h->prof_bn[h->prof_used] = (st.kind == ST_GEMM || st.kind == ST_CHAIN) ? st.block_n : 0;
+    h->prof_launches[h->prof_used] = 1;
     ++h->prof_used;
     return TMAE_OK;
 }
@@ -913,10 +917,19 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
     for (int si = a.begin; si < a.end; ++si) {
         const Step& sp = pl.steps[si];
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (h->profiling) {
+        // profiling: per launch, or (prof_by_run) per run of consecutive launches of one kernel family, which keeps
+        // the launch-to-launch overlap inside a run and drops the event gap between its members
+        const bool run_start = !h->prof_by_run || si == a.begin || pl.steps[si - 1].family != sp.family;
+        const bool run_end = !h->prof_by_run || si + 1 == a.end || pl.steps[si + 1].family != sp.family;
+        if (h->profiling && run_start) {
             int rc = prof_slot(h, sp, &e0, &e1);
             if (rc) return rc;
             CUDA_TRY(h, cudaEventRecord(e0, st));
+        } else if (h->profiling) {
+            const size_t cur = h->prof_used - 1;
+            h->prof_flops[cur] += sp.flops;
+            h->prof_bytes[cur] += sp.bytes;
+            h->prof_launches[cur] += 1;
         }
         switch (sp.kind) {
             case ST_ZERO_RATE:
@@ -962,7 +975,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
             case ST_Y_TO_PAD:
                 break;
         }
-        if (h->profiling) CUDA_TRY(h, cudaEventRecord(e1, st));
+        if (h->profiling && run_end) CUDA_TRY(h, cudaEventRecord(h->prof_events[h->prof_used - 1].second, st));
     }
     return TMAE_OK;
 }
@@ -1503,6 +1516,7 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
 int tmae_profile_enable(tmae_handle* h, int enable) {
     if (!h) return TMAE_EINVAL;
     h->profiling = enable != 0;
+    h->prof_by_run = enable == 2;
     h->prof_used = 0;
     return TMAE_OK;
 }
@@ -1517,7 +1531,7 @@ int tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entri
         cudaError_t e = cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second);
         if (e != cudaSuccess) return fail(h, TMAE_ECUDA, "cudaEventElapsedTime: %s (synchronise the stream first)", cudaGetErrorString(e));
         tmae_profile_entry& f = fam[h->prof_family[i]];
-        f.launches += 1;
+        f.launches += h->prof_launches[i];
         f.ms += ms;
         f.flops += h->prof_flops[i];
         f.bytes += h->prof_bytes[i];

@@ -328,9 +328,10 @@ class MCM(nn.Module):
         raise NotImplementedError("bitstream decoding is outside this path (SURVEY 8f-1)")
 
     # ------------------------------------------------------------------ profiling hooks (bench.py)
-    def profile(self, enable: bool):
+    def profile(self, enable: bool, by_run: bool = False):
+        """Device timing of the next forwards: per launch, or per run of consecutive same-family launches (by_run)."""
         self._ensure_handle()
-        _native.check(_native.load().tmae_profile_enable(self._handle, 1 if enable else 0), self._handle)
+        _native.check(_native.load().tmae_profile_enable(self._handle, (2 if by_run else 1) if enable else 0), self._handle)
 
     def profile_read(self):
         arr = (_native.TmaeProfileEntry * 16)()
