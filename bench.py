@@ -211,12 +211,15 @@ def run_b200(args, kwargs, batch, desc, wl):
     # every handle needs 3 forwards before it is in steady state (plain launches, graph capture, first replay) and its
     # stream's allocator pool is populated: warm up max(W, 3 S) steps so none of that lands in the timed region
     warm_eff = max(args.warmup, 3 * S)
-    for i in range(warm_eff):
-        step_dev(i)
-    barrier()
+    # the clock sampler (nvidia-smi -lms 100) starts BEFORE the warm-up: its process start / NVML initialisation stalls
+    # the GPU for tens of ms, which must not fall into a 40 ms timed region; it then samples through both timed regions
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for i in range(warm_eff):
+        step_dev(i)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     fork(e0)
@@ -299,6 +302,12 @@ def run_b200(args, kwargs, batch, desc, wl):
                         next(f for f in fams_launch if f["name"] == "gemm_tc")),
                     "families": {f["name"]: {"ms": round(f["ms"], 4), "launches": f["launches"]} for f in fams}}
 
+    # memory-bound kernel families against the measured HBM peak (algorithmic bytes / per-launch event time; these
+    # launches move 0.1-19 MB each, i.e. they are launch-latency bound at batch 64 - SURVEY 8d)
+    hbm_kernels = {f["name"]: {"GB/s": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1), "launches": f["launches"],
+                               "MB_per_launch": round(f["bytes"] / f["launches"] / 1e6, 3),
+                               "frac_of_hbm_peak": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
+                   for f in fams_launch if f["bytes"] > 0 and f["ms"] > 0}
     launches = model.launch_count(batch)
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ---------------------------
@@ -332,7 +341,7 @@ def run_b200(args, kwargs, batch, desc, wl):
                        "algorithmic_gflop_per_image": ALGO_GFLOP_PER_IMG.get(wl)},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "model_tflops": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3,
             "model_tflops_frac_of_peak": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3 / peaks["bf16_tflops_sustained"],
             "bpp_mean_last_step": out["bpp"].mean().item(),

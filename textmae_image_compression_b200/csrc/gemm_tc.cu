@@ -509,8 +509,11 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
     const int n0 = blockIdx.y * p.block_n;
     if (m_tile * kBlockM >= p.M || n0 >= p.N) return;   // grouped launches: grid is sized for the largest member
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // no static shared memory in this kernel, so the declared alignment puts the dynamic window on a 1024-byte boundary
+    // (SWIZZLE_128B atoms); checked rather than padded: the 1 KB matters for the two-CTA-per-SM configurations
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("tmae: dynamic shared memory not 1024-byte aligned\n"); __trap(); }
     const int block_n = p.block_n;
     const int stage_bytes = kgroup * (kAStageBytes + block_n * kBlockK * 2);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -844,7 +847,7 @@ int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes
     // shared memory and lets a CTA of another stream's kernel co-reside (measured +9 % throughput at 3 streams).
     static const int force_g = getenv("TMAE_KGROUP") ? atoi(getenv("TMAE_KGROUP")) : 0;
     const int atom = kAStageBytes + block_n * kBlockK * 2;
-    const int overhead = 1024 + 256;
+    const int overhead = 256;                       // barriers + TMEM slot (the pipeline itself starts at offset 0)
     const bool whole_sm = total_ctas <= 148 && !share_sm;
     const int budget = (whole_sm ? 226 : 113) * 1024 - overhead;
     const int max_kb_in_flight = whole_sm ? 10 : 6;

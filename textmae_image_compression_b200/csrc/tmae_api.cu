@@ -852,6 +852,18 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     }
     simple(ST_RATE, FAM_ENTROPY, "rate_finalize");
 
+    // algorithmic HBM bytes of the memory-bound kernels (bench.py reports them against the measured HBM peak)
+    for (Step& st : pl.steps) {
+        const double rows_t = (double)N * T, rows_k = (double)N * K, rows_z = (double)N * h->s4 * h->s4;
+        switch (st.kind) {
+            case ST_LN: st.bytes = st.ln_final ? rows_t * C * 4 + rows_k * C * (2 + 4) : rows_t * C * (4 + 2); break;
+            case ST_MASK: st.bytes = (double)N * h->L * (4 + 8 + 8) + rows_k * 8; break;
+            case ST_GATHER: st.bytes = rows_k * h->patch_dim * (4 + 2) + (double)N * C * 4; break;
+            case ST_EB: st.bytes = rows_z * Cz * (4 + 4 + 4 + 4 + 2); break;
+            case ST_GC: st.bytes = rows_k * h->sc * st.gc_slices * (3 * 4 + 3 * 4 + 2); break;
+            default: break;
+        }
+    }
     for (const Step& st : pl.steps)
         if (st.kind == ST_GEMM && pl.host_params[st.param_index].num_segs < 1) return fail(h, TMAE_EINVAL, "bad plan");
     if (!getenv("TMAE_NO_WEIGHT_PREFETCH")) {      // each GEMM step prefetches the weights of the next one (cyclically)
