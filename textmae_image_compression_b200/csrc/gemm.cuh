@@ -40,6 +40,7 @@ struct OutSpec {
 struct alignas(64) GemmParams {
     CUtensorMap a_map[kMaxSegs];      // linear: [rows, C_seg] box 64 x 128; conv: [C_seg, s, s, n_img] box 64 x s x box_y x box_n
     CUtensorMap b_map;                // [N, Kpacked] bf16, box 64 x block_n, SWIZZLE_128B
+    CUtensorMap out_map;              // TMA-store epilogue only: out[0] as [rows, N] bf16, box 32 x 128, SWIZZLE_64B
     // raw views of the same operands (CUDA-core checker kernel)
     const __nv_bfloat16* a_ptr[kMaxSegs];
     int a_ld[kMaxSegs];
@@ -64,6 +65,7 @@ struct alignas(64) GemmParams {
     int box_y, box_n;                 // conv: image rows / images per CTA tile
     int rows_used;                    // conv: s * box_y * box_n (<= 128) accumulator rows that hold pixels
     int y_tiles;                      // conv: ceil(s / box_y)
+    int tma_store_ok;                 // out_map is valid and the tile's accumulator rows are 128 consecutive output rows
     // epilogue
     const float* bias;                // [N] (already permuted for MAP_SHUF)
     int act;

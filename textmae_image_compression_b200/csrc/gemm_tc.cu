@@ -27,6 +27,7 @@ struct EpiCtx {
     const float* resid;
     const int64_t* gather_ids;
     OutSpec out[2];
+    const void* out_map;
     int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used;
 };
 
@@ -34,6 +35,7 @@ __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
     EpiCtx e;
     e.bias = p.bias; e.resid = p.resid; e.gather_ids = p.gather_ids;
     e.out[0] = p.out[0]; e.out[1] = p.out[1];
+    e.out_map = &p.out_map;
     e.act = p.act; e.resid_ld = p.resid_ld; e.resid_map = p.resid_map;
     e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.K = p.K; e.T = p.T;
     e.n_img = p.n_img; e.box_y = p.box_y; e.box_n = p.box_n; e.y_tiles = p.y_tiles; e.rows_used = p.rows_used;
@@ -212,7 +214,10 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 //   EPI_GENERIC        any row map / two outputs / gathered residual (patch embed, g_a.6, strided, PixelShuffle, mu/sigma, LRP)
 //   EPI_BF16_SAME      one bf16 output at the accumulator's own row (QKV, fc1, g_a.0-4, every conv mid layer)
 //   EPI_F32_SAME_RESID one fp32 output at the accumulator's own row with an fp32 residual at the same row (proj, fc2)
-enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2 };
+//   EPI_BF16_TMA       EPI_BF16_SAME when the tile is 128 consecutive output rows and block_n % 32 == 0: bias/activation in
+//                      registers, bf16 boxes of 32 columns staged in smem (64B swizzle) and written by TMA stores
+enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2, EPI_BF16_TMA = 3 };
+constexpr uint32_t kStoreBoxBytes = kBlockM * 32 * 2;      // one 128 x 32 bf16 box
 
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue of one 128 x block_n accumulator tile, executed by the 8 epilogue warps (warp index 2..9; TMEM lane
@@ -229,6 +234,53 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
     const int half = (warp - 2) >> 2;                  // which of the `nsub` warps of this TMEM lane quarter
     const int cstride = 32 * nsub;
     const int m0 = m_tile * kBlockM;                   // first row of the tile in a linear row space
+    if (EPI == EPI_BF16_TMA) {
+        // Thread = accumulator row: TMEM -> registers, + bias, activation, pack to bf16, 4 x 16-byte swizzled smem stores
+        // into a 128 x 32 box; the four warps that share a column subset (`half`) sync on a named barrier and one thread
+        // hands the box to the TMA (which clips rows >= M and columns >= N).  Two boxes per subset are in flight.
+        const int row = quarter * 32 + lane;
+        const uint32_t row_off = (uint32_t)row * 64u, sw = (uint32_t)((row >> 1) & 3);
+        const uint32_t buf0 = stage_base + (uint32_t)half * 2u * kStoreBoxBytes;
+        const bool issuer = quarter == 0 && lane == 0;
+        const int bar_id = 1 + half;
+        const int out_row0 = decode_row(e, m_tile, 0).lin;           // conv tiles on this path are contiguous pixel rows
+        const int nboxes = block_n >> 5;
+        mbar_wait(wait_bar, wait_parity);
+        tc_fence_after();
+        if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
+        const uint32_t lane_base = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+        int it = 0;
+        for (int b = half; b < nboxes; b += nsub, ++it) {
+            const int c0 = b * 32;
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)c0, acc);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const int col = n0 + c0 + g4 * 4;
+                const float4 bb = col < e.N ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pk[g4 * 2] = pack_bf16x2(act_fast<ACT>(__uint_as_float(acc[g4 * 4]) + bb.x), act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 1]) + bb.y));
+                pk[g4 * 2 + 1] = pack_bf16x2(act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 2]) + bb.z), act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 3]) + bb.w));
+            }
+            const uint32_t buf = buf0 + (uint32_t)(it & 1) * kStoreBoxBytes;
+            if (it >= 2) {                                 // the store that last read this buffer must be done with it
+                if (issuer) bulk_wait_group_read<1>();
+                named_bar_sync(bar_id, 128);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                sts128(buf + row_off + ((((uint32_t)ch) ^ sw) << 4), pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+            fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA (async proxy)
+            named_bar_sync(bar_id, 128);
+            if (issuer) {
+                tma_store_2d_a(e.out_map, buf, n0 + c0, out_row0);
+                bulk_commit_group();
+            }
+        }
+        if (issuer) bulk_wait_group_read<0>();             // smem may be reused / released once the TMA has read it
+        return;
+    }
     const RowCtx r = decode_row(e, m_tile, quarter * 32 + lane);
     const bool conv = e.in_mode == IN_CONV;            // conv tiles: output rows come from the decoded pixel, not m0 + r
     const bool shuf = e.out[0].map == MAP_SHUF || e.out[1].map == MAP_SHUF;
@@ -878,6 +930,12 @@ cudaError_t gemm_tc_configure() {
     if ((e = configure_one<ACT_NONE, EPI_BF16_SAME>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_GELU, EPI_BF16_SAME>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_NONE, EPI_F32_SAME_RESID>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_NONE, EPI_BF16_TMA>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_GELU, EPI_BF16_TMA>()) != cudaSuccess) return e;
+    prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>);
+    prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>);
+    if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>);
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>);
     if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
@@ -889,7 +947,7 @@ cudaError_t gemm_tc_configure() {
 // which removes the cross-stream overlap that mode relies on (measured: 26.5k vs 25.9k images/s at 3 streams).
 bool gemm_use_persistent(int groups, int epi, int act, int tiles, bool share_sm) {
     static const bool off = getenv("TMAE_NO_PERSISTENT") != nullptr;
-    return !off && !share_sm && groups == 1 && epi == EPI_BF16_SAME && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
+    return !off && !share_sm && groups == 1 && (epi == EPI_BF16_SAME || epi == EPI_BF16_TMA) && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
 }
 
 cudaError_t gemm_chain_configure() {
@@ -917,7 +975,9 @@ cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, i
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).
 int gemm_epi_kind(const GemmParams& p) {
     const bool one_out = p.out[1].dtype == OUT_NONE && p.out[0].map == MAP_SAME;
-    if (one_out && p.out[0].dtype == OUT_BF16 && p.resid == nullptr && p.act != ACT_HALF_TANH) return EPI_BF16_SAME;
+    static const bool no_tma_store = getenv("TMAE_NO_TMA_STORE") != nullptr;
+    if (one_out && p.out[0].dtype == OUT_BF16 && p.resid == nullptr && p.act != ACT_HALF_TANH)
+        return (p.tma_store_ok && (p.block_n & 31) == 0 && !no_tma_store) ? EPI_BF16_TMA : EPI_BF16_SAME;
     if (one_out && p.in_mode != IN_CONV && p.out[0].dtype == OUT_F32 && p.resid != nullptr && p.resid_map == MAP_SAME && p.act == ACT_NONE)
         return EPI_F32_SAME_RESID;
     return EPI_GENERIC;
@@ -941,13 +1001,17 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         const int psmem = overhead + pst * stage_bytes;
         const int tiles = (int)(grid.x * grid.y);
         const int ctas = tiles < 148 ? tiles : 148;
+        if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
+        if (epi == EPI_BF16_TMA) return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
         if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
         return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
     }
     int kgroup = 1;
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
     // every member of a grouped launch shares the activation and the store-phase specialisation
-    if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    else if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
     else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
     else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
     else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);

@@ -324,6 +324,21 @@ int make_map(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, 
     return TMAE_OK;
 }
 
+// Output of the TMA-store epilogue: [rows, cols] bf16 row-major, box = 32 columns x 128 rows, SWIZZLE_64B (64-byte rows).
+int make_store_map(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {ld_elems * 2};
+    cuuint32_t box[2] = {32, (cuuint32_t)kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(store) failed (%d): cols %llu rows %llu ld %llu", (int)r,
+                    (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld_elems);
+    return TMAE_OK;
+}
+
 // Conv A operand: the compact channels-last tensor [n_img, s, s, C] seen as a 4-D tensor (C, x, y, n); one box is
 // [64 ch, s, box_y, box_n] = rows_used rows of 128 B in smem (row = (nl * box_y + yl) * s + x), SWIZZLE_128B.
 int make_map4d(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, int s, int n_img, uint64_t ld_elems,
@@ -438,6 +453,19 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     int rc = make_map(h, &p->b_map, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)p->block_n);
     if (rc) return rc;
     p->in_mode = d.in_mode;
+    // TMA-store epilogue: one bf16 output at the accumulator's own rows, and those rows are 128 consecutive output rows
+    {
+        const bool one_bf16 = d.out0.dtype == OUT_BF16 && d.out0.map == MAP_SAME && d.out1.dtype == OUT_NONE && d.resid == nullptr;
+        const bool rows_ok = !conv || (cg.rows_used == kBlockM && (cg.box_n == 1 || cg.box_y == d.side));
+        const bool align_ok = (reinterpret_cast<uintptr_t>(d.out0.ptr) & 15) == 0 && ((size_t)d.out0.ld * 2) % 16 == 0;
+        p->tma_store_ok = 0;
+        if (one_bf16 && rows_ok && align_ok && L.Cout >= 32) {
+            const uint64_t out_rows = conv ? (uint64_t)d.a_rows : (uint64_t)d.M;
+            int rc2 = make_store_map(h, &p->out_map, d.out0.ptr, (uint64_t)L.Cout, out_rows, (uint64_t)d.out0.ld);
+            if (rc2) return rc2;
+            p->tma_store_ok = 1;
+        }
+    }
     p->bias = L.bias;
     p->act = d.act;
     p->resid = d.resid; p->resid_ld = d.resid_ld; p->resid_map = d.resid_map;
@@ -560,6 +588,13 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; bn = cand; }
         }
     }
+    {   // layers whose store phase can go through TMA (one bf16 same-row output): 32-column boxes -> block_n % 32 == 0
+        bool all_bf16_same = !getenv("TMAE_NO_TMA_STORE");
+        for (int g = 0; g < groups; ++g)
+            all_bf16_same = all_bf16_same && descs[g].out0.dtype == OUT_BF16 && descs[g].out0.map == MAP_SAME &&
+                            descs[g].out1.dtype == OUT_NONE && descs[g].resid == nullptr && descs[g].act != ACT_HALF_TANH;
+        if (all_bf16_same && bn % 32 != 0 && bn + 16 <= 256) bn += 16;
+    }
     for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
         if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF) bn = (bn + 31) / 32 * 32;
     for (int g = 0; g < groups; ++g) {
@@ -567,7 +602,8 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         int rc = fill_params(h, descs[g], groups, &p, bn);
         if (rc) return rc;
         const int ek = gemm_epi_kind(p);
-        if (g == 0) st.epi = ek; else if (ek != st.epi) st.epi = 0;     // mixed group -> generic store phase
+        if (g == 0) st.epi = ek;
+        else if (ek != st.epi) st.epi = ((ek == 1 || ek == 3) && (st.epi == 1 || st.epi == 3)) ? 1 : 0;   // mixed group -> common denominator
         pl.host_params.push_back(p);
         st.flops += descs[g].flops;
     }
