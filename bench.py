@@ -361,8 +361,12 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step for the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (independent handles/streams)")
+    ap.add_argument("--batch", type=int, default=0, help="experiment only: images per step instead of the workload's batch")
     args = ap.parse_args()
     kwargs, batch, desc = WORKLOADS[args.workload]
+    if args.batch > 0:
+        desc = desc.replace(f"batch {batch}", f"batch {args.batch} (EXPERIMENT, not the named workload)")
+        batch = args.batch
     if args.impl == "reference":
         run_reference(args, kwargs, batch, desc)
     else:

@@ -256,9 +256,55 @@ __global__ void __launch_bounds__(64, 1) ubench(long long* out) {
     if (warp == 1) tmem_dealloc(tmem_slot, 32);
 }
 
+// ---- TMA load cost: one thread issues `batch` loads of a 64 x `rows` bf16 box (SWIZZLE_128B) per mbarrier phase ----
+#include <cuda.h>
+__global__ void __launch_bounds__(32, 1) tma_batch(const __grid_constant__ CUtensorMap map, int batch, int box_bytes, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    __syncwarp();
+    const uint32_t bar_a = smem_u32(&bar), base = smem_u32(sm);
+    long long t0 = clock64();
+    uint32_t ph = 0;
+    for (int i = 0; i < iters; ++i) {
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx_a(bar_a, (uint32_t)(batch * box_bytes));
+            for (int j = 0; j < batch; ++j) tma_load_2d_a(base + (uint32_t)(j * box_bytes), &map, bar_a, 0, ((i * batch + j) * 128) % 4096);
+        }
+        __syncwarp();
+        mbar_wait_a(bar_a, ph);
+        ph ^= 1u;
+    }
+    long long t1 = clock64();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+}
+
+typedef CUresult (*PFN_enc)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                            const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void tma_bench(long long* d) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    void* buf; cudaMalloc(&buf, 8192 * 64 * 2); cudaMemset(buf, 0, 8192 * 64 * 2);
+    cudaFuncSetAttribute(tma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int rows : {128, 64, 32}) {
+        CUtensorMap m; cuuint64_t gd[2] = {64, 8192}; cuuint64_t gs[1] = {128}; cuuint32_t bx[2] = {64, (cuuint32_t)rows}; cuuint32_t es[2] = {1, 1};
+        ((PFN_enc)fn)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        for (int batch : {1, 2, 4, 8}) {
+            long long h = 0;
+            for (int rep = 0; rep < 2; ++rep) tma_batch<<<1, 32, 8 * 16384 + 1024>>>(m, batch, rows * 128, 500, d);
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+            printf("tma box 64x%-3d (%5d B) x batch %d: %8.1f clk per phase, %7.1f clk per load  %s\n", rows, rows * 128, batch, (double)h / 500, (double)h / 500 / batch,
+                   e == cudaSuccess ? "" : cudaGetErrorString(e));
+        }
+    }
+}
+
 int main() {
     long long* d;
     cudaMalloc(&d, 64);
+    tma_bench(d);
     const int modes[] = {0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14, 15, 16, 20, 21, 22, 23, 24, 25, 26, 17, 27, 28, 29, 30, 31, 32};
     const char* names[] = {"try_wait (completed phase)", "elect arrive + wait (self)", "elect + syncwarp", "tcgen05.fence::after",
                            "elect tcgen05.commit + wait (self)", "elect arrive.expect_tx(0) + wait (self)", "lane0 arrive + wait (self)",

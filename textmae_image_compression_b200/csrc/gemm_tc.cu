@@ -453,7 +453,12 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
 // The pipeline position (stage / phase / stage_off) is carried across tiles by the caller.
 __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages, int kgroup,
                                              int stage_bytes, uint32_t pipe_base, uint32_t full_a, uint32_t empty_a,
-                                             int& stage, uint32_t& phase, uint32_t& stage_off, long long* ticks) {
+                                             int& stage, uint32_t& phase, uint32_t& stage_off, long long* ticks,
+                                             int prod_id = 0, int num_prod = 1) {
+    // num_prod producer warps share the stage sequence round-robin (prod_id = which one this is): every producer walks
+    // all stages (same coordinate / parity bookkeeping) but waits, arms and loads only its own.  One warp needs
+    // ~300 cycles of barrier handshake PLUS ~140 cycles per 16 KB load it issues for every stage (the two add up: the
+    // loop was producer bound at ~210 ns per k-block on the narrow conv tiles); two warps overlap each other's handshake.
     const int nseg = p.num_segs;
     const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
     const void* map0 = &p.a_map[0];
@@ -470,14 +475,19 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     int sg = 0, k = 0, skb_cur = skb0;
     int dx = -1, cy = y0 - 1;                              // taps in (kh, kw) row-major order = the weight packing order
     const void* map_cur = map0;
+    int turn = 0;
     for (int kb = 0; kb < total_kb;) {
         const int nk = min(kgroup, total_kb - kb);
-        mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+        const bool mine = turn == prod_id;
+        if (++turn == num_prod) turn = 0;
         const uint32_t fb = full_a + 8u * stage;
-        if (elect_one()) mbar_arrive_expect_tx_a(fb, kb_bytes * (uint32_t)nk);
-        __syncwarp();
+        if (mine) {
+            mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+            if (elect_one()) mbar_arrive_expect_tx_a(fb, kb_bytes * (uint32_t)nk);
+            __syncwarp();
+        }
         for (int j = 0; j < nk; ++j, ++kb) {
-            if (elect_one()) {
+            if (mine && elect_one()) {
                 const uint32_t a_dst = pipe_base + stage_off + (uint32_t)(j * kAStageBytes);
                 if (conv) tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, cy, img0);
                 else tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
@@ -552,7 +562,8 @@ __device__ __forceinline__ void prefetch_next_weights(const GemmParams* __restri
 
 template <int ACT, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, const GemmParams* __restrict__ next, int next_groups) {
+gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, const GemmParams* __restrict__ next, int next_groups,
+               int two_producers) {
     pdl_launch_dependents();
     if (next != nullptr && threadIdx.x == 64)
         prefetch_next_weights(next, next_groups, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z);
@@ -611,11 +622,13 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
     // instead of moving them from a divergent lane for every instruction.
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    const int num_prod = (two_producers && total_kb > kgroup) ? 2 : 1;
     if (warp == 0) {
         // ===== TMA producer =====
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        produce_tile(p, m_tile, n0, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, ticks);
+        produce_tile(p, m_tile, n0, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, ticks,
+                     0, num_prod);
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int stage = 0;
@@ -630,6 +643,12 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
         // idle) pipeline buffers: accum_bar completes only after every MMA has finished reading them.
         // The staging tiles reuse the (now idle) pipeline buffers: accum_bar completes only after every MMA has
         // finished reading them.
+        if (warp == 2 && num_prod == 2) {             // second producer: an epilogue warp, idle until the accumulator is done
+            int stage = 0;
+            uint32_t phase = 0, stage_off = 0;
+            produce_tile(p, m_tile, n0, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off,
+                         nullptr, 1, 2);
+        }
         const EpiCtx e = load_epi(p);
         epilogue_tile<ACT, EPI>(e, m_tile, n0, block_n, tmem_base, smem_base, warp, lane, accum_bar, 0u, ticks);
         if (ticks && warp == 2 && lane == 0) ticks[6] = globaltimer_ns();
@@ -1006,17 +1025,19 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         if (act == ACT_GELU) return launch_k(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
         return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
     }
+    static const int two_prod_env = getenv("TMAE_TWO_PRODUCERS") ? atoi(getenv("TMAE_TWO_PRODUCERS")) : -1;
+    const int two_prod = two_prod_env >= 0 ? two_prod_env : (block_n <= 128 ? 1 : 0);   // wide tiles are MMA bound
     int kgroup = 1;
     const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
     // every member of a grouped launch shares the activation and the store-phase specialisation
-    if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
-    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups);
+    if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (epi == EPI_BF16_SAME && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (epi == EPI_F32_SAME_RESID && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_F32_SAME_RESID>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else if (act == ACT_HALF_TANH) return launch_k(gemm_tc_kernel<ACT_HALF_TANH, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
+    else return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GENERIC>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     return cudaGetLastError();
 }
 
