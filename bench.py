@@ -354,8 +354,8 @@ def run_b200(args, kwargs, batch, desc, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B64", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-sample", type=int, default=8, help="images per step for the CPU reference arm")

@@ -15,7 +15,8 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int KPITCH = HD + 8;        // bf16 elements per K row in smem: 36 words -> conflict-free B-fragment loads
-constexpr int kAttnThreads = 128;
+constexpr int kAttnWarps = 5;          // T = 65 (K = 64 kept patches + cls) is 5 query tiles of 16: one per warp, one round
+constexpr int kAttnThreads = 32 * kAttnWarps;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -35,9 +36,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 
 // qkv: bf16 [N*T, 3C] with columns [3][H][64] (timm reshape (B,T,3,H,hd)); out: bf16 [N*T, C] columns [H][64].
 // K and V of all keys are staged ROW-major (pitch 72 elements: the 8 rows of an ldmatrix tile fall in distinct bank
-// groups); B fragments come from ldmatrix (K: plain, V: .trans), so there is no transposed copy of V and no scalar
-// shared-memory traffic in the loop.
-// 6 CTAs/SM (<= 85 registers): N*H = 768 CTAs at batch 64 fit one wave of 888 slots instead of 1.04 waves of 740
+// groups) together with each warp's 16-row Q tile, all in one round of independent 16-byte global loads; every MMA
+// fragment then comes from ldmatrix (Q, K plain; V .trans): no transposed copy of V, no scalar shared-memory traffic
+// and no Q registers held across the key loop (<= 64 registers -> 6 CTAs / 30 warps per SM, 888 slots >= the 768
+// (image, head) CTAs of batch 64: one wave, one query tile per warp).
 __global__ void __launch_bounds__(kAttnThreads, 6)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
                  float scale_log2e) {
@@ -46,12 +48,26 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     extern __shared__ __align__(16) uint8_t smem_attn[];
     __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_attn);            // [Tp][KPITCH]
     __nv_bfloat16* sV = sK + (size_t)Tp * KPITCH;                                // [Tp][KPITCH]
+    __nv_bfloat16* sQ = sV + (size_t)Tp * KPITCH;                                // [kAttnWarps][16][KPITCH]
     const int n = blockIdx.x / H, h = blockIdx.x - n * H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const size_t ld = (size_t)3 * C;
     const __nv_bfloat16* base = qkv + (size_t)n * T * ld + (size_t)h * HD;
+    __nv_bfloat16* myQ = sQ + (size_t)warp * 16 * KPITCH;
 
+    // this warp's Q tile: 16 rows x 64 dims = 128 16-byte chunks, 4 per lane (rows >= T are zero)
+    auto stage_q = [&](int q0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = i * 32 + lane, r = e >> 3, c8 = (e & 7) * 8;
+            uint4 qv = make_uint4(0, 0, 0, 0);
+            if (q0 + r < T) qv = *reinterpret_cast<const uint4*>(base + (size_t)(q0 + r) * ld + c8);
+            *reinterpret_cast<uint4*>(myQ + r * KPITCH + c8) = qv;
+        }
+    };
+    const int q_tiles = Tp / 16;
+    if (warp < q_tiles) stage_q(warp * 16);
     // ---- stage K and V for all keys (16-byte chunks, coalesced: 8 threads per key row); zero the padding ----
 #pragma unroll 4
     for (int e = tid; e < Tp * (HD / 8); e += kAttnThreads) {
@@ -66,28 +82,20 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
     __syncthreads();
 
-    const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV);
+    const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(myQ);
     // per-lane ldmatrix row addresses (bytes) relative to the first key of a chunk
     //   K (plain):  matrix j = lane >> 3 covers d columns [8j, 8j+8) of keys (lane & 7)           (+32 columns for the 2nd load)
     //   V (.trans): matrices (keys 0-7, d0) (keys 8-15, d0) (keys 0-7, d0+8) (keys 8-15, d0+8)
+    //   Q (plain):  matrices (rows 0-7, k0) (rows 8-15, k0) (rows 0-7, k0+8) (rows 8-15, k0+8) = a0..a3 of one k-step
     const uint32_t k_lane = (uint32_t)(((lane & 7) * KPITCH + (lane >> 3) * 8) * 2);
     const uint32_t v_lane = (uint32_t)((((lane & 7) + ((lane >> 3) & 1) * 8) * KPITCH + (lane >> 4) * 8) * 2);
 
-    const int q_tiles = Tp / 16;
-    for (int qt = warp; qt < q_tiles; qt += kAttnThreads / 32) {
+    for (int qt = warp; qt < q_tiles; qt += kAttnWarps) {
         const int q0 = qt * 16;
-        // Q fragments for the 4 k-steps over head_dim (A operand, row-major 16x16 each)
-        uint32_t qa[4][4];
-        {
-            const int r0 = q0 + g, r1 = q0 + g + 8;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const int c = ks * 16 + 2 * t;
-                qa[ks][0] = r0 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c) : 0u;
-                qa[ks][1] = r1 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c) : 0u;
-                qa[ks][2] = r0 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r0 * ld + c + 8) : 0u;
-                qa[ks][3] = r1 < T ? *reinterpret_cast<const uint32_t*>(base + (size_t)r1 * ld + c + 8) : 0u;
-            }
+        if (qt != warp) {                          // later rounds (T > 80): restage this warp's Q slot
+            __syncwarp();
+            stage_q(q0);
+            __syncwarp();
         }
         float o[8][4];
 #pragma unroll
@@ -97,17 +105,20 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
         for (int k0 = 0; k0 < Tp; k0 += 16) {
             // S chunk = Q (16x64) * K[k0..k0+16)^T : two n-tiles of 8 keys
             float sacc[2][4];
+            sacc[0][0] = sacc[0][1] = sacc[0][2] = sacc[0][3] = 0.f;
+            sacc[1][0] = sacc[1][1] = sacc[1][2] = sacc[1][3] = 0.f;
+            const uint32_t ka = sK_a + (uint32_t)(k0 * KPITCH * 2) + k_lane;
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
-                sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-                const uint32_t ka = sK_a + (uint32_t)((k0 + nt * 8) * KPITCH * 2) + k_lane;
-                uint32_t kb0[4], kb1[4];
-                ldmatrix_x4(kb0, ka);              // d 0..31 : (b0, b1) of k-steps 0 and 1
-                ldmatrix_x4(kb1, ka + 64);         // d 32..63: k-steps 2 and 3
-                mma_bf16_16816(sacc[nt], qa[0], kb0[0], kb0[1]);
-                mma_bf16_16816(sacc[nt], qa[1], kb0[2], kb0[3]);
-                mma_bf16_16816(sacc[nt], qa[2], kb1[0], kb1[1]);
-                mma_bf16_16816(sacc[nt], qa[3], kb1[2], kb1[3]);
+            for (int hk = 0; hk < 2; ++hk) {       // d 0..31 (k-steps 0, 1), then d 32..63 (k-steps 2, 3)
+                uint32_t kb0[4], kb1[4], qa[4];
+                ldmatrix_x4(kb0, ka + (uint32_t)(hk * 64));                               // keys k0 .. k0+7
+                ldmatrix_x4(kb1, ka + (uint32_t)(8 * KPITCH * 2 + hk * 64));              // keys k0+8 .. k0+15
+                ldmatrix_x4(qa, sQ_a + v_lane + (uint32_t)(hk * 64));                     // k-step 2 hk
+                mma_bf16_16816(sacc[0], qa, kb0[0], kb0[1]);
+                mma_bf16_16816(sacc[1], qa, kb1[0], kb1[1]);
+                ldmatrix_x4(qa, sQ_a + v_lane + (uint32_t)(hk * 64 + 32));                // k-step 2 hk + 1
+                mma_bf16_16816(sacc[0], qa, kb0[2], kb0[3]);
+                mma_bf16_16816(sacc[1], qa, kb1[2], kb1[3]);
             }
             // scale (log2 domain), mask padded keys
             float cmax0 = -INFINITY, cmax1 = -INFINITY;
@@ -176,7 +187,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 inline int attn_tp(int T) { return (T + 15) / 16 * 16; }
 inline size_t attn_smem(int T) {
     const int Tp = attn_tp(T);
-    return (size_t)2 * Tp * KPITCH * sizeof(__nv_bfloat16);
+    return ((size_t)2 * Tp + (size_t)kAttnWarps * 16) * KPITCH * sizeof(__nv_bfloat16);
 }
 
 }  // namespace
