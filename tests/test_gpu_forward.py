@@ -99,6 +99,23 @@ def test_small_model_full_path(cuda_dev, simt):
     _compare(f"small_{'simt' if simt else 'tc'}", out, ref, cfg, bpp_tol=0.02)
 
 
+@pytest.mark.parametrize("img,K,N", [(128, 16, 5), (128, 64, 1), (128, 64, 3), (192, 144, 2), (320, 400, 1), (64, 16, 9)])
+def test_small_model_geometry_sweep(cuda_dev, img, K, N):
+    """Every conv tile geometry the path can meet - s = 4, 8, 12, 20 (and s/2, s/4: 1..10), odd batch sizes (ragged image
+    groups in the 4-D TMA boxes), a single image - through the whole path against the fp32 oracle, small encoder."""
+    kw = dict(img_size=img, encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2, num_keep_patches=K)
+    cfg = PathConfig(**kw)
+    sd = make_state_dict(cfg, seed=11)
+    g = torch.Generator().manual_seed(img + K + N)
+    imgs = torch.rand(N, 3, img, img, generator=g)
+    scores = torch.rand(N, cfg.num_patches, generator=g)
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(kw, sd, cuda_dev)
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    _compare(f"sweep_img{img}_K{K}_N{N}", out, ref, cfg, bpp_tol=0.02)
+
+
 @pytest.mark.parametrize("simt", [True, False], ids=["simt_checker", "tcgen05"])
 def test_small_model_teacher_forced_rate_half(cuda_dev, simt):
     """Oracle latent y in -> every conv / entropy kernel of the rate half, no encoder error."""
