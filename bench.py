@@ -217,8 +217,15 @@ def run_b200(args, kwargs, batch, desc, wl):
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
+    t_warm = time.perf_counter()
     for i in range(warm_eff):
         step_dev(i)
+    torch.cuda.synchronize()
+    while time.perf_counter() - t_warm < 1.0:                 # at least ~1 s under load before timing: clocks / power state settle
+        for i in range(S):
+            step_dev(warm_eff + i)
+        torch.cuda.synchronize()
+        warm_eff += S
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -12,7 +12,8 @@ batch_override = int(sys.argv[2]) if len(sys.argv) > 2 else None
 kwargs, batch, desc = WORKLOADS[wl]
 batch = batch_override or batch
 cfg = PathConfig(**kwargs)
-m = MCM(**kwargs); m.load_state_dict(make_state_dict(cfg, 0)); m.cuda().eval()
+share = len(sys.argv) > 3 and sys.argv[3] == "share"      # third argument 'share': the half-smem configs of multi-stream mode
+m = MCM(**kwargs, share_sm=share); m.load_state_dict(make_state_dict(cfg, 0)); m.cuda().eval()
 imgs, scores = make_inputs(kwargs, batch, 0, 2)
 imgs = [t.cuda() for t in imgs]; scores = [t.cuda() for t in scores]
 for i in range(3): m(imgs[i % 2], scores[i % 2])

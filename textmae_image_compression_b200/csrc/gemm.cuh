@@ -16,9 +16,12 @@ constexpr int kMaxTaps = 9;
 // Row spaces.  Every activation matrix is COMPACT channels-last: pixel (n, y, x) of an s x s grid is row n*s*s + y*s + x.
 //   IN_LINEAR  plain GEMM rows (tokens)
 //   IN_COMPACT plain GEMM rows that are pixels of an s x s grid (g_a, patch embed): only the token remap needs (n, j)
-//   IN_CONV    3x3 convolution: the A tile of a CTA is a 4-D TMA box [64 ch, s (x), box_y, box_n images] of the
-//              compact tensor; a tap (dy, dx) shifts the box coordinates and TMA zero-fills what falls outside the
-//              image, so there is no halo / im2col buffer and no wasted rows when s*box_y*box_n == 128.
+//   IN_CONV    3x3 convolution: the A tile of a CTA is a 4-D TMA box [64 ch, s (x), box_n images, box_y rows] of the
+//              compact tensor (accumulator row r = (yl * box_n + nl) * s + x); a tap (dy, dx) shifts the box
+//              coordinates and TMA zero-fills what falls outside the image, so there is no halo / im2col buffer and no
+//              wasted rows when s*box_y*box_n == 128.  conv_reuse: ONE box with a row of halo above and below
+//              ([64, s, box_n, box_y + 2]) is loaded per (channel block, dx) and serves the three dy taps through
+//              shared-memory descriptor offsets of box_n*s rows (a multiple of the 8-row swizzle atom).
 enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_CONV = 2 };
 enum RowMap : int {
     MAP_SAME = 0,        // out row = the pixel's / token's own compact row
@@ -38,9 +41,9 @@ struct OutSpec {
 };
 
 struct alignas(64) GemmParams {
-    CUtensorMap a_map[kMaxSegs];      // linear: [rows, C_seg] box 64 x 128; conv: [C_seg, s, s, n_img] box 64 x s x box_y x box_n
+    CUtensorMap a_map[kMaxSegs];      // linear: [rows, C_seg] box 64 x 128; conv: (C_seg, x, n, y) box 64 x s x box_n x box_y (+2 rows if conv_reuse)
     CUtensorMap b_map;                // [N, Kpacked] bf16, box 64 x block_n, SWIZZLE_128B
-    CUtensorMap out_map;              // TMA-store epilogue only: out[0] as [rows, N] bf16, box 32 x 128, SWIZZLE_64B
+    CUtensorMap out_map;              // TMA-store epilogue only: out[0] as [rows, N] bf16, box 32 x 128 (conv: (N, x, n, y), box 32 x s x box_n x box_y), SWIZZLE_64B
     // raw views of the same operands (CUDA-core checker kernel)
     const __nv_bfloat16* a_ptr[kMaxSegs];
     int a_ld[kMaxSegs];
@@ -65,7 +68,9 @@ struct alignas(64) GemmParams {
     int box_y, box_n;                 // conv: image rows / images per CTA tile
     int rows_used;                    // conv: s * box_y * box_n (<= 128) accumulator rows that hold pixels
     int y_tiles;                      // conv: ceil(s / box_y)
-    int tma_store_ok;                 // out_map is valid and the tile's accumulator rows are 128 consecutive output rows
+    int tma_store_ok;                 // out_map is valid (linear: the tile is 128 consecutive output rows; conv: the 4-D box of the tile)
+    int conv_reuse;                   // conv: one haloed A box per (channel block, dx) serves the three dy taps
+    int a_halo_rows;                  // conv_reuse: (box_y + 2) * box_n * s rows of 128 B per A box
     // epilogue
     const float* bias;                // [N] (already permuted for MAP_SHUF)
     int act;

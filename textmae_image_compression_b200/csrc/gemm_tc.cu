@@ -54,17 +54,17 @@ struct RowCtx {
 };
 
 // r = accumulator row (0..127) of CTA tile `m_tile`.  Linear row spaces: row m_tile*128 + r.  Conv: the A tile is the
-// TMA box [x][yl][nl] flattened, r = (nl * box_y + yl) * s + x, and the row it stands for is pixel (n0+nl, y0+yl, x).
+// TMA box [x][nl][yl] flattened, r = (yl * box_n + nl) * s + x, and the row it stands for is pixel (n0+nl, y0+yl, x).
 __device__ __forceinline__ RowCtx decode_row(const EpiCtx& p, int m_tile, int r) {
     RowCtx c;
     c.n = c.y = c.x = 0;
     if (p.in_mode == IN_CONV) {
         int y0, n0;
         conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, n0);
-        const int per_img = p.s * p.box_y;
-        const int nl = r / per_img, rem = r - nl * per_img;
-        const int yl = rem / p.s;
-        c.x = rem - yl * p.s;
+        const int per_y = p.s * p.box_n;
+        const int yl = r / per_y, rem = r - yl * per_y;
+        const int nl = rem / p.s;
+        c.x = rem - nl * p.s;
         c.y = y0 + yl;
         c.n = n0 + nl;
         c.valid = (r < p.rows_used) && (c.n < p.n_img) && (c.y < p.s);
@@ -243,7 +243,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
         const uint32_t buf0 = stage_base + (uint32_t)half * 2u * kStoreBoxBytes;
         const bool issuer = quarter == 0 && lane == 0;
         const int bar_id = 1 + half;
-        const int out_row0 = decode_row(e, m_tile, 0).lin;           // conv tiles on this path are contiguous pixel rows
+        const bool conv_t = e.in_mode == IN_CONV;                    // conv: the tile is a 4-D box (x, images, rows) of the output
+        int ty0 = 0, tn0 = 0;
+        if (conv_t) conv_tile_origin(m_tile, e.y_tiles, e.box_y, e.box_n, ty0, tn0);
         const int nboxes = block_n >> 5;
         mbar_wait(wait_bar, wait_parity);
         tc_fence_after();
@@ -274,7 +276,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
             fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA (async proxy)
             named_bar_sync(bar_id, 128);
             if (issuer) {
-                tma_store_2d_a(e.out_map, buf, n0 + c0, out_row0);
+                if (conv_t) tma_store_4d_a(e.out_map, buf, n0 + c0, 0, tn0, ty0);
+                else tma_store_2d_a(e.out_map, buf, n0 + c0, m0);
                 bulk_commit_group();
             }
         }
@@ -448,7 +451,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
 
 // TMA producer of one CTA tile (called by a whole warp; WARP-UNIFORM: all 32 lanes run the loop on identical values and
 // only the TMA instructions are elect-predicated, so addresses and descriptors stay in uniform registers).
-// Linear row spaces: A atom = 2-D box [64 ch, 128 rows].  Conv: 4-D box [64 ch, s, box_y, box_n] at pixel offset (dx, dy)
+// Linear row spaces: A atom = 2-D box [64 ch, 128 rows].  Conv: 4-D box [64 ch, s, box_n, box_y] at pixel offset (dx, dy)
 // of the tap; TMA zero-fills whatever falls outside the image (and images >= n_img), which IS the conv's zero padding.
 // The pipeline position (stage / phase / stage_off) is carried across tiles by the caller.
 __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages, int kgroup,
@@ -473,9 +476,49 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     const uint32_t kb_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2) + b_atom;
     const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
     int sg = 0, k = 0, skb_cur = skb0;
-    int dx = -1, cy = y0 - 1;                              // taps in (kh, kw) row-major order = the weight packing order
+    int dx = -1;                                           // x-shift of the current taps (the weights are packed tap-major in (kh, kw) order)
     const void* map_cur = map0;
     int turn = 0;
+    if (conv && p.conv_reuse) {
+        // stage = one haloed A box (channel block k of segment sg at x-shift dx, rows y0-1 .. y0+box_y) + the B atoms of
+        // the three taps (dy = -1, 0, +1) of that dx and channel block
+        const uint32_t a_bytes = (uint32_t)(p.a_halo_rows * kBlockK * 2);
+        const int kb_per_tap = skb0 + skb1 + skb2;
+        const int n_stage = 3 * kb_per_tap;
+        int koff = 0;                                      // k-block offset of (sg, k) inside one tap of the packed weights
+        for (int it = 0; it < n_stage; ++it) {
+            const bool mine = turn == prod_id;
+            if (++turn == num_prod) turn = 0;
+            if (mine) {
+                mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+                if (elect_one()) {
+                    const uint32_t fb = full_a + 8u * stage;
+                    mbar_arrive_expect_tx_a(fb, a_bytes + 3u * b_atom);
+                    tma_load_4d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, dx, img0, y0 - 1);
+#pragma unroll
+                    for (int t3 = 0; t3 < 3; ++t3)         // tap (dy = t3 - 1, dx): index t3 * 3 + (dx + 1) in (kh, kw) order
+                        tma_load_2d_a(pipe_base + stage_off + a_bytes + (uint32_t)t3 * b_atom, mapb, fb,
+                                      ((t3 * 3 + dx + 1) * kb_per_tap + koff) * kBlockK, n0);
+                    if (ticks && it == 0) ticks[2] = globaltimer_ns();
+                }
+                __syncwarp();
+            }
+            ++koff;
+            if (++k == skb_cur) {
+                k = 0;
+                if (++sg == nseg) { sg = 0; koff = 0; ++dx; }
+                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
+                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+            }
+            stage_off += (uint32_t)stage_bytes;
+            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+        }
+        return;
+    }
+    // Per-k-block loads.  Conv k-blocks run in the SAME order as the conv_reuse path - dx, channel segment, channel block,
+    // dy - so that a layer accumulates identically whichever path a launch takes (results do not depend on the batch size).
+    const int kb_per_tap = skb0 + skb1 + skb2;
+    int koff = 0, t3 = 0;
     for (int kb = 0; kb < total_kb;) {
         const int nk = min(kgroup, total_kb - kb);
         const bool mine = turn == prod_id;
@@ -489,15 +532,23 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
         for (int j = 0; j < nk; ++j, ++kb) {
             if (mine && elect_one()) {
                 const uint32_t a_dst = pipe_base + stage_off + (uint32_t)(j * kAStageBytes);
-                if (conv) tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, cy, img0);
-                else tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
-                tma_load_2d_a(pipe_base + stage_off + b_base + (uint32_t)j * b_atom, mapb, fb, kb * kBlockK, n0);
+                const uint32_t b_dst = pipe_base + stage_off + b_base + (uint32_t)j * b_atom;
+                if (conv) {
+                    tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, img0, y0 + t3 - 1);
+                    tma_load_2d_a(b_dst, mapb, fb, ((t3 * 3 + dx + 1) * kb_per_tap + koff) * kBlockK, n0);
+                } else {
+                    tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
+                    tma_load_2d_a(b_dst, mapb, fb, kb * kBlockK, n0);
+                }
                 if (ticks && kb == 0) ticks[2] = globaltimer_ns();
             }
             __syncwarp();
+            if (conv && ++t3 < 3) continue;            // next dy tap of the same (dx, channel block)
+            t3 = 0;
+            ++koff;
             if (++k == skb_cur) {
                 k = 0;
-                if (++sg == nseg) { sg = 0; if (++dx > 1) { dx = -1; ++cy; } }
+                if (++sg == nseg) { sg = 0; koff = 0; ++dx; }
                 skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
                 map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
             }
@@ -512,10 +563,40 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
 __device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, int kgroup, int stage_bytes,
                                          uint32_t pipe_base, uint32_t full_a, uint32_t empty_a, uint32_t tmem_acc,
                                          uint32_t done_bar, int& stage, uint32_t& phase, uint32_t& stage_off,
-                                         long long* ticks, int tick_issue, int tick_done) {
+                                         long long* ticks, int tick_issue, int tick_done,
+                                         uint32_t reuse_a_bytes = 0, uint32_t reuse_dy_bytes = 0) {
     const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
     const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);       // + (byte offset >> 4) selects stage / atom / k-slice
     const uint32_t b_atom = (uint32_t)(block_n * kBlockK * 2);
+    if (reuse_a_bytes != 0) {
+        // conv_reuse: total_kb counts k-blocks (9 taps); a stage holds the three dy taps of one (channel block, dx):
+        // tap dy reads the haloed A box from row offset (dy + 1) * box_n * s (a whole number of 8-row swizzle atoms)
+        const int n_stage = total_kb / 3;
+        for (int it = 0; it < n_stage; ++it) {
+            mbar_wait_a(full_a + 8u * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+                if (ticks && it == 0 && tick_issue >= 0) ticks[tick_issue] = globaltimer_ns();
+#pragma unroll
+                for (int t3 = 0; t3 < 3; ++t3) {
+                    const uint64_t a_desc = desc0 + (uint64_t)((stage_off + (uint32_t)t3 * reuse_dy_bytes) >> 4);
+                    const uint64_t b_desc = desc0 + (uint64_t)((stage_off + reuse_a_bytes + (uint32_t)t3 * b_atom) >> 4);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | t3 | k) != 0 ? 1u : 0u);
+                }
+                umma_commit_a(empty_a + 8u * stage);
+                if (it == n_stage - 1) {
+                    umma_commit_a(done_bar);
+                    if (ticks && tick_done >= 0) ticks[tick_done] = globaltimer_ns();
+                }
+            }
+            __syncwarp();
+            stage_off += (uint32_t)stage_bytes;
+            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+        }
+        return;
+    }
     const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
     for (int kb = 0; kb < total_kb;) {
         const int nk = min(kgroup, total_kb - kb);
@@ -578,7 +659,9 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("tmae: dynamic shared memory not 1024-byte aligned\n"); __trap(); }
     const int block_n = p.block_n;
-    const int stage_bytes = kgroup * (kAStageBytes + block_n * kBlockK * 2);
+    const bool reuse = p.in_mode == IN_CONV && p.conv_reuse != 0;
+    const uint32_t reuse_a_bytes = reuse ? (uint32_t)(p.a_halo_rows * kBlockK * 2) : 0u;
+    const int stage_bytes = reuse ? (int)reuse_a_bytes + 3 * block_n * kBlockK * 2 : kgroup * (kAStageBytes + block_n * kBlockK * 2);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* accum_bar = empty_bar + stages;
@@ -622,7 +705,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
     // instead of moving them from a divergent lane for every instruction.
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
-    const int num_prod = (two_producers && total_kb > kgroup) ? 2 : 1;
+    const int num_prod = (two_producers && total_kb > (reuse ? 3 : kgroup)) ? 2 : 1;
     if (warp == 0) {
         // ===== TMA producer =====
         int stage = 0;
@@ -634,7 +717,7 @@ gemm_tc_kernel(const GemmParams* __restrict__ params, int stages, int kgroup, co
         int stage = 0;
         uint32_t phase = 0, stage_off = 0;
         mma_tile(block_n, total_kb, stages, kgroup, stage_bytes, smem_base, full_a, empty_a, tmem_base, smem_u32(accum_bar),
-                 stage, phase, stage_off, ticks, 3, 4);
+                 stage, phase, stage_off, ticks, 3, 4, reuse_a_bytes, (uint32_t)(p.box_n * p.s * kBlockK * 2));
     } else {
         // ===== epilogue (warps 2..9; TMEM lane quarter = warp % 4, two warps per quarter alternate 32-column chunks) =====
         // Phase 1 (thread = accumulator row): TMEM -> registers -> smem staging tile (raw fp32 accumulators).
@@ -910,6 +993,18 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
 // ---------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------
+// conv_reuse launches: a stage is one haloed A box + three B atoms (`stage_bytes`); returns 0 if fewer than 2 fit
+int gemm_reuse_stages(int stage_bytes, int total_ctas, bool share_sm, int* smem_bytes) {
+    const int overhead = 256;
+    const bool whole_sm = total_ctas <= 148 && !share_sm;
+    const int budget = (whole_sm ? 226 : 113) * 1024 - overhead;
+    int stages = budget / stage_bytes;
+    if (stages > 4) stages = 4;                    // 12 k-blocks in flight
+    if (stages < 2) return 0;
+    *smem_bytes = overhead + stages * stage_bytes;
+    return stages;
+}
+
 int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes, int* kgroup) {
     // Small tiles are bound by (a) the TMA round trip: bytes in flight per SM is what matters, and (b) the ~300-cycle
     // producer <-> MMA handshake per pipeline stage: see produce_tile.  A single wave (<= 148 CTAs) gets the whole
@@ -1004,7 +1099,8 @@ int gemm_epi_kind(const GemmParams& p) {
 
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
-                        bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups) {
+                        bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups,
+                        int conv_reuse_stage_bytes) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
         gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
@@ -1012,7 +1108,7 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     }
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
-    if (gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y), share_sm)) {
+    if (conv_reuse_stage_bytes == 0 && gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y), share_sm)) {
         const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
         const int overhead = 1024 + 256 + kEpiStageBytes;
         int pst = (226 * 1024 - overhead) / stage_bytes;
@@ -1028,7 +1124,13 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     static const int two_prod_env = getenv("TMAE_TWO_PRODUCERS") ? atoi(getenv("TMAE_TWO_PRODUCERS")) : -1;
     const int two_prod = two_prod_env >= 0 ? two_prod_env : (block_n <= 128 ? 1 : 0);   // wide tiles are MMA bound
     int kgroup = 1;
-    const int stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
+    int stages;
+    if (conv_reuse_stage_bytes > 0) {
+        stages = gemm_reuse_stages(conv_reuse_stage_bytes, (int)(grid.x * grid.y * grid.z), share_sm, &smem);
+        if (stages == 0) return cudaErrorInvalidConfiguration;      // the plan only marks launches whose stages fit
+    } else {
+        stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
+    }
     // every member of a grouped launch shares the activation and the store-phase specialisation
     if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);

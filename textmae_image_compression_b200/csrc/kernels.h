@@ -25,7 +25,8 @@ cudaError_t gemm_chain_configure();
 cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream,
-                        const GemmParams* d_next = nullptr, int next_groups = 0);
+                        const GemmParams* d_next = nullptr, int next_groups = 0, int conv_reuse_stage_bytes = 0);
+int gemm_reuse_stages(int stage_bytes, int total_ctas, bool share_sm, int* smem_bytes);
 
 // mask.cu
 cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int softmax_isa, int64_t* ids_shuffle,

@@ -52,6 +52,7 @@ struct Step {
     // GEMM
     int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0, epi = 0;
     int next_index = -1, next_groups = 0;      // parameter blocks of the next GEMM step (weight prefetch target)
+    int conv_reuse_stage_bytes = 0;            // > 0: 3x3 conv launch with haloed-box A reuse, stage size in bytes
     double flops = 0, bytes = 0;
     // fused chain of layers (ST_CHAIN)
     ChainDesc chain;
@@ -339,43 +340,60 @@ int make_store_map(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t 
     return TMAE_OK;
 }
 
-// Conv A operand: the compact channels-last tensor [n_img, s, s, C] seen as a 4-D tensor (C, x, y, n); one box is
-// [64 ch, s, box_y, box_n] = rows_used rows of 128 B in smem (row = (nl * box_y + yl) * s + x), SWIZZLE_128B.
+// Conv A operand: the compact channels-last tensor [n_img, s, s, C] seen as a 4-D tensor (C, x, n, y); one box is
+// [64 ch, s, box_n, rows_y] = s * box_n * rows_y rows of 128 B in smem (row = (yl * box_n + nl) * s + x), SWIZZLE_128B.
+// rows_y = box_y, or box_y + 2 for the haloed box of conv_reuse.
 int make_map4d(tmae_handle* h, CUtensorMap* map, const void* base, uint64_t cols, int s, int n_img, uint64_t ld_elems,
-               int box_y, int box_n) {
-    cuuint64_t gdim[4] = {cols, (cuuint64_t)s, (cuuint64_t)s, (cuuint64_t)n_img};
-    cuuint64_t gstr[3] = {ld_elems * 2, (cuuint64_t)s * ld_elems * 2, (cuuint64_t)s * s * ld_elems * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)s, (cuuint32_t)box_y, (cuuint32_t)box_n};
+               int box_n, int rows_y, uint32_t box_cols = kBlockK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    cuuint64_t gdim[4] = {cols, (cuuint64_t)s, (cuuint64_t)n_img, (cuuint64_t)s};
+    cuuint64_t gstr[3] = {ld_elems * 2, (cuuint64_t)s * s * ld_elems * 2, (cuuint64_t)s * ld_elems * 2};
+    cuuint32_t box[4] = {box_cols, (cuuint32_t)s, (cuuint32_t)box_n, (cuuint32_t)rows_y};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (cols == 0 || s <= 0 || n_img <= 0) return fail(h, TMAE_EINVAL, "empty tensor map");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (gstr[0] & 15) != 0)
         return fail(h, TMAE_EINVAL, "tensor map base/stride not 16-byte aligned");
     CUresult r = h->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(4d) failed (%d): cols %llu s %d n %d ld %llu box %d x %d", (int)r,
-                    (unsigned long long)cols, s, n_img, (unsigned long long)ld_elems, box_y, box_n);
+                    (unsigned long long)cols, s, n_img, (unsigned long long)ld_elems, box_n, rows_y);
     return TMAE_OK;
 }
 
 // Tiling of a conv layer over an s x s grid: a CTA tile is box_y image rows of box_n images (s * box_y * box_n <= 128
-// accumulator rows).  Pick the pair with the fewest tiles; ties go to whole images (contiguous output rows).
-struct ConvGeom { int box_y = 0, box_n = 0, y_tiles = 0, m_tiles = 0, rows_used = 0; };
+// accumulator rows).  Pick the pair with the fewest tiles.  A pair whose dy shift (box_n * s rows) is a whole number of
+// 8-row swizzle atoms can use the haloed-box A reuse (GemmParams::conv_reuse); such a pair wins unless it costs more
+// than 15 % extra tiles.
+struct ConvGeom { int box_y = 0, box_n = 0, y_tiles = 0, m_tiles = 0, rows_used = 0; bool reuse_ok = false; };
 bool conv_geom(int s, int n_img, ConvGeom* g) {
     if (s <= 0 || s > kBlockM || n_img <= 0) return false;
-    long long best = -1;
+    long long best[2] = {-1, -1};          // [0] any pair, [1] reuse-compatible pair
+    ConvGeom cand[2];
     for (int by = (s < kBlockM / s ? s : kBlockM / s); by >= 1; --by) {
-        int bn = kBlockM / (s * by);
-        if (bn > n_img) bn = n_img;
-        if (bn > 256) bn = 256;
-        const int yt = (s + by - 1) / by;
-        const long long tiles = (long long)((n_img + bn - 1) / bn) * yt;
-        if (best < 0 || tiles < best) {
-            best = tiles;
-            g->box_y = by; g->box_n = bn; g->y_tiles = yt; g->m_tiles = (int)tiles; g->rows_used = s * by * bn;
+        for (int pass = 0; pass < 2; ++pass) {
+            int bn = kBlockM / (s * by);
+            if (bn > 256) bn = 256;
+            if (pass == 0) { if (bn > n_img) bn = n_img; }
+            else {
+                int q = 8; for (int d = 8; d >= 1; d >>= 1) if (s % d == 0) { q = 8 / d; break; }   // q = 8 / gcd(s, 8)
+                bn = bn / q * q;                                   // box_n * s must be a multiple of 8 rows
+                while (bn - q >= n_img && bn - q > 0) bn -= q;     // no more images per tile than needed
+                if (by < 2) bn = 0;                                // one row + two halo rows: nothing to reuse
+            }
+            if (bn <= 0) continue;
+            const int yt = (s + by - 1) / by;
+            const long long tiles = (long long)((n_img + bn - 1) / bn) * yt;
+            if (best[pass] < 0 || tiles < best[pass]) {
+                best[pass] = tiles;
+                cand[pass].box_y = by; cand[pass].box_n = bn; cand[pass].y_tiles = yt; cand[pass].m_tiles = (int)tiles;
+                cand[pass].rows_used = s * by * bn; cand[pass].reuse_ok = pass == 1;
+            }
         }
     }
+    if (best[0] < 0) return false;
+    static const bool no_reuse = getenv("TMAE_NO_CONV_REUSE") != nullptr;
+    *g = (!no_reuse && best[1] > 0 && best[1] * 100 <= best[0] * 115) ? cand[1] : cand[0];
     return true;
 }
 
@@ -406,6 +424,7 @@ struct GemmDesc {
     int in_mode = IN_LINEAR;
     int side = 0;               // grid side for IN_COMPACT / IN_CONV
     int n_img = 0;              // IN_CONV: images
+    bool conv_reuse = false;    // IN_CONV: haloed-box A reuse (decided per launch in add_gemm_group)
     bool conv3 = false;
     int act = ACT_NONE;
     const float* resid = nullptr; int resid_ld = 0; int resid_map = MAP_SAME;
@@ -435,7 +454,8 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
         p->a_cols[i] = d.seg[i].cols;
         p->a_rows[i] = d.a_rows;
         p->seg_kblocks[i] = pad64(d.seg[i].cols) / 64;
-        int rc = conv ? make_map4d(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_y, cg.box_n)
+        int rc = conv ? make_map4d(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_n,
+                                   cg.box_y + (d.conv_reuse ? 2 : 0))
                       : make_map(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
         if (rc) return rc;
     }
@@ -446,6 +466,9 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->K = d.side * d.side;
     p->T = p->K + 1;
     p->n_img = d.n_img; p->box_y = cg.box_y; p->box_n = cg.box_n; p->y_tiles = cg.y_tiles; p->rows_used = cg.rows_used;
+    if (d.conv_reuse && !(conv && cg.reuse_ok)) return fail(h, TMAE_EINVAL, "conv_reuse requested for an incompatible tile geometry");
+    p->conv_reuse = d.conv_reuse ? 1 : 0;
+    p->a_halo_rows = conv ? (cg.box_y + 2) * cg.box_n * d.side : 0;
     p->M = d.M;
     p->N = L.Cout;
     const int m_tiles = (d.M + kBlockM - 1) / kBlockM;
@@ -456,12 +479,14 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     // TMA-store epilogue: one bf16 output at the accumulator's own rows, and those rows are 128 consecutive output rows
     {
         const bool one_bf16 = d.out0.dtype == OUT_BF16 && d.out0.map == MAP_SAME && d.out1.dtype == OUT_NONE && d.resid == nullptr;
-        const bool rows_ok = !conv || (cg.rows_used == kBlockM && (cg.box_n == 1 || cg.box_y == d.side));
+        const bool rows_ok = true;        // conv tiles are stored as the 4-D box they are (any geometry)
         const bool align_ok = (reinterpret_cast<uintptr_t>(d.out0.ptr) & 15) == 0 && ((size_t)d.out0.ld * 2) % 16 == 0;
         p->tma_store_ok = 0;
         if (one_bf16 && rows_ok && align_ok && L.Cout >= 32) {
             const uint64_t out_rows = conv ? (uint64_t)d.a_rows : (uint64_t)d.M;
-            int rc2 = make_store_map(h, &p->out_map, d.out0.ptr, (uint64_t)L.Cout, out_rows, (uint64_t)d.out0.ld);
+            int rc2 = conv ? make_map4d(h, &p->out_map, d.out0.ptr, (uint64_t)L.Cout, d.side, d.n_img, (uint64_t)d.out0.ld, cg.box_n, cg.box_y,
+                                        32, CU_TENSOR_MAP_SWIZZLE_64B)
+                           : make_store_map(h, &p->out_map, d.out0.ptr, (uint64_t)L.Cout, out_rows, (uint64_t)d.out0.ld);
             if (rc2) return rc2;
             p->tma_store_ok = 1;
         }
@@ -564,6 +589,18 @@ double conv_flops(long long out_positions, int cin, int cout, int taps) {
     return 2.0 * (double)out_positions * cin * cout * taps;
 }
 
+// conv_reuse decision for one launch: the geometry must allow it and at least two stages (one haloed A box + three B
+// atoms each) must fit the launch's shared-memory budget.  Returns the stage size in bytes, 0 = per-tap loads.
+int conv_reuse_stage_bytes(const tmae_handle* h, const GemmDesc& d, int bn, int n_tiles, int groups) {
+    if (d.in_mode != IN_CONV || h->use_chain) return 0;
+    ConvGeom cg;
+    if (!conv_geom(d.side, d.n_img, &cg) || !cg.reuse_ok) return 0;
+    const int stage = ((cg.box_y + 2) * cg.box_n * d.side + 3 * bn) * kBlockK * 2;
+    int smem = 0;
+    const bool share = (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0;
+    return gemm_reuse_stages(stage, cg.m_tiles * n_tiles * groups, share, &smem) >= 2 ? stage : 0;
+}
+
 int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, const char* tag) {
     Step st;
     st.kind = ST_GEMM;
@@ -597,9 +634,15 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     }
     for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
         if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF) bn = (bn + 31) / 32 * 32;
+    // 3x3 conv launches: haloed-box A reuse when every member agrees on the geometry and the stages fit
+    st.conv_reuse_stage_bytes = conv_reuse_stage_bytes(h, descs[0], bn, (max_N + bn - 1) / bn, groups);
+    for (int g = 1; g < groups; ++g)
+        if (descs[g].in_mode != descs[0].in_mode || descs[g].side != descs[0].side || descs[g].n_img != descs[0].n_img) st.conv_reuse_stage_bytes = 0;
     for (int g = 0; g < groups; ++g) {
         GemmParams p;
-        int rc = fill_params(h, descs[g], groups, &p, bn);
+        GemmDesc dg = descs[g];
+        dg.conv_reuse = st.conv_reuse_stage_bytes > 0;
+        int rc = fill_params(h, dg, groups, &p, bn);
         if (rc) return rc;
         const int ek = gemm_epi_kind(p);
         if (g == 0) st.epi = ek;
@@ -647,7 +690,7 @@ int add_chain(tmae_handle* h, Plan& pl, const std::vector<std::vector<GemmDesc>>
             if (rc) return rc;
             const int ek = gemm_epi_kind(p);
             int k = -1;
-            if (p.act == ACT_GELU && ek == 1 /*EPI_BF16_SAME*/) k = CHAIN_GELU_BF16_SAME;
+            if (p.act == ACT_GELU && (ek == 1 || ek == 3) /*EPI_BF16_SAME / EPI_BF16_TMA*/) k = CHAIN_GELU_BF16_SAME;
             else if (p.act == ACT_NONE) k = CHAIN_NONE_GENERIC;
             else if (p.act == ACT_HALF_TANH) k = CHAIN_HALF_TANH_GENERIC;
             if (k < 0 || (kind >= 0 && k != kind)) return fail(h, TMAE_EINVAL, "chain layer %zu: unsupported epilogue mix", l);
@@ -994,7 +1037,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
-                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups));
+                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes));
                 break;
             case ST_CHAIN:
                 CUDA_TRY(h, gemm_chain_launch(pl.d_params, sp.chain, sp.chain_grid, sp.chain_max_bn, st));
@@ -1393,8 +1436,17 @@ int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* li
 }
 
 // ---- engine self-tests ---------------------------------------------------------------------------------
-static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int impl, cudaStream_t st) {
+static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st) {
     GemmParams p;
+    GemmDesc d = d_in;
+    int reuse_bytes = 0;
+    if (d.in_mode == IN_CONV) {          // same decision as add_gemm_group (block_n first, then whether the reuse stages fit)
+        const int mt = (d.M + kBlockM - 1) / kBlockM;
+        const int bn = block_n > 0 ? block_n : pick_block_n(mt, d.layer->Cout, 1);
+        block_n = bn;
+        reuse_bytes = conv_reuse_stage_bytes(tmp, d, bn, (d.layer->Cout + bn - 1) / bn, 1);
+        d.conv_reuse = reuse_bytes > 0;
+    }
     int rc = fill_params(tmp, d, 1, &p, block_n);
     if (rc) return rc;
     GemmParams* dp = nullptr;
@@ -1415,12 +1467,12 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
         p.dbg_ticks = dticks;
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
-    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st);
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
         cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
         cudaEventRecord(ev0, st);
-        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st);
+        e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, reuse_bytes);
         cudaEventRecord(ev1, st);
         cudaStreamSynchronize(st);
         float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
@@ -1442,14 +1494,14 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d, int block_n, int i
             const int reps = 50;
             cudaStreamSynchronize(st);
             cudaEventRecord(ev0, st);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, reuse_bytes);
             cudaEventRecord(ev1, st);
             cudaStreamSynchronize(st);
             float ms_plain = 0; cudaEventElapsedTime(&ms_plain, ev0, ev1);
             cudaStream_t cs; cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
             cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
             cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
-            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, cs);
+            for (int i = 0; i < reps; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, cs, nullptr, 0, reuse_bytes);
             cudaStreamEndCapture(cs, &graph);
             float ms_graph = -1;
             if (graph && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
