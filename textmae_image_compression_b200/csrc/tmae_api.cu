@@ -651,6 +651,10 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         st.flops += descs[g].flops;
     }
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
+    static const bool plan_debug = getenv("TMAE_PLAN_DEBUG") != nullptr;
+    if (plan_debug)
+        fprintf(stderr, "[plan] %-14s groups %2d M %6d N %4d bn %3d ctas %4d epi %d conv_reuse_stage %6d B\n", tag, groups, max_M, max_N, bn,
+                m_tiles * ((max_N + bn - 1) / bn) * groups, st.epi, st.conv_reuse_stage_bytes);
     for (int g = 1; g < groups; ++g) if (descs[g].act != descs[0].act) return fail(h, TMAE_EINVAL, "grouped GEMM members must share the activation");
     pl.steps.push_back(st);
     return TMAE_OK;
