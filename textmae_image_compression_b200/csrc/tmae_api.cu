@@ -630,7 +630,11 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         for (int g = 0; g < groups; ++g)
             all_bf16_same = all_bf16_same && descs[g].out0.dtype == OUT_BF16 && descs[g].out0.map == MAP_SAME &&
                             descs[g].out1.dtype == OUT_NONE && descs[g].resid == nullptr && descs[g].act != ACT_HALF_TANH;
-        if (all_bf16_same && bn % 32 != 0 && bn + 16 <= 256) bn += 16;
+        // conv layers keep their exact tile width (rounding 112 -> 128 or 80 -> 96 computes 14-20 % dead columns; such layers
+        // use the register/smem store phase instead): measured equal or slightly better at the power cap
+        static const int round_mode = getenv("TMAE_BN_ROUND") ? atoi(getenv("TMAE_BN_ROUND")) : 2;   // 0 never, 1 always, 2 only linear layers
+        const bool conv_layer = descs[0].in_mode == IN_CONV;
+        if (all_bf16_same && bn % 32 != 0 && bn + 16 <= 256 && (round_mode == 1 || (round_mode == 2 && !conv_layer))) bn += 16;
     }
     for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
         if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF) bn = (bn + 31) / 32 * 32;
