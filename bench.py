@@ -217,15 +217,24 @@ def run_b200(args, kwargs, batch, desc, wl):
     if rank == 0:
         sampler.start()
         time.sleep(0.5)
-    t_warm = time.perf_counter()
-    for i in range(warm_eff):
+    for i in range(S):                                        # first call per handle: lazy initialisation (plans, NCCL)
         step_dev(i)
     torch.cuda.synchronize()
-    while time.perf_counter() - t_warm < 1.0:                 # at least ~1 s under load before timing: clocks / power state settle
-        for i in range(S):
-            step_dev(warm_eff + i)
-        torch.cuda.synchronize()
-        warm_eff += S
+    t_warm = time.perf_counter()
+    for i in range(S, warm_eff):
+        step_dev(i)
+    torch.cuda.synchronize()
+    # at least ~1 s under load before timing (clocks / power state settle).  The number of extra steps is agreed across
+    # ranks (every step carries the 16-byte rate all-reduce when world > 1, so all ranks must run the same count).
+    el = time.perf_counter() - t_warm
+    extra = 0 if el >= 1.0 else int((1.0 - el) / max(el / max(warm_eff - S, 1), 1e-5) / S + 1) * S
+    if world > 1:
+        t_extra = torch.tensor([extra], dtype=torch.int64, device=dev)
+        dist.all_reduce(t_extra, op=dist.ReduceOp.MAX)
+        extra = int(t_extra.item())
+    for i in range(extra):
+        step_dev(warm_eff + i)
+    warm_eff += extra
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
