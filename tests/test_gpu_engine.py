@@ -29,7 +29,10 @@ def test_gemm_matches_torch(cuda_dev, M, N, K, bn, impl):
                                                   # tails), row tiles of one image, tiny and odd grids, the B64 slice shape
                                                   (7, 12, 64, 48, False), (9, 6, 128, 64, True), (20, 3, 64, 32, False),
                                                   (40, 2, 192, 96, False), (1, 8, 64, 32, False), (2, 32, 64, 32, False),
-                                                  (64, 8, 352, 224, True)])
+                                                  (64, 8, 352, 224, True),
+                                                  # haloed-box A reuse with partial tiles: 96 of 128 accumulator rows (s = 6, 2 rows
+                                                  # x 8 images), ragged image groups at s = 4 / 2, one image of 16 x 16
+                                                  (40, 6, 128, 64, True), (21, 4, 64, 48, False), (70, 2, 64, 32, False), (3, 16, 64, 96, True)])
 @pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
 def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin)
