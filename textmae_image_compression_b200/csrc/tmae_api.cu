@@ -595,6 +595,9 @@ int conv_reuse_stage_bytes(const tmae_handle* h, const GemmDesc& d, int bn, int 
     if (d.in_mode != IN_CONV || h->use_chain) return 0;
     ConvGeom cg;
     if (!conv_geom(d.side, d.n_img, &cg) || !cg.reuse_ok) return 0;
+    // a tap's MMA always reads 128 rows from its dy offset: with a partial tile the rows past the A box must still lie
+    // inside the stage (they land in the B atoms; the accumulator rows they feed are never stored)
+    if (cg.rows_used + 3 * bn < kBlockM) return 0;
     const int stage = ((cg.box_y + 2) * cg.box_n * d.side + 3 * bn) * kBlockK * 2;
     int smem = 0;
     const bool share = (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0;
