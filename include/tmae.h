@@ -171,6 +171,12 @@ TMAE_API int  tmae_profile_read_steps(tmae_handle* h, tmae_profile_step* steps, 
 /* Number of kernels tmae_forward launches for batch N (after planning). */
 TMAE_API int  tmae_launch_count(tmae_handle* h, int N);
 
+/* Host-only (no device needed): the CTA tiling the conv engine uses for an s x s grid of n_img images.
+ * out[6] = {box_y, box_n, y_tiles, m_tiles, rows_used, reuse_ok}.  A tile covers image rows [y0, y0 + box_y) of images
+ * [n0, n0 + box_n); rows_used = s * box_y * box_n <= 128 accumulator rows; reuse_ok = the haloed-box A reuse applies
+ * (box_n * s is a multiple of the 8-row swizzle atom).  Returns TMAE_EINVAL for s outside 1..128. */
+TMAE_API int  tmae_conv_geometry(int s, int n_img, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,3 +83,33 @@ def test_product_path_never_imports_oracle():
     for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.h")):
         txt = f.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt.replace("oracle/mask_oracle.c for the pinned", ""), f
+
+
+def test_conv_tiling_geometry_invariants():
+    """Host logic of the conv engine (no GPU): for every grid side and batch size the tiles cover every pixel exactly once,
+    fit 128 accumulator rows, and the haloed-box reuse is only claimed when a dy shift is a whole number of swizzle atoms."""
+    import ctypes as C
+    from textmae_image_compression_b200 import _native
+    lib = _native.load()
+    out = (C.c_int * 6)()
+    assert lib.tmae_conv_geometry(0, 4, out) != 0 and lib.tmae_conv_geometry(129, 1, out) != 0
+    for s in list(range(1, 41)) + [48, 64, 96, 128]:
+        for n in (1, 2, 3, 5, 7, 16, 64, 257):
+            assert lib.tmae_conv_geometry(s, n, out) == 0, (s, n)
+            box_y, box_n, y_tiles, m_tiles, rows_used, reuse = list(out)
+            assert 1 <= box_y <= s and box_n >= 1 and rows_used == s * box_y * box_n <= 128, (s, n, list(out))
+            assert y_tiles == -(-s // box_y) and m_tiles == y_tiles * -(-n // box_n), (s, n, list(out))
+            covered = set()
+            for t in range(m_tiles):
+                n0, y0 = (t // y_tiles) * box_n, (t % y_tiles) * box_y
+                for nl in range(box_n):
+                    for yl in range(box_y):
+                        if n0 + nl < n and y0 + yl < s:
+                            assert (n0 + nl, y0 + yl) not in covered
+                            covered.add((n0 + nl, y0 + yl))
+            assert len(covered) == n * s, (s, n, list(out))
+            if reuse:
+                assert (box_n * s) % 8 == 0 and box_y >= 2, (s, n, list(out))
+    # the shapes of the shipped configurations keep all 128 accumulator rows busy
+    for s in (2, 4, 8, 16):
+        assert lib.tmae_conv_geometry(s, 64, out) == 0 and out[4] == 128 and out[5] == 1, (s, list(out))

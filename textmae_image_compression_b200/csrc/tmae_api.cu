@@ -1332,6 +1332,13 @@ int tmae_reserve(tmae_handle* h, int N) {
     return build_plan(h, N, &pl);
 }
 
+int tmae_conv_geometry(int s, int n_img, int* out) {
+    ConvGeom cg;
+    if (!out || !conv_geom(s, n_img, &cg)) return TMAE_EINVAL;
+    out[0] = cg.box_y; out[1] = cg.box_n; out[2] = cg.y_tiles; out[3] = cg.m_tiles; out[4] = cg.rows_used; out[5] = cg.reuse_ok ? 1 : 0;
+    return TMAE_OK;
+}
+
 int tmae_launch_count(tmae_handle* h, int N) {
     Plan* pl = nullptr;
     if (check_ready(h, N) || build_plan(h, N, &pl)) return -1;
