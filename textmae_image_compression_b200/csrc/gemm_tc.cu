@@ -1,12 +1,16 @@
 // tcgen05 / TMEM / TMA GEMM engine for sm_100a.
 //
 // One CTA computes a 128 x block_n fp32 accumulator tile in tensor memory:
-//   warp 0    : TMA producer  - per k-block one 128x64 bf16 A tile (row-shifted per conv tap, channel segment
-//                               per concatenated source) and one block_n x 64 bf16 weight tile, 128B-swizzled
-//   warp 1    : allocates TMEM, single elected thread issues tcgen05.mma (M=128, N=block_n, K=16) x 4 per k-block,
-//               tcgen05.commit releases the smem stage / publishes the accumulator
-//   warps 2-5 : epilogue - tcgen05.ld 32 lanes x 32 columns, + bias, GELU / 0.5*tanh, residual / pos-embed add,
-//               row remap (halo layout, stride-2 subsample, PixelShuffle, token rows), bf16 / fp32 stores
+//   warp 0     : TMA producer - per pipeline stage one or two k-blocks (128x64 bf16 A tile + block_n x 64 bf16 weight
+//                tile, 128B-swizzled); A = 2-D box of a token matrix (one map per concatenated channel segment), or a
+//                4-D box of a compact image tensor for 3x3 convs, optionally one haloed box shared by three dy taps
+//   warp 1     : allocates TMEM, issues tcgen05.mma (M=128, N=block_n, K=16) x 4 per k-block from one elected lane,
+//                tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-9  : epilogue - tcgen05.ld 32 lanes x 32 columns, + bias, GELU / 0.5*tanh, residual / pos-embed add,
+//                row remap (stride-2 subsample, PixelShuffle, token rows), bf16 / fp32 stores or TMA stores;
+//                warp 2 doubles as second TMA producer on narrow tiles
+// Variants: persistent tile loop with double-buffered TMEM (gemm_tc_persistent_kernel), cooperative multi-layer chain
+// (gemm_tc_chain_kernel, opt-in), CUDA-core checker (gemm_simt_kernel).
 // Serves reference layers: PatchEmbed conv (MCM.py:300-302), Block linears (MCM.py:313-322), g_a 1x1 convs
 // (MCM.py:77-93), h_a / h_s / cc_transform / lrp_transform 3x3 convs (MCM.py:115-293).
 #include <stdio.h>

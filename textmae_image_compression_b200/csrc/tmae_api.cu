@@ -41,7 +41,7 @@ struct Layer {                      // one prepacked linear / conv
     int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
 };
 
-enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_CHAIN, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE, ST_Y_TO_PAD };
+enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_CHAIN, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE };
 enum Family { FAM_GEMM = 0, FAM_ATTN, FAM_LN, FAM_MASK, FAM_GATHER, FAM_ENTROPY, FAM_MISC, FAM_COUNT };
 const char* kFamilyNames[FAM_COUNT] = {"gemm_tc", "attention", "layernorm", "mask_select", "gather_patches",
                                        "entropy_elementwise", "misc"};
@@ -1073,8 +1073,6 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
             case ST_RATE:
                 CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
                                                  o.bpp ? o.bpp : w.bpp, o.rate_sums ? o.rate_sums : w.rate_sums, st, a.io));
-                break;
-            case ST_Y_TO_PAD:
                 break;
         }
         if (h->profiling && run_end) CUDA_TRY(h, cudaEventRecord(h->prof_events[h->prof_used - 1].second, st));
