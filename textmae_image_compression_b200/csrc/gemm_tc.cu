@@ -1126,7 +1126,6 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
         return launch_k(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, dim3(ctas), dim3(kPersistThreads), psmem, stream, true, d_params, pst, (int)grid.x, (int)grid.y, d_next, next_groups);
     }
     static const int two_prod_env = getenv("TMAE_TWO_PRODUCERS") ? atoi(getenv("TMAE_TWO_PRODUCERS")) : -1;
-    const int two_prod = two_prod_env >= 0 ? two_prod_env : (block_n <= 128 ? 1 : 0);   // wide tiles are MMA bound
     int kgroup = 1;
     int stages;
     if (conv_reuse_stage_bytes > 0) {
@@ -1135,6 +1134,10 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     } else {
         stages = gemm_pick_stages(block_n, (int)(grid.x * grid.y * grid.z), share_sm, &smem, &kgroup);
     }
+    // Second producer warp (TMAE_TWO_PRODUCERS=1): in isolation it shortens producer-bound main loops (64-wide GEMM
+    // tiles -20 %, fc2 -8 %), but since the conv layers moved to one haloed A box per three taps the whole forward is
+    // 4 % FASTER without it (25.6k vs 24.4k images/s, one batch in flight; equal with four) - off by default.
+    const int two_prod = two_prod_env >= 0 ? two_prod_env : 0;
     // every member of a grouped launch shares the activation and the store-phase specialisation
     if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
