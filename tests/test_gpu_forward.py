@@ -288,3 +288,37 @@ def test_fused_chain_kernel_matches_per_layer_launches(cuda_dev, monkeypatch):
         assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["sigma"], b["sigma"])
         assert torch.equal(a["latents"]["y_hat"], b["latents"]["y_hat"])
         assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6)
+
+
+_SWITCH_SCRIPT = r"""
+import sys, json, torch
+sys.path.insert(0, {root!r})
+from oracle import ref_model
+from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
+kw = dict(img_size=128, encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2, num_keep_patches=64)
+cfg = PathConfig(**kw); sd = make_state_dict(cfg, seed=5)
+g = torch.Generator().manual_seed(7)
+imgs = torch.rand(5, 3, 128, 128, generator=g); scores = torch.rand(5, cfg.num_patches, generator=g)
+ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+m = MCM(**kw, softmax_isa=16); m.load_state_dict(sd); m.cuda().eval()
+for _ in range(3):                       # plain launches, graph capture, graph replay
+    out = m(imgs.cuda(), scores.cuda())
+torch.cuda.synchronize()
+flips = (out["latents"]["y_sym"].cpu() != ref["y_sym"]).float().mean().item()
+rel = ((out["bpp"].cpu() - ref["bpp"]).abs() / ref["bpp"]).max().item()
+print(json.dumps(dict(ids=bool(torch.equal(out["ids_restore"].cpu(), ref["ids_restore"])), flips=flips, bpp_rel=rel)))
+"""
+
+
+@pytest.mark.parametrize("switch", ["TMAE_NO_GRAPH", "TMAE_NO_PDL", "TMAE_NO_TMA_STORE", "TMAE_NO_CONV_REUSE",
+                                    "TMAE_NO_WEIGHT_PREFETCH", "TMAE_TWO_PRODUCERS", "TMAE_KGROUP", "TMAE_CHAIN"])
+def test_ab_switches_keep_parity(cuda_dev, switch):
+    """Every A/B switch named in INTEGRATION.md selects a path that still meets the parity bar (the switches are read
+    once per process, hence one subprocess each)."""
+    import subprocess, sys
+    root = str(Path(__file__).resolve().parent.parent)
+    env = dict(os.environ, **{switch: "1"})
+    p = subprocess.run([sys.executable, "-c", _SWITCH_SCRIPT.format(root=root)], capture_output=True, text=True, timeout=300, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    st = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    assert st["ids"] and st["flips"] < 0.08 and st["bpp_rel"] < 0.02, (switch, st)
