@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TMAE_ABI_VERSION 1
+#define TMAE_ABI_VERSION 2
 #if defined(__GNUC__)
 #define TMAE_API __attribute__((visibility("default")))
 #else
@@ -67,6 +67,12 @@ typedef struct {
 #define TMAE_FLAG_DEBUG_SIMT    2u   /* bring-up only: run GEMM/conv layers on the CUDA-core checker kernel */
 #define TMAE_FLAG_SHARE_SM      4u   /* several handles/streams run concurrently on this GPU: size every launch so that
                                         CTAs of two kernels can share an SM (<= half the shared memory each) */
+/* Accuracy modes ("precise"): the named layers run with split-bf16 operands - every activation and weight is a pair of
+ * bf16 planes (hi, lo) and each product is three tensor-core terms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo accumulated in fp32
+ * (relative product error ~2^-17 instead of 2^-9), so that the quantised symbols round(y - mu) match the reference's fp32
+ * arithmetic up to rounding-boundary ties (north_star; MCM.py:735, 761-783). */
+#define TMAE_FLAG_PRECISE_RATE  8u   /* g_a, h_a, h_s_*, cc_transform_*, lrp_transform: everything after the encoder */
+#define TMAE_FLAG_PRECISE_ALL   16u  /* the encoder as well (patch embed, Block linears, fp32 softmax attention) */
 
 /* Outputs of one forward; any pointer may be NULL (that output is skipped).
  * N = batch, L = (img/patch)^2, K = num_keep_patches, s = sqrt(K), Cy = latent_depth, Cz = hyperprior_depth. */
@@ -146,6 +152,13 @@ TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, fl
 /* 3x3 pad-1 stride-1 convolution on the engine: x bf16 [N, s, s, Cin] NHWC, w f32 [Cout, Cin, 3, 3] -> f32 NHWC. */
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
                        int Cin, int Cout, int gelu, int impl, void* stream);
+
+/* The same two self-tests in the precise configuration (TMAE_FLAG_PRECISE_*): fp32 operands, split into (hi, lo) bf16
+ * planes inside, three tensor-core terms per product, fp32 accumulate -> results agree with an fp32 GEMM / conv to ~1e-5. */
+TMAE_API int  tmae_gemm_split(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
+                     int block_n, int impl, void* stream);
+TMAE_API int  tmae_conv3x3_split(const float* x, const float* w, const float* bias, float* out, int N, int s,
+                        int Cin, int Cout, int gelu, int impl, void* stream);
 
 /* Per-kernel-family device timing (bench.py roofline): enable = 1 brackets every launch of tmae_forward with CUDA
  * events on `stream`; enable = 2 brackets every RUN of consecutive launches of one kernel family (keeps the

@@ -46,3 +46,39 @@ def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
     out = G.conv3x3(x, w, b, gelu=gelu, impl=impl)
     err = G.rel_err(out, ref)
     assert err < 3e-5, f"impl={impl} rel err {err}"
+
+
+# ---- precise configuration (split-bf16 planes, three tensor-core terms per product): fp32 operands, compared with an
+# fp64 product of the SAME fp32 operands.  Expected error ~2^-17 per product (the dropped lo*lo term and the rounding of
+# the lo planes), i.e. 100x below the 2^-9 of plain bf16 operands.
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 224, 384, 0), (1000, 2304, 768, 256), (4160, 768, 3072, 0),
+                                       (257, 80, 176, 0), (130, 32, 80, 32)])
+@pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
+def test_gemm_split_matches_fp64(cuda_dev, M, N, K, bn, impl):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + 7)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev)
+    B = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev)
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    ref = (A.double() @ B.double().t() + bias.double())
+    out = G.gemm_split(A, B, bias, block_n=bn, impl=impl)
+    err = G.rel_err(out, ref)
+    bf16_err = G.rel_err(A.bfloat16().double() @ B.bfloat16().double().t() + bias.double(), ref)
+    assert err < 2e-5 and err < bf16_err / 50, f"impl={impl} rel err {err} (plain bf16 operands: {bf16_err})"
+
+
+@pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (5, 8, 80, 32, False),
+                                                  (1, 16, 576, 224, True), (7, 12, 64, 48, False), (40, 2, 192, 96, False),
+                                                  (64, 8, 352, 224, True), (40, 6, 128, 64, True), (21, 4, 64, 48, False)])
+@pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
+def test_conv3x3_split_matches_fp64(cuda_dev, N, s, Cin, Cout, gelu, impl):
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin + 3)
+    x = torch.randn(N, s, s, Cin, generator=g).to(cuda_dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))).to(cuda_dev)
+    b = torch.randn(Cout, generator=g).to(cuda_dev)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1)
+    if gelu:
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    out = G.conv3x3_split(x, w, b, gelu=gelu, impl=impl)
+    err = G.rel_err(out, ref)
+    assert err < 2e-5, f"impl={impl} rel err {err}"

@@ -2,8 +2,14 @@
 fp32 oracle on identical inputs, with the north-star tolerances:
    mask indices / token order      bit-exact
    encoder output                  <= 2e-2 relative (bf16 tensor-core operands vs fp32)
-   quantised symbols               bit-exact up to a REPORTED count of boundary flips (bf16 error on y - mu)
-   per-image bpp                   <= 0.5 %
+   quantised symbols               bit-exact apart from a reported count of ties at rounding boundaries
+   likelihoods, per-image bpp      <= 0.5 %
+Two operating modes are tested:
+   precise="all"  (conformance mode, split-bf16 operands = fp32-equivalent products): every tolerance above is ASSERTED
+                  (`_compare_precise`): symbols differ from the fp32 oracle only next to a rounding boundary, at a rate
+                  comparable to the oracle's own fp32-vs-fp64 disagreement.
+   precise=None   (throughput mode, bf16 operands, the bench headline): indices bit-exact, encoder <= 2e-2, bpp <= 0.5 %;
+                  its symbols are NOT interoperable with an fp32 entropy model (flip counts reported, `_compare`).
 A JSON report of every measured deviation is written to gpurun_out/parity_report.json."""
 import json
 import os
@@ -83,6 +89,139 @@ def _compare(tag, out, ref, cfg, bpp_tol, enc_tol=2e-2):
     assert stats["y_sym_flips"] / stats["y_sym_total"] < 0.12, stats
     assert stats["bpp_rel_max"] < bpp_tol, stats
     return stats
+
+
+def _compare_precise(tag, out, ref, cfg, ref64=None, teacher_forced=False, flip_frac=5e-3, near=2e-3):
+    """Conformance bar (north_star) for the precise modes.  `ref` = fp32 oracle, `ref64` = the same oracle in fp64 (gives
+    the oracle's own noise floor: how many symbols fp32 and fp64 arithmetic of the SAME algorithm disagree on)."""
+    st = {}
+    if not teacher_forced:
+        assert torch.equal(out["ids_keep"].cpu(), ref["ids_keep"]), "ids_keep"
+        assert torch.equal(out["ids_restore"].cpu(), ref["ids_restore"]), "ids_restore"
+        st["x_remain_rel"] = G.rel_err(out["x_remain"].cpu(), ref["x_remain"])
+        st["y_rel"] = G.rel_err(out["y"].cpu(), ref["y"])
+    st["z_rel"] = G.rel_err(out["z"].cpu(), ref["z"])
+    st["mu_rel"] = G.rel_err(out["mu"].cpu(), ref["mu"])
+    st["sigma_rel"] = G.rel_err(out["sigma"].cpu(), ref["sigma"])
+    ysym, zsym = out["latents"]["y_sym"].cpu(), out["latents"]["z_sym"].cpu()
+    yflip = ysym != ref["y_sym"]
+    st["y_sym_flips"] = int(yflip.sum()); st["y_sym_total"] = ysym.numel()
+    st["z_sym_flips"] = int((zsym != ref["z_sym"]).sum()); st["z_sym_total"] = zsym.numel()
+    frac = (ref["y"] - ref["mu"]) - torch.floor(ref["y"] - ref["mu"])
+    dist = (frac - 0.5).abs()                                    # oracle's distance to the rounding boundary
+    st["y_flips_exact_tie(<1e-4)"] = int((yflip & (dist < 1e-4)).sum())
+    st["y_flips_near_boundary(<%g)" % near] = int((yflip & (dist < near)).sum())
+    st["y_flips_far"] = int((yflip & (dist >= near)).sum())
+    st["y_flip_max_boundary_dist"] = dist[yflip].max().item() if yflip.any() else 0.0
+    st["y_sym_max_abs_diff"] = int((ysym - ref["y_sym"]).abs().max())
+    if ref64 is not None:                                        # noise floor of the oracle itself
+        st["oracle_fp32_vs_fp64_y_flips"] = int((ref["y_sym"] != ref64["y_sym"]).sum())
+        st["ours_vs_fp64_y_flips"] = int((ysym != ref64["y_sym"]).sum())
+        st["oracle_fp32_vs_fp64_mu_rel"] = G.rel_err(ref["mu"], ref64["mu"])
+        st["ours_vs_fp64_mu_rel"] = G.rel_err(out["mu"].cpu(), ref64["mu"])
+    lik, rlik = out["likelihoods"]["y"].cpu(), ref["y_lik"]
+    rel = ((lik - rlik).abs() / rlik)[~yflip]
+    st["y_lik_rel_median"] = rel.median().item()
+    st["y_lik_rel_p99"] = rel.quantile(0.99).item() if rel.numel() < 10_000_000 else -1
+    st["y_lik_rel_max"] = rel.max().item()
+    st["y_lik_frac_within_0.5pct"] = (rel <= 5e-3).float().mean().item()
+    zl, rzl = out["likelihoods"]["z"].cpu(), ref["z_lik"]
+    zagree = zsym == ref["z_sym"]
+    st["z_lik_rel_max"] = ((zl - rzl).abs() / rzl)[zagree].max().item()
+    bpp, rbpp = out["bpp"].cpu(), ref["bpp"]
+    st["bpp_rel_max"] = ((bpp - rbpp).abs() / rbpp).max().item()
+    st["y_hat_rel"] = G.rel_err(out["latents"]["y_hat"].cpu(), ref["y_hat"])
+    _report(tag, st)
+    print(tag, json.dumps(st))
+    if not teacher_forced:
+        assert st["x_remain_rel"] < 1e-4, st                                   # north_star asks 2e-2; precise gives ~1e-5
+    assert st["z_sym_flips"] <= max(1, st["z_sym_total"] // 2000), st
+    assert st["y_sym_flips"] <= flip_frac * st["y_sym_total"], st             # <= 0.5 % (VERDICT r1 next #1)
+    assert st["y_sym_max_abs_diff"] <= 1, st
+    assert st["y_lik_rel_median"] < 5e-3, st                                   # north_star: likelihoods within 0.5 %
+    assert st["bpp_rel_max"] < 5e-3, st                                        # north_star: per-image bpp within 0.5 %
+    return st
+
+
+@pytest.mark.parametrize("simt", [True, False], ids=["simt_checker", "tcgen05"])
+@pytest.mark.parametrize("mode", ["all", "rate"])
+def test_small_model_full_path_precise(cuda_dev, simt, mode):
+    cfg = PathConfig(**SMALL)
+    sd = make_state_dict(cfg, seed=3)
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(3, 3, 64, 64, generator=g)
+    scores = torch.rand(3, cfg.num_patches, generator=g)
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(SMALL, sd, cuda_dev, debug_simt=simt, precise=mode)
+    for rep in range(3):                    # plain launches, graph capture, graph replay
+        out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    if mode == "all":
+        ref64 = ref_model.forward_rate(sd, cfg, imgs, scores, dtype=torch.float64)
+        st = _compare_precise(f"precise_all_small_{'simt' if simt else 'tc'}", out, ref, cfg, ref64=ref64)
+        assert st["y_flips_far"] == 0, st
+    else:                                   # encoder in bf16: only the rate half is fp32-equivalent -> compare through forward_from_latent
+        out2 = m.forward_from_latent(ref["y"].cuda())
+        torch.cuda.synchronize()
+        st = _compare_precise(f"precise_rate_small_tf_{'simt' if simt else 'tc'}", out2, ref, cfg, teacher_forced=True)
+        assert st["y_flips_far"] == 0, st
+        assert torch.equal(out["ids_restore"].cpu(), ref["ids_restore"])
+
+
+@pytest.mark.parametrize("img,K,N", [(128, 16, 5), (128, 64, 3), (192, 144, 2), (320, 400, 1), (64, 16, 9)])
+def test_geometry_sweep_precise(cuda_dev, img, K, N):
+    kw = dict(img_size=img, encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2, num_keep_patches=K)
+    cfg = PathConfig(**kw)
+    sd = make_state_dict(cfg, seed=11)
+    g = torch.Generator().manual_seed(img + K + N)
+    imgs = torch.rand(N, 3, img, img, generator=g)
+    scores = torch.rand(N, cfg.num_patches, generator=g)
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(kw, sd, cuda_dev, precise="all")
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    _compare_precise(f"precise_all_sweep_img{img}_K{K}_N{N}", out, ref, cfg)
+
+
+@pytest.mark.parametrize("K,n_img", [(64, 2), (144, 1)])
+def test_vit_base_kodak_precise(cuda_dev, kodak, K, n_img):
+    """The headline model (ViT-B/16, Kodak images + reference-generated scores) in conformance mode against the live fp32
+    oracle (and its fp64 twin for the noise floor), end to end and teacher-forced."""
+    imgs, scores = kodak
+    cfg = vit_base(K)
+    sd = make_state_dict(cfg, seed=0)
+    ref = ref_model.forward_rate(sd, cfg, imgs[:n_img], scores[:n_img])
+    ref64 = ref_model.forward_rate(sd, cfg, imgs[:n_img], scores[:n_img], dtype=torch.float64)
+    m = _build(dict(num_keep_patches=K), sd, cuda_dev, precise="all")
+    out = m(imgs[:n_img].cuda(), scores[:n_img].cuda())
+    torch.cuda.synchronize()
+    _compare_precise(f"precise_all_vitB_K{K}_kodak", out, ref, cfg, ref64=ref64)
+    out_tf = m.forward_from_latent(ref["y"].cuda())
+    torch.cuda.synchronize()
+    st = _compare_precise(f"precise_all_vitB_K{K}_kodak_teacher_forced", out_tf, ref, cfg, ref64=ref64, teacher_forced=True)
+    assert st["y_flips_far"] == 0, st
+    del m
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("K", [256, 400])
+def test_vit_large_512_precise(cuda_dev, K):
+    """BASELINE.json config 4 / 5 geometry (ViT-L/16, 512x512, K = 256 and 400) in conformance mode."""
+    from textmae_image_compression_b200 import vit_large
+    cfg = vit_large(K, 512)
+    kwargs = dict(img_size=512, encoder_embed_dim=1024, encoder_depth=24, encoder_num_heads=16, num_keep_patches=K)
+    sd = make_state_dict(cfg, seed=0)
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand(2, 3, 512, 512, generator=g)
+    scores = torch.rand(2, cfg.num_patches, generator=g)
+    scores[1] = torch.round(scores[1] * 40) / 40
+    ref = ref_model.forward_rate(sd, cfg, imgs, scores)
+    m = _build(kwargs, sd, cuda_dev, precise="all")
+    out = m(imgs.cuda(), scores.cuda())
+    torch.cuda.synchronize()
+    _compare_precise(f"precise_all_vitL_K{K}_512", out, ref, cfg)
+    del m
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("simt", [True, False], ids=["simt_checker", "tcgen05"])
@@ -266,30 +405,6 @@ def test_graph_replay_matches_direct_launches(cuda_dev, monkeypatch):
     assert not torch.equal(outs_g[1]["latents"]["y_sym"], outs_g[2]["latents"]["y_sym"])   # really different inputs
 
 
-def test_fused_chain_kernel_matches_per_layer_launches(cuda_dev, monkeypatch):
-    """TMAE_CHAIN=1 runs each serial cc / lrp net (5 conv layers) as one cooperative launch with grid barriers between
-    layers; it must reproduce the per-layer launches bit for bit (same tiles, same accumulation order)."""
-    cfg = PathConfig(**SMALL)
-    sd = make_state_dict(cfg, seed=3)
-    g = torch.Generator().manual_seed(31)
-    imgs = torch.rand(5, 3, 64, 64, generator=g).cuda()
-    scores = torch.rand(5, cfg.num_patches, generator=g).cuda()
-    m_plain = _build(SMALL, sd, cuda_dev)
-    m_plain._ensure_handle()
-    monkeypatch.setenv("TMAE_CHAIN", "1")
-    m_chain = _build(SMALL, sd, cuda_dev)
-    m_chain._ensure_handle()
-    monkeypatch.delenv("TMAE_CHAIN")
-    assert m_chain.launch_count(5) < m_plain.launch_count(5) - 40
-    for _ in range(2):                                  # second call = graph replay with the cooperative nodes
-        a, b = m_chain(imgs, scores), m_plain(imgs, scores)
-        torch.cuda.synchronize()
-        assert torch.equal(a["latents"]["y_sym"], b["latents"]["y_sym"])
-        assert torch.equal(a["mu"], b["mu"]) and torch.equal(a["sigma"], b["sigma"])
-        assert torch.equal(a["latents"]["y_hat"], b["latents"]["y_hat"])
-        assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6)
-
-
 _SWITCH_SCRIPT = r"""
 import sys, json, torch
 sys.path.insert(0, {root!r})
@@ -311,7 +426,7 @@ print(json.dumps(dict(ids=bool(torch.equal(out["ids_restore"].cpu(), ref["ids_re
 
 
 @pytest.mark.parametrize("switch", ["TMAE_NO_GRAPH", "TMAE_NO_PDL", "TMAE_NO_TMA_STORE", "TMAE_NO_CONV_REUSE",
-                                    "TMAE_NO_WEIGHT_PREFETCH", "TMAE_TWO_PRODUCERS", "TMAE_KGROUP", "TMAE_CHAIN"])
+                                    "TMAE_NO_WEIGHT_PREFETCH", "TMAE_TWO_PRODUCERS", "TMAE_KGROUP"])
 def test_ab_switches_keep_parity(cuda_dev, switch):
     """Every A/B switch named in INTEGRATION.md selects a path that still meets the parity bar (the switches are read
     once per process, hence one subprocess each)."""

@@ -14,6 +14,8 @@ TMAE_OK, TMAE_EINVAL, TMAE_ECUDA, TMAE_ESTATE, TMAE_ENOMEM = 0, 1, 2, 3, 4
 FLAG_SKIP_DEAD_LRP = 1
 FLAG_DEBUG_SIMT = 2
 FLAG_SHARE_SM = 4
+FLAG_PRECISE_RATE = 8
+FLAG_PRECISE_ALL = 16
 
 
 class TmaeConfig(C.Structure):
@@ -64,6 +66,8 @@ SIGNATURES = {
     "tmae_bottleneck_rate": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "tmae_gemm_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tmae_gemm_split": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "tmae_conv3x3_split": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_profile_enable": (C.c_int, [_P, C.c_int]),
     "tmae_profile_read": (C.c_int, [_P, C.POINTER(TmaeProfileEntry), C.c_int, C.POINTER(C.c_int)]),
     "tmae_profile_read_steps": (C.c_int, [_P, C.POINTER(TmaeProfileStep), C.c_int, C.POINTER(C.c_int)]),

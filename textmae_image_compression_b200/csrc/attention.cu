@@ -190,10 +190,94 @@ inline size_t attn_smem(int T) {
     return ((size_t)2 * Tp + (size_t)kAttnWarps * 16) * KPITCH * sizeof(__nv_bfloat16);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Precise mode (TMAE_FLAG_PRECISE_ALL): fp32 softmax attention on CUDA cores.  q, k, v arrive as split-bf16 plane pairs
+// (hi + lo = 16 mantissa bits) from the precise QKV GEMM; scores, softmax (expf, like the reference's fp32 softmax) and
+// the PV sum run in fp32; the result leaves as a plane pair for the precise proj GEMM.  One CTA per (image, head):
+// K (pitch 65, conflict-free for lane = key) and V (lane = dim) of all keys in shared memory, one warp per query row.
+// This op is 0.8-3 % of the path's FLOPs; precise mode trades throughput for reference-exact symbols.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAttnF32Warps = 8;
+constexpr int KP32 = HD + 1;
+__global__ void __launch_bounds__(32 * kAttnF32Warps)
+attention_f32_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_lo, __nv_bfloat16* __restrict__ out, long long out_lo,
+                     int T, int H, int C, float scale) {
+    pdl_wait();
+    pdl_launch_dependents();
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    float* sK = reinterpret_cast<float*>(smem_attn);                 // [T][65]
+    float* sV = sK + (size_t)T * KP32;                               // [T][64]
+    float* sQ = sV + (size_t)T * HD;                                 // [warps][64]
+    float* sP = sQ + kAttnF32Warps * HD;                             // [warps][T]
+    const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t ld = (size_t)3 * C;
+    const __nv_bfloat16* base = qkv + (size_t)n * T * ld + (size_t)h * HD;
+    auto ldf = [&](const __nv_bfloat16* p) { return __bfloat162float(p[0]) + __bfloat162float(p[qkv_lo]); };
+    for (int e = tid; e < T * HD; e += blockDim.x) {
+        const int key = e / HD, d = e - key * HD;
+        sK[key * KP32 + d] = ldf(base + (size_t)key * ld + C + d);
+        sV[key * HD + d] = ldf(base + (size_t)key * ld + 2 * C + d);
+    }
+    __syncthreads();
+    float* myQ = sQ + warp * HD;
+    float* myP = sP + (size_t)warp * T;
+    for (int q = warp; q < T; q += kAttnF32Warps) {
+        myQ[lane] = ldf(base + (size_t)q * ld + lane);
+        myQ[lane + 32] = ldf(base + (size_t)q * ld + lane + 32);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < T; j += 32) {
+            const float* kr = sK + j * KP32;
+            float acc = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < HD; ++d) acc = fmaf(myQ[d], kr[d], acc);
+            acc *= scale;
+            myP[j] = acc;
+            mx = fmaxf(mx, acc);
+        }
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < T; j += 32) {
+            const float pj = expf(myP[j] - mx);
+            myP[j] = pj;
+            sum += pj;
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float o0 = 0.f, o1 = 0.f;
+        for (int j = 0; j < T; ++j) {
+            const float pj = myP[j];
+            o0 = fmaf(pj, sV[j * HD + lane], o0);
+            o1 = fmaf(pj, sV[j * HD + lane + 32], o1);
+        }
+        const float inv = 1.f / sum;
+        o0 *= inv; o1 *= inv;
+        __nv_bfloat16* dst = out + ((size_t)n * T + q) * C + (size_t)h * HD;
+        const __nv_bfloat16 h0 = __float2bfloat16(o0), h1 = __float2bfloat16(o1);
+        dst[lane] = h0;
+        dst[lane + 32] = h1;
+        dst[out_lo + lane] = __float2bfloat16(o0 - __bfloat162float(h0));
+        dst[out_lo + lane + 32] = __float2bfloat16(o1 - __bfloat162float(h1));
+        __syncwarp();
+    }
+}
+inline size_t attn_f32_smem(int T) {
+    return ((size_t)T * KP32 + (size_t)T * HD + (size_t)kAttnF32Warps * HD + (size_t)kAttnF32Warps * T) * sizeof(float);
+}
+
 }  // namespace
 
+// The dynamic shared-memory limit is a property of the (process-global) kernel, not of a handle: it is raised to the
+// device maximum once, so handles with different token counts can coexist in one process in any creation order.
 cudaError_t attention_configure(int T) {
-    return cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem(T));
+    if (attn_smem(T) > 227 * 1024) return cudaErrorInvalidValue;
+    static cudaError_t once = [] {
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    }();
+    return once;
 }
 
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int T, int H, int C, float scale,
@@ -203,6 +287,15 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
     TMAE_CARVEOUT_ONCE(attention_kernel);
     return launch_k(attention_kernel, dim3(N * H), dim3(kAttnThreads), attn_smem(T), st, true, qkv, out, T, Tp, H, C,
                     scale * 1.4426950408889634f);
+}
+
+cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,
+                                 int T, int H, int C, float scale, cudaStream_t st) {
+    if (C != H * HD || qkv_lo == 0 || out_lo == 0) return cudaErrorInvalidValue;
+    if (attn_f32_smem(T) > 227 * 1024) return cudaErrorInvalidValue;
+    TMAE_CARVEOUT_ONCE(attention_f32_kernel);
+    return launch_k(attention_f32_kernel, dim3(N * H), dim3(32 * kAttnF32Warps), attn_f32_smem(T), st, true, qkv, qkv_lo, out,
+                    out_lo, T, H, C, scale);
 }
 
 }  // namespace tmae

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(192)
 gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict__ ids_keep,
                       __nv_bfloat16* __restrict__ patches, float* __restrict__ x, const float* __restrict__ cls_token,
                       const float* __restrict__ pos_embed, int S, int grid_w, int K, int T, int C, int in_chans,
-                      int patch, const IoBlock* __restrict__ io) {
+                      int patch, long long lo_off, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
     if (io) imgs = io->imgs;
@@ -40,20 +40,28 @@ gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict_
         const int p = rem / patch, q = rem - p * patch;
         const float4 v = __ldg(reinterpret_cast<const float4*>(
             imgs + (((size_t)n * in_chans + c) * S + (py * patch + p)) * S + px * patch + q));
-        uint2 pk;
-        pk.x = pack_bf16x2(v.x, v.y);
-        pk.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(dst + e) = pk;
+        if (lo_off != 0) {                 // precise patch embed: second plane bf16(v - bf16(v))
+            uint2 hi, lo;
+            split_bf16x2(v.x, v.y, hi.x, lo.x);
+            split_bf16x2(v.z, v.w, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(dst + e) = hi;
+            *reinterpret_cast<uint2*>(dst + lo_off + e) = lo;
+        } else {
+            uint2 pk;
+            pk.x = pack_bf16x2(v.x, v.y);
+            pk.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(dst + e) = pk;
+        }
     }
 }
 
 cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __nv_bfloat16* patches, float* x,
                                   const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
-                                  int T, int C, int in_chans, int patch, cudaStream_t st, const IoBlock* io) {
+                                  int T, int C, int in_chans, int patch, long long lo_off, cudaStream_t st, const IoBlock* io) {
     dim3 grid(K + 1, N);
     TMAE_CARVEOUT_ONCE(gather_patches_kernel);
     return launch_k(gather_patches_kernel, grid, dim3(192), 0, st, true, imgs, ids_keep, patches, x, cls_token, pos_embed, S,
-                    grid_w, K, T, C, in_chans, patch, io);
+                    grid_w, K, T, C, in_chans, patch, lo_off, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -66,7 +74,7 @@ template <int VEC_PER_LANE>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32, int rows, int C, int T, int drop_cls,
-                 float eps, const IoBlock* __restrict__ io) {
+                 float eps, long long lo_off, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
     if (io) out_f32 = io->out.x_remain;
@@ -104,26 +112,35 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
         const float o1 = (v[i].y - mean) * rstd * g.y + b.y;
         const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
         const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
-        uint2 pk;
-        pk.x = pack_bf16x2(o0, o1);
-        pk.y = pack_bf16x2(o2, o3);
-        *reinterpret_cast<uint2*>(out + (size_t)orow * C + (i * 32 + lane) * 4) = pk;
+        __nv_bfloat16* dst = out + (size_t)orow * C + (i * 32 + lane) * 4;
+        if (lo_off != 0) {                 // the consumer is a precise layer: second plane bf16(v - bf16(v))
+            uint2 hi, lo;
+            split_bf16x2(o0, o1, hi.x, lo.x);
+            split_bf16x2(o2, o3, hi.y, lo.y);
+            *reinterpret_cast<uint2*>(dst) = hi;
+            *reinterpret_cast<uint2*>(dst + lo_off) = lo;
+        } else {
+            uint2 pk;
+            pk.x = pack_bf16x2(o0, o1);
+            pk.y = pack_bf16x2(o2, o3);
+            *reinterpret_cast<uint2*>(dst) = pk;
+        }
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)orow * C + (i * 32 + lane) * 4) = make_float4(o0, o1, o2, o3);
     }
 }
 
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
-                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st, const IoBlock* io) {
+                             int rows, int C, int T, int drop_cls, float eps, long long lo_off, cudaStream_t st, const IoBlock* io) {
     const int blocks = (rows * 32 + 255) / 256;
     if (C % 128 != 0) return cudaErrorInvalidValue;
     switch (C / 128) {
-        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); return launch_k(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); return launch_k(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); return launch_k(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); return launch_k(layernorm_kernel<1>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); return launch_k(layernorm_kernel<2>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); return launch_k(layernorm_kernel<3>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
-        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); return launch_k(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, io);
+        case 6: TMAE_CARVEOUT_ONCE(layernorm_kernel<6>); return launch_k(layernorm_kernel<6>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 8: TMAE_CARVEOUT_ONCE(layernorm_kernel<8>); return launch_k(layernorm_kernel<8>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 10: TMAE_CARVEOUT_ONCE(layernorm_kernel<10>); return launch_k(layernorm_kernel<10>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 1: TMAE_CARVEOUT_ONCE(layernorm_kernel<1>); return launch_k(layernorm_kernel<1>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 2: TMAE_CARVEOUT_ONCE(layernorm_kernel<2>); return launch_k(layernorm_kernel<2>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 3: TMAE_CARVEOUT_ONCE(layernorm_kernel<3>); return launch_k(layernorm_kernel<3>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
+        case 4: TMAE_CARVEOUT_ONCE(layernorm_kernel<4>); return launch_k(layernorm_kernel<4>, dim3(blocks), dim3(256), 0, st, true, x, gamma, beta, out, out_f32, rows, C, T, drop_cls, eps, lo_off, io);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -168,7 +185,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf
 __global__ void __launch_bounds__(256)
 bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab, long long total, int Cz,
                   float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
-                  __nv_bfloat16* __restrict__ zhat_bf, int s4, double* __restrict__ rate_acc, int rows_per_image,
+                  __nv_bfloat16* __restrict__ zhat_bf, long long lo_off, int s4, double* __restrict__ rate_acc, int rows_per_image,
                   const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
@@ -193,7 +210,11 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
         if (sym_out) sym_out[idx] = (int32_t)sym;
         if (zhat_out) zhat_out[idx] = zh;
         n = (int)(row / rows_per_image);
-        if (zhat_bf) zhat_bf[idx] = __float2bfloat16(zh);
+        if (zhat_bf) {
+            const __nv_bfloat16 hi = __float2bfloat16(zh);
+            zhat_bf[idx] = hi;
+            if (lo_off != 0) zhat_bf[idx + lo_off] = __float2bfloat16(zh - __bfloat162float(hi));
+        }
         lg = log2f(lik);
     }
     if (rate_acc) {
@@ -210,13 +231,13 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
 }
 
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
-                              float* zhat, __nv_bfloat16* zhat_bf, int s4, double* rate_acc, int rows_per_image,
+                              float* zhat, __nv_bfloat16* zhat_bf, long long lo_off, int s4, double* rate_acc, int rows_per_image,
                               cudaStream_t st, const IoBlock* io) {
     const long long total = rows * Cz;
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(bottleneck_kernel);
-    return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_bf, s4,
+    return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_bf, lo_off, s4,
                     rate_acc, rows_per_image, io);
 }
 
@@ -241,7 +262,7 @@ __global__ void __launch_bounds__(256)
 gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
                       int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_bf,
-                      int ld_bf, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
+                      long long lo_off, int ld_bf, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
     if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; }
@@ -268,10 +289,19 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
         const int K = s * s;
         n = (int)(row / K);
         if (yhat_bf) {
-            uint2 pk;
-            pk.x = pack_bf16x2(yh.x, yh.y);
-            pk.y = pack_bf16x2(yh.z, yh.w);
-            *reinterpret_cast<uint2*>(yhat_bf + (size_t)row * ld_bf + c) = pk;
+            __nv_bfloat16* dst = yhat_bf + (size_t)row * ld_bf + c;
+            if (lo_off != 0) {
+                uint2 hi, lo;
+                split_bf16x2(yh.x, yh.y, hi.x, lo.x);
+                split_bf16x2(yh.z, yh.w, hi.y, lo.y);
+                *reinterpret_cast<uint2*>(dst) = hi;
+                *reinterpret_cast<uint2*>(dst + lo_off) = lo;
+            } else {
+                uint2 pk;
+                pk.x = pack_bf16x2(yh.x, yh.y);
+                pk.y = pack_bf16x2(yh.z, yh.w);
+                *reinterpret_cast<uint2*>(dst) = pk;
+            }
         }
         lg = (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
     }
@@ -288,14 +318,14 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
 }
 
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
-                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, int ld_bf,
-                                  int s, double* rate_acc, cudaStream_t st, const IoBlock* io) {
+                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, long long lo_off,
+                                  int ld_bf, int s, double* rate_acc, cudaStream_t st, const IoBlock* io) {
     const long long total = rows * (cs / 4);
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
     return launch_k(gaussian_slice_kernel, dim3(blocks), dim3(256), 0, st, true, y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat,
-                    yhat_bf, ld_bf, s, rate_acc, io);
+                    yhat_bf, lo_off, ld_bf, s, rate_acc, io);
 }
 
 // flat variant for the stand-alone operator (n elements, no layout)
@@ -387,24 +417,28 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
 // Weight prepack: fp32 [Cout, Cin_total, kh, kw] (or [Cout, Cin] linear) -> bf16 [Cout, Kp], K index =
 // tap-major, then channel segment (each padded to a multiple of 64 with zeros), then channel.
 // shuffle = 1: output row q*Cq + c takes source channel c*4 + q (PixelShuffle(2) made contiguous per quadrant).
+// planes = 2 (precise layers): every tap holds its segments twice - the hi planes bf16(w), then the lo planes
+// bf16(w - bf16(w)).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
                                       int Cin_total, int taps, int nseg, int seg_c0, int seg_c1, int seg_c2,
-                                      int shuffle) {
+                                      int shuffle, int planes) {
     const int segc[3] = {seg_c0, seg_c1, seg_c2};
     int segpad[3], kp_tap = 0;
     for (int i = 0; i < 3; ++i) {
         segpad[i] = i < nseg ? ((segc[i] + 63) / 64) * 64 : 0;
         kp_tap += segpad[i];
     }
-    const long long Kp = (long long)kp_tap * taps;
+    const long long Kp = (long long)kp_tap * taps * planes;
     const long long total = (long long)Cout * Kp;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int ro = (int)(idx / Kp);
         const long long kidx = idx - (long long)ro * Kp;
-        const int tap = (int)(kidx / kp_tap);
-        int within = (int)(kidx - (long long)tap * kp_tap);
+        const int tap = (int)(kidx / (kp_tap * planes));
+        int within = (int)(kidx - (long long)tap * kp_tap * planes);
+        const int plane = within / kp_tap;
+        within -= plane * kp_tap;
         int ci = -1, cbase = 0;
         for (int i = 0; i < nseg; ++i) {
             if (within < segpad[i]) {
@@ -422,13 +456,14 @@ __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16
         }
         float v = 0.f;
         if (ci >= 0) v = w[((size_t)co * Cin_total + ci) * taps + tap];
-        out[idx] = __float2bfloat16(v);
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        out[idx] = plane == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
     }
 }
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
-                                  const int* segc, int shuffle, cudaStream_t st) {
+                                  const int* segc, int shuffle, int planes, cudaStream_t st) {
     prepack_weight_kernel<<<1024, 256, 0, st>>>(w, out, Cout, Cin_total, taps, nseg, segc[0], nseg > 1 ? segc[1] : 0,
-                                                nseg > 2 ? segc[2] : 0, shuffle);
+                                                nseg > 2 ? segc[2] : 0, shuffle, planes);
     return cudaGetLastError();
 }
 
@@ -483,13 +518,16 @@ cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaSt
     return cudaGetLastError();
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o, long long n) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        o[i] = __float2bfloat16(a[i]);
+__global__ void f32_to_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o, long long n, long long lo_off) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const __nv_bfloat16 hi = __float2bfloat16(a[i]);
+        o[i] = hi;
+        if (lo_off != 0) o[i + lo_off] = __float2bfloat16(a[i] - __bfloat162float(hi));
+    }
 }
-cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, cudaStream_t st) {
+cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    f32_to_bf16_kernel<<<512, 256, 0, st>>>(a, o, n);
+    f32_to_bf16_kernel<<<512, 256, 0, st>>>(a, o, n, lo_off);
     return cudaGetLastError();
 }
 

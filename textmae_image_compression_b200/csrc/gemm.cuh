@@ -10,7 +10,7 @@ namespace tmae {
 
 constexpr int kBlockM = 128;      // UMMA M (cta_group::1)
 constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one 128B-swizzle atom row
-constexpr int kMaxSegs = 3;
+constexpr int kMaxSegs = 9;       // 3 concatenated channel segments x 3 split-bf16 terms (precise layers)
 constexpr int kMaxTaps = 9;
 
 // Row spaces.  Every activation matrix is COMPACT channels-last: pixel (n, y, x) of an s x s grid is row n*s*s + y*s + x.
@@ -22,6 +22,12 @@ constexpr int kMaxTaps = 9;
 //              wasted rows when s*box_y*box_n == 128.  conv_reuse: ONE box with a row of halo above and below
 //              ([64, s, box_n, box_y + 2]) is loaded per (channel block, dx) and serves the three dy taps through
 //              shared-memory descriptor offsets of box_n*s rows (a multiple of the 8-row swizzle atom).
+//
+// Precise layers (split-bf16, TMAE_FLAG_PRECISE_*): every operand is a pair of bf16 planes (hi = bf16(v),
+// lo = bf16(v - hi)) and a product a*w is issued as three tensor-core terms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo
+// (relative error ~2^-17 instead of 2^-9; the dropped a_lo*w_lo term is ~2^-18).  The terms are simply MORE K SEGMENTS
+// of the same main loop: segment list (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) per concatenated source, the weights hold
+// the hi planes of a tap followed by its lo planes (seg_b_kb0 points each segment at its weight columns).
 enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_CONV = 2 };
 enum RowMap : int {
     MAP_SAME = 0,        // out row = the pixel's / token's own compact row
@@ -38,6 +44,7 @@ struct OutSpec {
     int ld;        // elements per row
     int dtype;     // OutType
     int map;       // RowMap
+    long long lo_off;   // bf16 outputs feeding a precise layer: element offset of the "lo" plane holding bf16(v - bf16(v)); 0 = none
 };
 
 struct alignas(64) GemmParams {
@@ -54,6 +61,8 @@ struct alignas(64) GemmParams {
     // K loop
     int num_segs;
     int seg_kblocks[kMaxSegs];        // ceil(C_seg / 64)
+    int seg_b_kb0[kMaxSegs];          // first k-block of the segment's weights inside one tap of the packed B matrix
+    int b_kb_per_tap;                 // k-blocks per tap of the packed B matrix (precise layers: hi planes then lo planes)
     int num_taps;                     // 1, or 9 for IN_CONV: taps in (kh, kw) row-major order, shift (kw - 1, kh - 1)
     // problem
     int M;                            // linear: rows; conv: m_tiles * 128 (virtual rows of the tile grid)
@@ -79,23 +88,9 @@ struct alignas(64) GemmParams {
     int resid_map;
     const int64_t* gather_ids;        // MAP_GATHER1
     OutSpec out[2];
-    double flops;                     // algorithmic flops of this GEMM (profiling)
+    double flops;                     // flops of this GEMM as the reference would count them for the rows computed (profiling)
+    int mma_terms;                    // tensor-core products issued per algorithmic product: 1, or 3 for precise (split-bf16) layers
     long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)
 };
-
-// A chain = consecutive layers of one net (or of several independent nets, grouped) that all work on the same pixel
-// grid: executed by ONE cooperative launch with a grid-wide barrier between layers instead of one launch per layer.
-constexpr int kMaxChainLayers = 6;
-struct ChainDesc {
-    int num_layers;
-    int first[kMaxChainLayers];      // index of the layer's first GemmParams in the plan's parameter array
-    int groups[kMaxChainLayers];     // independent members of the layer (grouped nets / slices)
-    int m_tiles[kMaxChainLayers];
-    int n_tiles[kMaxChainLayers];
-    int kind[kMaxChainLayers];       // ChainKind: activation + store-phase specialisation of the layer
-    unsigned int* bar;               // [2] device words: arrival counter, generation (sense-reversing grid barrier)
-};
-enum ChainKind : int { CHAIN_GELU_BF16_SAME = 0, CHAIN_NONE_GENERIC = 1, CHAIN_HALF_TANH_GENERIC = 2 };
-
 
 }  // namespace tmae

@@ -9,8 +9,9 @@
 //   warps 2-9  : epilogue - tcgen05.ld 32 lanes x 32 columns, + bias, GELU / 0.5*tanh, residual / pos-embed add,
 //                row remap (stride-2 subsample, PixelShuffle, token rows), bf16 / fp32 stores or TMA stores;
 //                warp 2 doubles as second TMA producer on narrow tiles
-// Variants: persistent tile loop with double-buffered TMEM (gemm_tc_persistent_kernel), cooperative multi-layer chain
-// (gemm_tc_chain_kernel, opt-in), CUDA-core checker (gemm_simt_kernel).
+// Variants: persistent tile loop with double-buffered TMEM (gemm_tc_persistent_kernel), CUDA-core checker
+// (gemm_simt_kernel).  Precise layers (split-bf16, three tensor-core terms per product) are the same kernels walking
+// three times as many K segments (gemm.cuh).
 // Serves reference layers: PatchEmbed conv (MCM.py:300-302), Block linears (MCM.py:313-322), g_a 1x1 convs
 // (MCM.py:77-93), h_a / h_s / cc_transform / lrp_transform 3x3 convs (MCM.py:115-293).
 #include <stdio.h>
@@ -156,7 +157,16 @@ __device__ __forceinline__ void finish_store(const EpiCtx& p, float (&v)[NV], in
         if (os.dtype == OUT_NONE || orow < 0) continue;
         if (os.dtype == OUT_BF16) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(os.ptr) + orow * os.ld + ocol;
-            if (NV == 8) {
+            if (os.lo_off != 0) {
+#pragma unroll
+                for (int i = 0; i < NV; i += 4) {
+                    uint2 hi, lo;
+                    split_bf16x2(v[i], v[i + 1], hi.x, lo.x);
+                    split_bf16x2(v[i + 2], v[i + 3], hi.y, lo.y);
+                    *reinterpret_cast<uint2*>(dst + i) = hi;
+                    *reinterpret_cast<uint2*>(dst + os.lo_off + i) = lo;
+                }
+            } else if (NV == 8) {
                 uint4 pk;
                 pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
                 pk.z = pack_bf16x2(v[NV - 4], v[NV - 3]); pk.w = pack_bf16x2(v[NV - 2], v[NV - 1]);
@@ -178,10 +188,19 @@ __device__ __forceinline__ void finish_store(const EpiCtx& p, float (&v)[NV], in
 __device__ __forceinline__ void store_out4(const OutSpec& os, int orow, int ocol, const float (&v)[4]) {
     if (os.dtype == OUT_NONE || orow < 0) return;
     if (os.dtype == OUT_BF16) {
-        uint2 pk;
-        pk.x = pack_bf16x2(v[0], v[1]);
-        pk.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(os.ptr) + (long long)orow * os.ld + ocol) = pk;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(os.ptr) + (long long)orow * os.ld + ocol;
+        if (os.lo_off != 0) {
+            uint2 hi, lo;
+            split_bf16x2(v[0], v[1], hi.x, lo.x);
+            split_bf16x2(v[2], v[3], hi.y, lo.y);
+            *reinterpret_cast<uint2*>(dst) = hi;
+            *reinterpret_cast<uint2*>(dst + os.lo_off) = lo;
+        } else {
+            uint2 pk;
+            pk.x = pack_bf16x2(v[0], v[1]);
+            pk.y = pack_bf16x2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(dst) = pk;
+        }
     } else {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(os.ptr) + (long long)orow * os.ld + ocol) =
             make_float4(v[0], v[1], v[2], v[3]);
@@ -306,6 +325,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
     };
     float4 bias_next = load_bias(half * 32);
     const bool has_resid = e.resid != nullptr;
+    const long long lo_off = e.out[0].lo_off;          // EPI_BF16_SAME of a layer that feeds a precise layer: second plane
     const unsigned valid_mask = __ballot_sync(0xffffffffu, r.valid != 0);   // rows of this quarter that produce output
     mbar_wait(wait_bar, wait_parity);
     tc_fence_after();
@@ -348,10 +368,21 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                 const int orow = __shfl_sync(0xffffffffu, r.lin, rr);
                 if (col_ok && ((valid_mask >> rr) & 1u)) {
                     const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                    uint2 pk;
-                    pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
-                    pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) + (long long)orow * e.out[0].ld + col) = pk;
+                    const float v0 = act_fast<ACT>(t4.x + b4.x), v1 = act_fast<ACT>(t4.y + b4.y);
+                    const float v2 = act_fast<ACT>(t4.z + b4.z), v3 = act_fast<ACT>(t4.w + b4.w);
+                    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) + (long long)orow * e.out[0].ld + col;
+                    if (lo_off != 0) {
+                        uint2 hi, lo;
+                        split_bf16x2(v0, v1, hi.x, lo.x);
+                        split_bf16x2(v2, v3, hi.y, lo.y);
+                        *reinterpret_cast<uint2*>(dst) = hi;
+                        *reinterpret_cast<uint2*>(dst + lo_off) = lo;
+                    } else {
+                        uint2 pk;
+                        pk.x = pack_bf16x2(v0, v1);
+                        pk.y = pack_bf16x2(v2, v3);
+                        *reinterpret_cast<uint2*>(dst) = pk;
+                    }
                 }
             }
             __syncwarp();
@@ -367,10 +398,20 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                     const int rr = it * 4 + rsub;
                     if ((valid_mask >> rr) & 1u) {
                         const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                        uint2 pk;
-                        pk.x = pack_bf16x2(act_fast<ACT>(t4.x + b4.x), act_fast<ACT>(t4.y + b4.y));
-                        pk.y = pack_bf16x2(act_fast<ACT>(t4.z + b4.z), act_fast<ACT>(t4.w + b4.w));
-                        *reinterpret_cast<uint2*>(dst) = pk;
+                        const float v0 = act_fast<ACT>(t4.x + b4.x), v1 = act_fast<ACT>(t4.y + b4.y);
+                        const float v2 = act_fast<ACT>(t4.z + b4.z), v3 = act_fast<ACT>(t4.w + b4.w);
+                        if (lo_off != 0) {
+                            uint2 hi, lo;
+                            split_bf16x2(v0, v1, hi.x, lo.x);
+                            split_bf16x2(v2, v3, hi.y, lo.y);
+                            *reinterpret_cast<uint2*>(dst) = hi;
+                            *reinterpret_cast<uint2*>(dst + lo_off) = lo;
+                        } else {
+                            uint2 pk;
+                            pk.x = pack_bf16x2(v0, v1);
+                            pk.y = pack_bf16x2(v2, v3);
+                            *reinterpret_cast<uint2*>(dst) = pk;
+                        }
                     }
                 }
             }
@@ -467,11 +508,8 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     // ~300 cycles of barrier handshake PLUS ~140 cycles per 16 KB load it issues for every stage (the two add up: the
     // loop was producer bound at ~210 ns per k-block on the narrow conv tiles); two warps overlap each other's handshake.
     const int nseg = p.num_segs;
-    const int skb0 = p.seg_kblocks[0], skb1 = nseg > 1 ? p.seg_kblocks[1] : 0, skb2 = nseg > 2 ? p.seg_kblocks[2] : 0;
-    const void* map0 = &p.a_map[0];
-    const void* map1 = &p.a_map[1];
-    const void* map2 = &p.a_map[2];
     const void* mapb = &p.b_map;
+    const int b_kb_per_tap = p.b_kb_per_tap;               // k-blocks per tap of the packed weights
     const bool conv = p.in_mode == IN_CONV;
     int y0 = 0, img0 = 0;
     if (conv) conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, img0);
@@ -479,17 +517,16 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     const uint32_t b_atom = (uint32_t)(p.block_n * kBlockK * 2);
     const uint32_t kb_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2) + b_atom;
     const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
-    int sg = 0, k = 0, skb_cur = skb0;
+    int sg = 0, k = 0, skb_cur = p.seg_kblocks[0];
+    int koff = p.seg_b_kb0[0];                             // k-block of (sg, k) inside one tap of the packed weights
     int dx = -1;                                           // x-shift of the current taps (the weights are packed tap-major in (kh, kw) order)
-    const void* map_cur = map0;
+    const void* map_cur = &p.a_map[0];
     int turn = 0;
     if (conv && p.conv_reuse) {
         // stage = one haloed A box (channel block k of segment sg at x-shift dx, rows y0-1 .. y0+box_y) + the B atoms of
         // the three taps (dy = -1, 0, +1) of that dx and channel block
         const uint32_t a_bytes = (uint32_t)(p.a_halo_rows * kBlockK * 2);
-        const int kb_per_tap = skb0 + skb1 + skb2;
-        const int n_stage = 3 * kb_per_tap;
-        int koff = 0;                                      // k-block offset of (sg, k) inside one tap of the packed weights
+        const int n_stage = total_kb / 3;
         for (int it = 0; it < n_stage; ++it) {
             const bool mine = turn == prod_id;
             if (++turn == num_prod) turn = 0;
@@ -502,7 +539,7 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
 #pragma unroll
                     for (int t3 = 0; t3 < 3; ++t3)         // tap (dy = t3 - 1, dx): index t3 * 3 + (dx + 1) in (kh, kw) order
                         tma_load_2d_a(pipe_base + stage_off + a_bytes + (uint32_t)t3 * b_atom, mapb, fb,
-                                      ((t3 * 3 + dx + 1) * kb_per_tap + koff) * kBlockK, n0);
+                                      ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, n0);
                     if (ticks && it == 0) ticks[2] = globaltimer_ns();
                 }
                 __syncwarp();
@@ -510,9 +547,10 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
             ++koff;
             if (++k == skb_cur) {
                 k = 0;
-                if (++sg == nseg) { sg = 0; koff = 0; ++dx; }
-                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+                if (++sg == nseg) { sg = 0; ++dx; }
+                skb_cur = p.seg_kblocks[sg];
+                koff = p.seg_b_kb0[sg];
+                map_cur = &p.a_map[sg];
             }
             stage_off += (uint32_t)stage_bytes;
             if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
@@ -521,8 +559,7 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
     }
     // Per-k-block loads.  Conv k-blocks run in the SAME order as the conv_reuse path - dx, channel segment, channel block,
     // dy - so that a layer accumulates identically whichever path a launch takes (results do not depend on the batch size).
-    const int kb_per_tap = skb0 + skb1 + skb2;
-    int koff = 0, t3 = 0;
+    int t3 = 0;
     for (int kb = 0; kb < total_kb;) {
         const int nk = min(kgroup, total_kb - kb);
         const bool mine = turn == prod_id;
@@ -539,10 +576,10 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
                 const uint32_t b_dst = pipe_base + stage_off + b_base + (uint32_t)j * b_atom;
                 if (conv) {
                     tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, img0, y0 + t3 - 1);
-                    tma_load_2d_a(b_dst, mapb, fb, ((t3 * 3 + dx + 1) * kb_per_tap + koff) * kBlockK, n0);
+                    tma_load_2d_a(b_dst, mapb, fb, ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, n0);
                 } else {
                     tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
-                    tma_load_2d_a(b_dst, mapb, fb, kb * kBlockK, n0);
+                    tma_load_2d_a(b_dst, mapb, fb, koff * kBlockK, n0);
                 }
                 if (ticks && kb == 0) ticks[2] = globaltimer_ns();
             }
@@ -552,9 +589,10 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
             ++koff;
             if (++k == skb_cur) {
                 k = 0;
-                if (++sg == nseg) { sg = 0; koff = 0; ++dx; }
-                skb_cur = sg == 0 ? skb0 : (sg == 1 ? skb1 : skb2);
-                map_cur = sg == 0 ? map0 : (sg == 1 ? map1 : map2);
+                if (++sg == nseg) { sg = 0; ++dx; }
+                skb_cur = p.seg_kblocks[sg];
+                koff = p.seg_b_kb0[sg];
+                map_cur = &p.a_map[sg];
             }
         }
         stage_off += (uint32_t)stage_bytes;
@@ -841,119 +879,6 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Chain kernel: the 5 conv layers of a cc_transform / lrp_transform net (all members of a grouped launch) in ONE
-// cooperative launch.  Every CTA keeps its barriers / TMEM / role warps alive across layers; between layers the grid
-// meets at a sense-reversing barrier in global memory (the next layer's TMA loads read what other CTAs just stored, so
-// the barrier is followed by a generic->async proxy fence).  Replaces 5 launches + 5 prologues / pipeline drains of a
-// latency-bound dependency chain by 1 launch + 4 grid barriers.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int num_ctas) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int* gen_p = bar + 1;
-        const unsigned int gen = *gen_p;
-        __threadfence();                                        // this CTA's stores (cumulative over bar.sync) before arrival
-        if (atomicAdd(bar, 1u) == num_ctas - 1u) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);                             // release everybody
-        } else {
-            const long long t0 = clock64();
-            while (*gen_p == gen) {
-                if (clock64() - t0 > 4000000000LL) { printf("tmae: grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
-            }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    asm volatile("fence.proxy.async;\n" ::: "memory");          // generic-proxy stores of other CTAs -> this CTA's TMA loads
-}
-
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_chain_kernel(const GemmParams* __restrict__ params, const ChainDesc cd, int stages, int stage_bytes) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    constexpr int kStaging = 8 * 32 * kEpiPitch * 4;            // dedicated epilogue staging (36 KB, multiple of 1024)
-    uint8_t* pipe = smem + kStaging;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(pipe + (size_t)stages * stage_bytes);
-    uint64_t* empty_bar = full_bar + stages;
-    uint64_t* tfull_bar = empty_bar + stages;                    // accumulator ready   (MMA -> epilogue)
-    uint64_t* tempty_bar = tfull_bar + 1;                        // accumulator drained (epilogue -> MMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        mbar_init(tfull_bar, 1);
-        mbar_init(tempty_bar, 8);
-        fence_barrier_init();
-    }
-    if (warp == 1) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t pipe_base = smem_u32(pipe);
-    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
-    const uint32_t stage_base = smem_u32(smem);
-
-    // pipeline / accumulator bookkeeping persists across tiles and layers (each role tracks its own copy)
-    int stage = 0;
-    uint32_t phase = 0, stage_off = 0;
-    int tile_it = 0;                                             // accumulator uses so far (parity of tfull / tempty)
-
-    for (int l = 0; l < cd.num_layers; ++l) {
-        const int mt = cd.m_tiles[l], nt = cd.n_tiles[l];
-        const int total_tiles = mt * nt * cd.groups[l];
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
-            const int g = t / (mt * nt);
-            const int rem = t - g * mt * nt;
-            const GemmParams& p = params[cd.first[l] + g];
-            const int block_n = p.block_n;
-            const int m_tile = rem / nt, n0 = (rem % nt) * block_n;
-            int kb_per_tap = 0;
-            for (int sg = 0; sg < p.num_segs; ++sg) kb_per_tap += p.seg_kblocks[sg];
-            const int total_kb = kb_per_tap * p.num_taps;
-            const uint32_t acc_phase = (uint32_t)tile_it & 1u;
-            if (m_tile * kBlockM >= p.M || n0 >= p.N) {          // member smaller than the group's grid: keep parities in step
-                if (warp >= 2) { /* nothing to drain */ }
-                --tile_it;
-                continue;
-            }
-            if (warp == 0) {
-                // ===== TMA producer (warp-uniform) =====
-                produce_tile(p, m_tile, n0, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, stage, phase,
-                             stage_off, nullptr);
-            } else if (warp == 1) {
-                // ===== MMA issuer (warp-uniform) =====
-                mbar_wait(tempty_bar, acc_phase ^ 1u);             // previous tile's accumulator has been drained
-                tc_fence_after();
-                mma_tile(block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, tmem_base, smem_u32(tfull_bar),
-                         stage, phase, stage_off, nullptr, -1, -1);
-            } else {
-                // ===== epilogue warps =====
-                const EpiCtx e = load_epi(p);
-                const int kind = cd.kind[l];
-                if (kind == CHAIN_GELU_BF16_SAME)
-                    epilogue_tile<ACT_GELU, EPI_BF16_SAME>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
-                else if (kind == CHAIN_HALF_TANH_GENERIC)
-                    epilogue_tile<ACT_HALF_TANH, EPI_GENERIC>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
-                else
-                    epilogue_tile<ACT_NONE, EPI_GENERIC>(e, m_tile, n0, block_n, tmem_base, stage_base, warp, lane, tfull_bar, acc_phase, nullptr);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar);
-            }
-        }
-        if (l + 1 < cd.num_layers) grid_barrier(cd.bar, gridDim.x);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // CUDA-core checker: same parameter block, same epilogue, plain loads.  Bring-up / tests only.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -966,8 +891,6 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
     const RowCtx r = decode_row(e, m / kBlockM, m % kBlockM);
     if (!r.valid) return;
     const bool conv = p.in_mode == IN_CONV;
-    int kp_per_tap = 0;
-    for (int sg = 0; sg < p.num_segs; ++sg) kp_per_tap += p.seg_kblocks[sg] * kBlockK;
     for (int col = threadIdx.x * 8; col < p.N; col += blockDim.x * 8) {
         float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int tap = 0; tap < p.num_taps; ++tap) {
@@ -976,8 +899,8 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
                 const int yy = r.y + tap / 3 - 1, xx = r.x + tap % 3 - 1;
                 row = (yy >= 0 && yy < p.s && xx >= 0 && xx < p.s) ? (long long)r.n * p.K + yy * p.s + xx : -1;
             }
-            int kbase = tap * kp_per_tap;
             for (int sg = 0; sg < p.num_segs; ++sg) {
+                const int kbase = (tap * p.b_kb_per_tap + p.seg_b_kb0[sg]) * kBlockK;
                 if (row >= 0 && row < p.a_rows[sg]) {
                     const __nv_bfloat16* a = p.a_ptr[sg] + row * p.a_ld[sg];
                     for (int c = 0; c < p.a_cols[sg]; ++c) {
@@ -987,7 +910,6 @@ gemm_simt_kernel(const GemmParams* __restrict__ params) {
                             v[i] = fmaf(av, __bfloat162float(p.b_ptr[(long long)(col + i) * p.b_ld + kbase + c]), v[i]);
                     }
                 }
-                kbase += p.seg_kblocks[sg] * kBlockK;
             }
         }
         epilogue8(e, r, col, v);
@@ -1066,28 +988,6 @@ cudaError_t gemm_tc_configure() {
 bool gemm_use_persistent(int groups, int epi, int act, int tiles, bool share_sm) {
     static const bool off = getenv("TMAE_NO_PERSISTENT") != nullptr;
     return !off && !share_sm && groups == 1 && (epi == EPI_BF16_SAME || epi == EPI_BF16_TMA) && (act == ACT_NONE || act == ACT_GELU) && tiles > 2 * 148;
-}
-
-cudaError_t gemm_chain_configure() {
-    prefer_max_smem_carveout(gemm_tc_chain_kernel);
-    return cudaFuncSetAttribute(gemm_tc_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-}
-
-// One cooperative launch for a whole chain.  max_block_n = widest N tile of any layer (sizes the pipeline stages).
-cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream) {
-    const int stage_bytes = kAStageBytes + max_block_n * kBlockK * 2;
-    const int overhead = 1024 + 256 + 8 * 32 * kEpiPitch * 4;
-    int stages = (226 * 1024 - overhead) / stage_bytes;
-    if (stages > 8) stages = 8;
-    if (stages < 2) return cudaErrorInvalidValue;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid_ctas); cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = overhead + stages * stage_bytes; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_tc_chain_kernel, d_params, cd, stages, stage_bytes);
 }
 
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).

@@ -21,8 +21,6 @@ struct IoBlock {
 cudaError_t gemm_tc_configure();
 int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes, int* kgroup);
 int gemm_epi_kind(const GemmParams& p);
-cudaError_t gemm_chain_configure();
-cudaError_t gemm_chain_launch(const GemmParams* d_params, const ChainDesc& cd, int grid_ctas, int max_block_n, cudaStream_t stream);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream,
                         const GemmParams* d_next = nullptr, int next_groups = 0, int conv_reuse_stage_bytes = 0);
@@ -36,19 +34,24 @@ cudaError_t launch_mask_select(const float* scores, int N, int L, int K, int sof
 cudaError_t attention_configure(int T);
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int T, int H, int C, float scale,
                              cudaStream_t st);
+// precise mode: fp32 softmax attention on CUDA cores over split-bf16 (hi + lo plane) q, k, v; writes both planes
+cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,
+                                 int T, int H, int C, float scale, cudaStream_t st);
 
 // elementwise.cu
 cudaError_t launch_gather_patches(const float* imgs, const int64_t* ids_keep, __nv_bfloat16* patches, float* x,
                                   const float* cls_token, const float* pos_embed, int N, int S, int grid_w, int K,
-                                  int T, int C, int in_chans, int patch, cudaStream_t st, const IoBlock* io = nullptr);
+                                  int T, int C, int in_chans, int patch, long long lo_off, cudaStream_t st,
+                                  const IoBlock* io = nullptr);
 cudaError_t launch_layernorm(const float* x, const float* gamma, const float* beta, __nv_bfloat16* out, float* out_f32,
-                             int rows, int C, int T, int drop_cls, float eps, cudaStream_t st, const IoBlock* io = nullptr);
+                             int rows, int C, int T, int drop_cls, float eps, long long lo_off, cudaStream_t st,
+                             const IoBlock* io = nullptr);
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
-                              float* zhat, __nv_bfloat16* zhat_bf, int s4, double* rate_acc, int rows_per_image,
+                              float* zhat, __nv_bfloat16* zhat_bf, long long lo_off, int s4, double* rate_acc, int rows_per_image,
                               cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
-                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, int ld_bf,
-                                  int s, double* rate_acc, cudaStream_t st, const IoBlock* io = nullptr);
+                                  int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, long long lo_off,
+                                  int ld_bf, int s, double* rate_acc, cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* sigma, long long n, float* lik,
                                  int32_t* sym, float* yhat, cudaStream_t st);
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,
@@ -58,9 +61,9 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
                                 const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
                                 cudaStream_t st);
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
-                                  const int* segc, int shuffle, cudaStream_t st);
+                                  const int* segc, int shuffle, int planes, cudaStream_t st);
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st);
 cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st);
-cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, cudaStream_t st);
+cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st);
 
 }  // namespace tmae

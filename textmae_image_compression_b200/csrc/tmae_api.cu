@@ -39,9 +39,18 @@ struct Layer {                      // one prepacked linear / conv
     __nv_bfloat16* w = nullptr;     // [Cout, Kp]
     float* bias = nullptr;          // [Cout] (permuted for PixelShuffle layers)
     int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
+    int planes = 1;                 // 2 = precise layer: every tap holds the hi planes of its segments, then the lo planes
+    int kb_tap = 0;                 // k-blocks of one plane of one tap
 };
 
-enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_CHAIN, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE };
+// bf16 activation buffer of the workspace; `lo` = element offset of its second (lo) plane when the layer that reads it
+// is precise (split-bf16), else 0
+struct Bf {
+    __nv_bfloat16* p = nullptr;
+    long long lo = 0;
+};
+
+enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE };
 enum Family { FAM_GEMM = 0, FAM_ATTN, FAM_LN, FAM_MASK, FAM_GATHER, FAM_ENTROPY, FAM_MISC, FAM_COUNT };
 const char* kFamilyNames[FAM_COUNT] = {"gemm_tc", "attention", "layernorm", "mask_select", "gather_patches",
                                        "entropy_elementwise", "misc"};
@@ -54,9 +63,7 @@ struct Step {
     int next_index = -1, next_groups = 0;      // parameter blocks of the next GEMM step (weight prefetch target)
     int conv_reuse_stage_bytes = 0;            // > 0: 3x3 conv launch with haloed-box A reuse, stage size in bytes
     double flops = 0, bytes = 0;
-    // fused chain of layers (ST_CHAIN)
-    ChainDesc chain;
-    int chain_grid = 0, chain_max_bn = 0;
+    int mma_terms = 1;                         // 3 for precise (split-bf16) GEMM steps
     // LN
     const float* ln_gamma = nullptr;
     const float* ln_beta = nullptr;
@@ -84,24 +91,22 @@ struct Workspace {
     std::vector<void*> allocs;
     // encoder
     int64_t* ids_keep = nullptr;
-    __nv_bfloat16 *patches = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *h1 = nullptr, *enc = nullptr;
+    Bf patches, xn, qkv, attn, h1, enc;
     float* x = nullptr;
     // g_a
-    __nv_bfloat16 *ga1 = nullptr, *ga2 = nullptr, *ga3 = nullptr, *y_bf = nullptr;
+    Bf ga1, ga2, ga3, y_bf;
     float *y = nullptr, *z = nullptr, *mu = nullptr, *sigma = nullptr, *yhat = nullptr;
     // h_a / h_s
-    __nv_bfloat16 *ha1 = nullptr, *ha2 = nullptr, *ha3 = nullptr, *ha4 = nullptr, *zhat_bf = nullptr;
-    __nv_bfloat16 *hs1[2] = {nullptr, nullptr}, *hs2[2] = {nullptr, nullptr}, *hs3[2] = {nullptr, nullptr},
-                  *hs4[2] = {nullptr, nullptr}, *lat[2] = {nullptr, nullptr};     // 0 = means, 1 = scales
-    __nv_bfloat16* yhat_bf = nullptr;
-    __nv_bfloat16* t[18][4] = {{nullptr}};     // [slice-group member j (0..5) * 3 + net (mean, scale, lrp)][layer]
+    Bf ha1, ha2, ha3, ha4, zhat_bf;
+    Bf hs1[2], hs2[2], hs3[2], hs4[2], lat[2];     // 0 = means, 1 = scales
+    Bf yhat_bf;
+    Bf t[18][4];                                   // [slice-group member j (0..5) * 3 + net (mean, scale, lrp)][layer]
     double* rate_acc = nullptr;
     float* bpp = nullptr;
     double* rate_sums = nullptr;
     // host-buffer entry staging
     float *st_imgs = nullptr, *st_scores = nullptr;
     IoBlock* io = nullptr;           // per-call pointers for graph replays
-    unsigned int* grid_bar = nullptr; // [2] counter + generation of the chain kernels' grid barrier
 };
 
 }  // namespace
@@ -121,9 +126,8 @@ struct tmae_handle {
     PFN_encodeTiled encode = nullptr;
     std::vector<void*> weight_allocs;
     bool use_graph = true;           // TMAE_NO_GRAPH=1 disables CUDA-graph replay
-    bool use_chain = false;          // TMAE_CHAIN=1: fuse each serial cc/lrp net (5 conv layers) into one cooperative launch.
-                                     // Measured on B200: per-launch roofline 0.29 -> 0.32, but end-to-end it loses to the
-                                     // PDL + CUDA-graph path (22.5k vs 23.4k img/s, and it blocks cross-stream overlap), so off.
+    bool precise_rate = false;       // TMAE_FLAG_PRECISE_RATE / _ALL: split-bf16 layers after the encoder
+    bool precise_enc = false;        // TMAE_FLAG_PRECISE_ALL: the encoder as well
     cudaStream_t cap_stream = nullptr;
     // profiling
     bool profiling = false;
@@ -271,7 +275,7 @@ int need_raw(tmae_handle* h, const std::string& name, size_t numel, const RawTen
 
 // Prepack one conv / linear: weight [Cout, Cin, taps] fp32 -> bf16 [Cout, Kp]; bias fp32 (permuted if shuffle).
 int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname, int Cout, int Cin, int taps, int nseg,
-               const int* segc, int shuffle) {
+               const int* segc, int shuffle, bool precise) {
     const RawTensor *w = nullptr, *b = nullptr;
     int rc = need_raw(h, wname + ".weight", (size_t)Cout * Cin * taps, &w);
     if (rc) return rc;
@@ -282,12 +286,14 @@ int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname,
     int kp_tap = 0, csum = 0;
     for (int i = 0; i < nseg; ++i) { L.segc[i] = segc[i]; kp_tap += pad64(segc[i]); csum += segc[i]; }
     if (csum != Cin) return fail(h, TMAE_EINVAL, "layer %s: segments sum %d != Cin %d", key.c_str(), csum, Cin);
-    L.Kp = kp_tap * taps;
+    L.planes = precise ? 2 : 1;
+    L.kb_tap = kp_tap / 64;
+    L.Kp = kp_tap * taps * L.planes;
     rc = dev_alloc(h, h->weight_allocs, &L.w, (size_t)Cout * L.Kp);
     if (rc) return rc;
     rc = dev_alloc(h, h->weight_allocs, &L.bias, (size_t)Cout);
     if (rc) return rc;
-    CUDA_TRY(h, launch_prepack_weight(w->ptr, L.w, Cout, Cin, taps, nseg, L.segc, shuffle, 0));
+    CUDA_TRY(h, launch_prepack_weight(w->ptr, L.w, Cout, Cin, taps, nseg, L.segc, shuffle, L.planes, 0));
     if (shuffle) CUDA_TRY(h, launch_permute_bias_shuffle(b->ptr, L.bias, Cout, 0));
     else CUDA_TRY(h, cudaMemcpyAsync(L.bias, b->ptr, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, 0));
     h->layers[key] = L;
@@ -413,6 +419,7 @@ struct SegSrc {
     const __nv_bfloat16* ptr;   // first column of the segment
     int cols;                   // channels in the segment
     int ld;                     // row pitch (elements)
+    long long lo;               // element offset of the lo plane (precise layers), else 0
 };
 
 struct GemmDesc {
@@ -429,8 +436,8 @@ struct GemmDesc {
     int act = ACT_NONE;
     const float* resid = nullptr; int resid_ld = 0; int resid_map = MAP_SAME;
     const int64_t* gather_ids = nullptr;
-    OutSpec out0 = {nullptr, 0, OUT_NONE, MAP_SAME};
-    OutSpec out1 = {nullptr, 0, OUT_NONE, MAP_SAME};
+    OutSpec out0 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
+    OutSpec out1 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
     double flops = 0;
 };
 
@@ -446,18 +453,31 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
         if (d.M != cg.m_tiles * kBlockM || d.a_rows != (long long)d.n_img * d.side * d.side)
             return fail(h, TMAE_EINVAL, "conv descriptor rows inconsistent with its geometry");
     }
-    p->num_segs = d.nseg;
+    // K segments: one per concatenated source, or three per source for a precise layer: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
+    const bool precise = L.planes == 2;
+    p->num_segs = 0;
+    p->b_kb_per_tap = L.kb_tap * L.planes;
+    p->mma_terms = precise ? 3 : 1;
+    int kb0 = 0;
     for (int i = 0; i < d.nseg; ++i) {
         if (d.seg[i].cols != L.segc[i]) return fail(h, TMAE_EINVAL, "segment %d width %d != packed %d", i, d.seg[i].cols, L.segc[i]);
-        p->a_ptr[i] = d.seg[i].ptr;
-        p->a_ld[i] = d.seg[i].ld;
-        p->a_cols[i] = d.seg[i].cols;
-        p->a_rows[i] = d.a_rows;
-        p->seg_kblocks[i] = pad64(d.seg[i].cols) / 64;
-        int rc = conv ? make_map4d(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_n,
-                                   cg.box_y + (d.conv_reuse ? 2 : 0))
-                      : make_map(h, &p->a_map[i], d.seg[i].ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
-        if (rc) return rc;
+        if (precise && d.seg[i].lo == 0) return fail(h, TMAE_EINVAL, "precise layer: segment %d has no lo plane", i);
+        const int skb = pad64(d.seg[i].cols) / 64;
+        for (int term = 0; term < (precise ? 3 : 1); ++term) {
+            const int j = p->num_segs++;
+            const __nv_bfloat16* ptr = d.seg[i].ptr + (term == 1 ? d.seg[i].lo : 0);
+            p->a_ptr[j] = ptr;
+            p->a_ld[j] = d.seg[i].ld;
+            p->a_cols[j] = d.seg[i].cols;
+            p->a_rows[j] = d.a_rows;
+            p->seg_kblocks[j] = skb;
+            p->seg_b_kb0[j] = kb0 + (term == 2 ? L.kb_tap : 0);
+            int rc = conv ? make_map4d(h, &p->a_map[j], ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_n,
+                                       cg.box_y + (d.conv_reuse ? 2 : 0))
+                          : make_map(h, &p->a_map[j], ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
+            if (rc) return rc;
+        }
+        kb0 += skb;
     }
     p->b_ptr = L.w;
     p->b_ld = L.Kp;
@@ -478,7 +498,8 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->in_mode = d.in_mode;
     // TMA-store epilogue: one bf16 output at the accumulator's own rows, and those rows are 128 consecutive output rows
     {
-        const bool one_bf16 = d.out0.dtype == OUT_BF16 && d.out0.map == MAP_SAME && d.out1.dtype == OUT_NONE && d.resid == nullptr;
+        const bool one_bf16 = d.out0.dtype == OUT_BF16 && d.out0.map == MAP_SAME && d.out1.dtype == OUT_NONE && d.resid == nullptr &&
+                              d.out0.lo_off == 0;        // two-plane outputs take the register store phase
         const bool rows_ok = true;        // conv tiles are stored as the 4-D box they are (any geometry)
         const bool align_ok = (reinterpret_cast<uintptr_t>(d.out0.ptr) & 15) == 0 && ((size_t)d.out0.ld * 2) % 16 == 0;
         p->tma_store_ok = 0;
@@ -522,49 +543,55 @@ int ensure_workspace(tmae_handle* h, int N) {
     int ci[5], co[5], aux[5];
 #define WS_ALLOC(field, count)                                                        \
     do { int _rc = dev_alloc(h, w.allocs, &(field), (count), &tot); if (_rc) return _rc; } while (0)
+    // bf16 activation: one plane, or two (hi, lo) when the layers that read it run split-bf16 (precise)
+#define WS_ALLOC_BF(field, count, two)                                                \
+    do { const size_t _c = ((size_t)(count) + 63) / 64 * 64;                          \
+         int _rc = dev_alloc(h, w.allocs, &(field).p, _c * ((two) ? 2 : 1), &tot); if (_rc) return _rc; \
+         (field).lo = (two) ? (long long)_c : 0; } while (0)
+    const bool pe = h->precise_enc, pr = h->precise_rate;
     WS_ALLOC(w.ids_keep, rk);
-    WS_ALLOC(w.patches, rk * h->patch_dim);
+    WS_ALLOC_BF(w.patches, rk * h->patch_dim, pe);
     WS_ALLOC(w.x, rt * C);
-    WS_ALLOC(w.xn, rt * C);
-    WS_ALLOC(w.qkv, rt * 3 * C);
-    WS_ALLOC(w.attn, rt * C);
-    WS_ALLOC(w.h1, rt * h->mlp);
-    WS_ALLOC(w.enc, rk * C);
-    WS_ALLOC(w.ga1, rk * h->ga_ch[1]);
-    WS_ALLOC(w.ga2, rk * h->ga_ch[2]);
-    WS_ALLOC(w.ga3, rk * h->ga_ch[3]);
-    WS_ALLOC(w.y_bf, rp * Cy);
+    WS_ALLOC_BF(w.xn, rt * C, pe);
+    WS_ALLOC_BF(w.qkv, rt * 3 * C, pe);
+    WS_ALLOC_BF(w.attn, rt * C, pe);
+    WS_ALLOC_BF(w.h1, rt * h->mlp, pe);
+    WS_ALLOC_BF(w.enc, rk * C, pr);
+    WS_ALLOC_BF(w.ga1, rk * h->ga_ch[1], pr);
+    WS_ALLOC_BF(w.ga2, rk * h->ga_ch[2], pr);
+    WS_ALLOC_BF(w.ga3, rk * h->ga_ch[3], pr);
+    WS_ALLOC_BF(w.y_bf, rp * Cy, pr);
     WS_ALLOC(w.y, rk * Cy);
     WS_ALLOC(w.z, rz * Cz);
     WS_ALLOC(w.mu, rk * Cy);
     WS_ALLOC(w.sigma, rk * Cy);
     WS_ALLOC(w.yhat, rk * Cy);
     ha_layers(h, ci, co, aux);
-    WS_ALLOC(w.ha1, rp * co[0]);
-    WS_ALLOC(w.ha2, rp * co[1]);
-    WS_ALLOC(w.ha3, rp2 * co[2]);
-    WS_ALLOC(w.ha4, rp2 * co[3]);
-    WS_ALLOC(w.zhat_bf, rp4 * Cz);
+    WS_ALLOC_BF(w.ha1, rp * co[0], pr);
+    WS_ALLOC_BF(w.ha2, rp * co[1], pr);
+    WS_ALLOC_BF(w.ha3, rp2 * co[2], pr);
+    WS_ALLOC_BF(w.ha4, rp2 * co[3], pr);
+    WS_ALLOC_BF(w.zhat_bf, rp4 * Cz, pr);
     hs_layers(h, ci, co, aux);
     for (int net = 0; net < 2; ++net) {
-        WS_ALLOC(w.hs1[net], rp4 * co[0]);
-        WS_ALLOC(w.hs2[net], rp2 * co[1]);
-        WS_ALLOC(w.hs3[net], rp2 * co[2]);
-        WS_ALLOC(w.hs4[net], rp * co[3]);
-        WS_ALLOC(w.lat[net], rp * Cy);
+        WS_ALLOC_BF(w.hs1[net], rp4 * co[0], pr);
+        WS_ALLOC_BF(w.hs2[net], rp2 * co[1], pr);
+        WS_ALLOC_BF(w.hs3[net], rp2 * co[2], pr);
+        WS_ALLOC_BF(w.hs4[net], rp * co[3], pr);
+        WS_ALLOC_BF(w.lat[net], rp * Cy, pr);
     }
-    WS_ALLOC(w.yhat_bf, rp * Cy);
+    WS_ALLOC_BF(w.yhat_bf, rp * Cy, pr);
     int ch[6];
     cc_channels(h, ch, 0, false);
     for (int net = 0; net < 18; ++net)
-        for (int l = 0; l < 4; ++l) WS_ALLOC(w.t[net][l], rp * ch[l + 1]);
+        for (int l = 0; l < 4; ++l) WS_ALLOC_BF(w.t[net][l], rp * ch[l + 1], pr);
     WS_ALLOC(w.rate_acc, (size_t)N);
     WS_ALLOC(w.bpp, (size_t)N);
     WS_ALLOC(w.rate_sums, (size_t)2);
     WS_ALLOC(w.st_imgs, (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size);
     WS_ALLOC(w.st_scores, (size_t)N * h->L);
     WS_ALLOC(w.io, (size_t)1);
-    WS_ALLOC(w.grid_bar, (size_t)2);
+#undef WS_ALLOC_BF
 #undef WS_ALLOC
     w.cap_N = N;
     w.bytes = tot;
@@ -580,6 +607,8 @@ size_t workspace_bytes_estimate(const tmae_handle* h, int N) {
     b += rp * (384 + 336) * 2 + rp2 * (288 + 240) * 2 + rp4 * h->Cz * 2;
     b += 2 * (rp4 * 240 + rp2 * (288 + 336) + rp * (384 + 384)) * 2 + rp * h->Cy * 2;
     b += 18 * rp * (224 + 176 + 128 + 80) * 2;
+    if (h->precise_rate) b += b / 2;            // second bf16 plane of the activations (upper bound)
+    if (h->precise_enc) b += b / 3;
     b += (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size * 4 + (size_t)N * h->L * 4;
     return b;
 }
@@ -592,7 +621,7 @@ double conv_flops(long long out_positions, int cin, int cout, int taps) {
 // conv_reuse decision for one launch: the geometry must allow it and at least two stages (one haloed A box + three B
 // atoms each) must fit the launch's shared-memory budget.  Returns the stage size in bytes, 0 = per-tap loads.
 int conv_reuse_stage_bytes(const tmae_handle* h, const GemmDesc& d, int bn, int n_tiles, int groups) {
-    if (d.in_mode != IN_CONV || h->use_chain) return 0;
+    if (d.in_mode != IN_CONV) return 0;
     ConvGeom cg;
     if (!conv_geom(d.side, d.n_img, &cg) || !cg.reuse_ok) return 0;
     // a tap's MMA always reads 128 rows from its dy offset: with a partial tile the rows past the A box must still lie
@@ -656,6 +685,7 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         else if (ek != st.epi) st.epi = ((ek == 1 || ek == 3) && (st.epi == 1 || st.epi == 3)) ? 1 : 0;   // mixed group -> common denominator
         pl.host_params.push_back(p);
         st.flops += descs[g].flops;
+        st.mma_terms = p.mma_terms;
     }
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
     static const bool plan_debug = getenv("TMAE_PLAN_DEBUG") != nullptr;
@@ -667,64 +697,10 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     return TMAE_OK;
 }
 
-// layers[l] = the (grouped) members of layer l; all layers share the pixel grid.  One cooperative launch.
-int add_chain(tmae_handle* h, Plan& pl, const std::vector<std::vector<GemmDesc>>& layers, const char* tag) {
-    Step st;
-    st.kind = ST_CHAIN;
-    st.family = FAM_GEMM;
-    st.tag = tag;
-    memset(&st.chain, 0, sizeof(st.chain));
-    st.chain.num_layers = (int)layers.size();
-    if (st.chain.num_layers > kMaxChainLayers) return fail(h, TMAE_EINVAL, "chain too long");
-    int grid = 1, max_bn = 32;
-    for (size_t l = 0; l < layers.size(); ++l) {
-        const std::vector<GemmDesc>& mem = layers[l];
-        const int groups = (int)mem.size();
-        int max_M = 0, max_N = 0;
-        for (const GemmDesc& d : mem) { if (d.M > max_M) max_M = d.M; if (d.layer->Cout > max_N) max_N = d.layer->Cout; }
-        const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
-        // column tiles: as many as keep the layer within one wave of 148 CTAs (each >= 32 wide), at least ceil(N / 256)
-        int nt = 148 / (m_tiles * groups);
-        if (nt < 1) nt = 1;
-        while (nt > 1 && round16((max_N + nt - 1) / nt) < 32) --nt;
-        if (nt < (max_N + 255) / 256) nt = (max_N + 255) / 256;
-        const int bn = round16((max_N + nt - 1) / nt);
-        const int n_tiles = (max_N + bn - 1) / bn;
-        st.chain.first[l] = (int)pl.host_params.size();
-        st.chain.groups[l] = groups;
-        st.chain.m_tiles[l] = m_tiles;
-        st.chain.n_tiles[l] = n_tiles;
-        int kind = -1;
-        for (int g = 0; g < groups; ++g) {
-            GemmParams p;
-            int rc = fill_params(h, mem[g], groups, &p, bn);
-            if (rc) return rc;
-            const int ek = gemm_epi_kind(p);
-            int k = -1;
-            if (p.act == ACT_GELU && (ek == 1 || ek == 3) /*EPI_BF16_SAME / EPI_BF16_TMA*/) k = CHAIN_GELU_BF16_SAME;
-            else if (p.act == ACT_NONE) k = CHAIN_NONE_GENERIC;
-            else if (p.act == ACT_HALF_TANH) k = CHAIN_HALF_TANH_GENERIC;
-            if (k < 0 || (kind >= 0 && k != kind)) return fail(h, TMAE_EINVAL, "chain layer %zu: unsupported epilogue mix", l);
-            kind = k;
-            pl.host_params.push_back(p);
-            st.flops += mem[g].flops;
-        }
-        st.chain.kind[l] = kind;
-        const int tiles = m_tiles * n_tiles * groups;
-        if (tiles > grid) grid = tiles;
-        if (bn > max_bn) max_bn = bn;
-    }
-    st.chain.bar = h->ws.grid_bar;
-    st.chain_grid = grid < 148 ? grid : 148;
-    st.chain_max_bn = max_bn;
-    st.param_index = st.chain.first[0];
-    st.groups = 1; st.max_M = 0; st.max_N = 0; st.block_n = max_bn;
-    pl.steps.push_back(st);
-    return TMAE_OK;
-}
-
-SegSrc seg(const __nv_bfloat16* p, int cols, int ld) { SegSrc s; s.ptr = p; s.cols = cols; s.ld = ld; return s; }
-OutSpec outspec(void* p, int ld, int dtype, int map) { OutSpec o; o.ptr = p; o.ld = ld; o.dtype = dtype; o.map = map; return o; }
+SegSrc seg(const __nv_bfloat16* p, int cols, int ld, long long lo = 0) { SegSrc s; s.ptr = p; s.cols = cols; s.ld = ld; s.lo = lo; return s; }
+SegSrc seg(const Bf& b, int cols, int ld, int col0 = 0) { return seg(b.p + col0, cols, ld, b.lo); }
+OutSpec outspec(void* p, int ld, int dtype, int map, long long lo = 0) { OutSpec o; o.ptr = p; o.ld = ld; o.dtype = dtype; o.map = map; o.lo_off = lo; return o; }
+OutSpec outspec(const Bf& b, int ld, int map, int col0 = 0) { return outspec(b.p + col0, ld, OUT_BF16, map, b.lo); }
 
 const Layer* get_layer(tmae_handle* h, const std::string& key) {
     auto it = h->layers.find(key);
@@ -763,7 +739,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         d.a_rows = rk; d.M = (int)rk; d.in_mode = IN_COMPACT; d.side = s;
         d.resid = h->vecs["encoder_pos_embed"]; d.resid_ld = C; d.resid_map = MAP_GATHER1; d.gather_ids = w.ids_keep;
         d.out0 = outspec(w.x, C, OUT_F32, MAP_TO_TOKEN);
-        d.flops = 2.0 * (double)N * h->L * h->patch_dim * C;       // reference embeds all L patches
+        d.flops = 2.0 * (double)rk * h->patch_dim * C;             // executed: the K kept patches (the reference embeds all L: bench adds that figure)
         rc = add_gemm_group(h, pl, &d, 1, "patch_embed");
         if (rc) return rc;
     }
@@ -774,7 +750,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         GemmDesc d;
         d.layer = get_layer(h, pre + ".attn.qkv");
         d.seg[0] = seg(w.xn, C, C); d.a_rows = rt; d.M = (int)rt;
-        d.out0 = outspec(w.qkv, 3 * C, OUT_BF16, MAP_SAME);
+        d.out0 = outspec(w.qkv, 3 * C, MAP_SAME);
         d.flops = 2.0 * rt * C * 3.0 * C;
         snprintf(tag, sizeof(tag), "blk%d.qkv", i);
         rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
@@ -793,7 +769,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         GemmDesc f1;
         f1.layer = get_layer(h, pre + ".mlp.fc1");
         f1.seg[0] = seg(w.xn, C, C); f1.a_rows = rt; f1.M = (int)rt; f1.act = ACT_GELU;
-        f1.out0 = outspec(w.h1, h->mlp, OUT_BF16, MAP_SAME);
+        f1.out0 = outspec(w.h1, h->mlp, MAP_SAME);
         f1.flops = 2.0 * rt * C * (double)h->mlp;
         snprintf(tag, sizeof(tag), "blk%d.fc1", i);
         rc = add_gemm_group(h, pl, &f1, 1, tag); if (rc) return rc;
@@ -812,15 +788,15 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     }
     pl.encoder_end_step = (int)pl.steps.size();
     {   // g_a: four 1x1 convs == per-token linears (MCM.py:77-93, 735)
-        const __nv_bfloat16* srcs[4] = {w.enc, w.ga1, w.ga2, w.ga3};
-        __nv_bfloat16* dsts[3] = {w.ga1, w.ga2, w.ga3};
+        const Bf srcs[4] = {w.enc, w.ga1, w.ga2, w.ga3};
+        const Bf dsts[3] = {w.ga1, w.ga2, w.ga3};
         for (int l = 0; l < 4; ++l) {
             GemmDesc d;
             d.layer = get_layer(h, "g_a." + std::to_string(2 * l));
             d.seg[0] = seg(srcs[l], h->ga_ch[l], h->ga_ch[l]); d.a_rows = rk; d.M = (int)rk;
             d.in_mode = IN_COMPACT; d.side = s;
-            if (l < 3) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], h->ga_ch[l + 1], OUT_BF16, MAP_SAME); }
-            else { d.out0 = outspec(w.y, Cy, OUT_F32, MAP_SAME); d.out1 = outspec(w.y_bf, Cy, OUT_BF16, MAP_SAME); }
+            if (l < 3) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], h->ga_ch[l + 1], MAP_SAME); }
+            else { d.out0 = outspec(w.y, Cy, OUT_F32, MAP_SAME); d.out1 = outspec(w.y_bf, Cy, MAP_SAME); }
             d.flops = 2.0 * rk * h->ga_ch[l] * (double)h->ga_ch[l + 1];
             snprintf(tag, sizeof(tag), "g_a.%d", 2 * l);
             rc = add_gemm_group(h, pl, &d, 1, tag); if (rc) return rc;
@@ -830,15 +806,15 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     {   // h_a (MCM.py:115-129, 739)
         int ci[5], co[5], st[5];
         ha_layers(h, ci, co, st);
-        const __nv_bfloat16* srcs[5] = {w.y_bf, w.ha1, w.ha2, w.ha3, w.ha4};
-        __nv_bfloat16* dsts[4] = {w.ha1, w.ha2, w.ha3, w.ha4};
+        const Bf srcs[5] = {w.y_bf, w.ha1, w.ha2, w.ha3, w.ha4};
+        const Bf dsts[4] = {w.ha1, w.ha2, w.ha3, w.ha4};
         const int sides[5] = {s, s, s, h->s2, h->s2};
         for (int l = 0; l < 5; ++l) {
             GemmDesc d;
             d.layer = get_layer(h, "h_a." + std::to_string(2 * l));
             d.seg[0] = seg(srcs[l], ci[l], ci[l]);
             conv_in(d, sides[l]);
-            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], co[l], OUT_BF16, st[l] == 2 ? MAP_S2 : MAP_SAME); }
+            if (l < 4) { d.act = ACT_GELU; d.out0 = outspec(dsts[l], co[l], st[l] == 2 ? MAP_S2 : MAP_SAME); }
             else d.out0 = outspec(w.z, Cz, OUT_F32, st[l] == 2 ? MAP_S2 : MAP_SAME);
             const long long outpos = (long long)N * (sides[l] / st[l]) * (sides[l] / st[l]);
             d.flops = conv_flops(outpos, ci[l], co[l], 9);
@@ -855,13 +831,13 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         for (int l = 0; l < 5; ++l) {
             GemmDesc d[2];
             for (int net = 0; net < 2; ++net) {
-                const __nv_bfloat16* srcs[5] = {w.zhat_bf, w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net]};
-                __nv_bfloat16* dsts[5] = {w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net], w.lat[net]};
+                const Bf srcs[5] = {w.zhat_bf, w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net]};
+                const Bf dsts[5] = {w.hs1[net], w.hs2[net], w.hs3[net], w.hs4[net], w.lat[net]};
                 d[net].layer = get_layer(h, std::string(nets[net]) + "." + std::to_string(2 * l));
                 d[net].seg[0] = seg(srcs[l], ci[l], ci[l]);
                 conv_in(d[net], sides[l]);
                 d[net].act = l < 4 ? ACT_GELU : ACT_NONE;
-                d[net].out0 = outspec(dsts[l], co[l], OUT_BF16, up[l] == 2 ? MAP_SHUF : MAP_SAME);
+                d[net].out0 = outspec(dsts[l], co[l], up[l] == 2 ? MAP_SHUF : MAP_SAME);
                 d[net].flops = conv_flops((long long)N * sides[l] * sides[l], ci[l], co[l] * up[l] * up[l], 9);
             }
             snprintf(tag, sizeof(tag), "h_s.%d", 2 * l);
@@ -877,8 +853,6 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
         const int sup = i0 < half_sl ? i0 : half_sl;
         int ch[6];
         cc_channels(h, ch, i0, false);
-        const bool fuse = h->use_chain && cnt == 1 && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT);
-        std::vector<std::vector<GemmDesc>> chain_layers;
         for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i] of every member, grouped
             std::vector<GemmDesc> d((size_t)cnt * 2);
             for (int j = 0; j < cnt; ++j)
@@ -895,20 +869,17 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                         g.seg[0] = seg(w.t[j * 3 + net][l - 1], ch[l], ch[l]);
                     }
                     conv_in(g, s);
-                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + net][l], ch[l + 1], OUT_BF16, MAP_SAME); }
+                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + net][l], ch[l + 1], MAP_SAME); }
                     else g.out0 = outspec((net == 0 ? w.mu : w.sigma) + i * h->sc, Cy, OUT_F32, MAP_SAME);
                     g.flops = conv_flops(rk, ch[l], ch[l + 1], 9);
                 }
             snprintf(tag, sizeof(tag), "cc.%d.%d", i0, 2 * l);
-            if (fuse) chain_layers.push_back(d);
-            else { rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc; }
+            rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc;
         }
-        if (fuse) { snprintf(tag, sizeof(tag), "cc.%d.chain", i0); rc = add_chain(h, pl, chain_layers, tag); if (rc) return rc; }
         { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i0; g.gc_slices = cnt; g.tag = "gaussian." + std::to_string(i0); pl.steps.push_back(g); }
         if (!(skip_dead && i0 >= half_sl)) {
             int lch[6];
             cc_channels(h, lch, i0, true);
-            chain_layers.clear();
             for (int l = 0; l < 5; ++l) {    // lrp_transform[i] (MCM.py:780-783)
                 std::vector<GemmDesc> d((size_t)cnt);
                 for (int j = 0; j < cnt; ++j) {
@@ -918,25 +889,23 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                     if (l == 0) {
                         g.seg[0] = seg(w.lat[0], Cy, Cy);
                         if (i < half_sl) { g.seg[1] = seg(w.yhat_bf, h->sc * (i + 1), Cy); g.nseg = 2; }
-                        else { g.seg[1] = seg(w.yhat_bf, h->sc * sup, Cy); g.seg[2] = seg(w.yhat_bf + i * h->sc, h->sc, Cy); g.nseg = 3; }
+                        else { g.seg[1] = seg(w.yhat_bf, h->sc * sup, Cy); g.seg[2] = seg(w.yhat_bf, h->sc, Cy, i * h->sc); g.nseg = 3; }
                     } else {
                         g.seg[0] = seg(w.t[j * 3 + 2][l - 1], lch[l], lch[l]);
                     }
                     conv_in(g, s);
-                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + 2][l], lch[l + 1], OUT_BF16, MAP_SAME); }
+                    if (l < 4) { g.act = ACT_GELU; g.out0 = outspec(w.t[j * 3 + 2][l], lch[l + 1], MAP_SAME); }
                     else {
                         g.act = ACT_HALF_TANH;
                         g.resid = w.yhat + i * h->sc; g.resid_ld = Cy; g.resid_map = MAP_SAME;
                         g.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_SAME);
-                        g.out1 = outspec(w.yhat_bf + i * h->sc, Cy, OUT_BF16, MAP_SAME);
+                        g.out1 = outspec(w.yhat_bf, Cy, MAP_SAME, i * h->sc);
                     }
                     g.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
                 }
                 snprintf(tag, sizeof(tag), "lrp.%d.%d", i0, 2 * l);
-                if (fuse) chain_layers.push_back(d);
-                else { rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc; }
+                rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc;
             }
-            if (fuse) { snprintf(tag, sizeof(tag), "lrp.%d.chain", i0); rc = add_chain(h, pl, chain_layers, tag); if (rc) return rc; }
         }
         i0 += cnt;
     }
@@ -1003,8 +972,8 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
     h->prof_flops[h->prof_used] = st.flops;
     h->prof_bytes[h->prof_used] = st.bytes;
     h->prof_tag[h->prof_used] = st.tag;
-    h->prof_ctas[h->prof_used] = st.kind == ST_CHAIN ? st.chain_grid : st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
-    h->prof_bn[h->prof_used] = (st.kind == ST_GEMM || st.kind == ST_CHAIN) ? st.block_n : 0;
+    h->prof_ctas[h->prof_used] = st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
+    h->prof_bn[h->prof_used] = st.kind == ST_GEMM ? st.block_n : 0;
     h->prof_launches[h->prof_used] = 1;
     ++h->prof_used;
     return TMAE_OK;
@@ -1042,33 +1011,33 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                                                o.ids_restore, w.ids_keep, st, a.io));
                 break;
             case ST_GATHER:
-                CUDA_TRY(h, launch_gather_patches(a.imgs, w.ids_keep, w.patches, w.x, h->vecs["cls_token"],
+                CUDA_TRY(h, launch_gather_patches(a.imgs, w.ids_keep, w.patches.p, w.x, h->vecs["cls_token"],
                                                   h->vecs["encoder_pos_embed"], N, h->cfg.img_size, h->grid_w, K, T, C,
-                                                  h->cfg.in_chans, h->cfg.patch_size, st, a.io));
+                                                  h->cfg.in_chans, h->cfg.patch_size, w.patches.lo, st, a.io));
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
                                         sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes));
                 break;
-            case ST_CHAIN:
-                CUDA_TRY(h, gemm_chain_launch(pl.d_params, sp.chain, sp.chain_grid, sp.chain_max_bn, st));
-                break;
             case ST_LN:
                 if (sp.ln_final)
-                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.enc, o.x_remain, N * T, C, T, 1, h->cfg.ln_eps, st, a.io));
+                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.enc.p, o.x_remain, N * T, C, T, 1, h->cfg.ln_eps, w.enc.lo, st, a.io));
                 else
-                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.xn, nullptr, N * T, C, T, 0, h->cfg.ln_eps, st));
+                    CUDA_TRY(h, launch_layernorm(w.x, sp.ln_gamma, sp.ln_beta, w.xn.p, nullptr, N * T, C, T, 0, h->cfg.ln_eps, w.xn.lo, st));
                 break;
             case ST_ATTN:
-                CUDA_TRY(h, launch_attention(w.qkv, w.attn, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                if (h->precise_enc)
+                    CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                else
+                    CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 break;
             case ST_EB:
                 CUDA_TRY(h, launch_bottleneck(w.z, h->eb_tab, (long long)N * h->s4 * h->s4, h->Cz, o.z_likelihoods,
-                                              o.z_symbols, o.z_hat, w.zhat_bf, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
+                                              o.z_symbols, o.z_hat, w.zhat_bf.p, w.zhat_bf.lo, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
                 break;
             case ST_GC:
                 CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc * sp.gc_slices,
-                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_bf, h->Cy, s, w.rate_acc, st, a.io));
+                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_bf.p, w.yhat_bf.lo, h->Cy, s, w.rate_acc, st, a.io));
                 break;
             case ST_RATE:
                 CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
@@ -1181,12 +1150,11 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     h->encode = reinterpret_cast<PFN_encodeTiled>(fn);
     e = gemm_tc_configure();
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "gemm configure: %s", cudaGetErrorString(e));
-    e = gemm_chain_configure();
-    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "chain configure: %s", cudaGetErrorString(e));
     e = attention_configure(h->T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
     h->use_graph = getenv("TMAE_NO_GRAPH") == nullptr;
-    h->use_chain = getenv("TMAE_CHAIN") != nullptr;
+    h->precise_enc = (h->cfg.flags & TMAE_FLAG_PRECISE_ALL) != 0;
+    h->precise_rate = h->precise_enc || (h->cfg.flags & TMAE_FLAG_PRECISE_RATE) != 0;
     *out = h.release();
     return TMAE_OK;
 }
@@ -1239,23 +1207,23 @@ int tmae_finalize_weights(tmae_handle* h) {
     int rc;
     if ((rc = keep_vec(h, "cls_token", C))) return rc;
     if ((rc = keep_vec(h, "encoder_pos_embed", (size_t)(h->L + 1) * C))) return rc;
-    { int sg[1] = {h->patch_dim}; if ((rc = pack_layer(h, "encoder_embed.proj", "encoder_embed.proj", C, h->patch_dim, 1, 1, sg, 0))) return rc; }
+    { int sg[1] = {h->patch_dim}; if ((rc = pack_layer(h, "encoder_embed.proj", "encoder_embed.proj", C, h->patch_dim, 1, 1, sg, 0, h->precise_enc))) return rc; }
     for (int i = 0; i < h->cfg.encoder_depth; ++i) {
         const std::string pre = "encoder_blocks." + std::to_string(i);
         for (const char* nm : {".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"})
             if ((rc = keep_vec(h, pre + nm, C))) return rc;
         int sgC[1] = {C}, sgM[1] = {h->mlp};
-        if ((rc = pack_layer(h, pre + ".attn.qkv", pre + ".attn.qkv", 3 * C, C, 1, 1, sgC, 0))) return rc;
-        if ((rc = pack_layer(h, pre + ".attn.proj", pre + ".attn.proj", C, C, 1, 1, sgC, 0))) return rc;
-        if ((rc = pack_layer(h, pre + ".mlp.fc1", pre + ".mlp.fc1", h->mlp, C, 1, 1, sgC, 0))) return rc;
-        if ((rc = pack_layer(h, pre + ".mlp.fc2", pre + ".mlp.fc2", C, h->mlp, 1, 1, sgM, 0))) return rc;
+        if ((rc = pack_layer(h, pre + ".attn.qkv", pre + ".attn.qkv", 3 * C, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
+        if ((rc = pack_layer(h, pre + ".attn.proj", pre + ".attn.proj", C, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
+        if ((rc = pack_layer(h, pre + ".mlp.fc1", pre + ".mlp.fc1", h->mlp, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
+        if ((rc = pack_layer(h, pre + ".mlp.fc2", pre + ".mlp.fc2", C, h->mlp, 1, 1, sgM, 0, h->precise_enc))) return rc;
     }
     if ((rc = keep_vec(h, "encoder_norm.weight", C))) return rc;
     if ((rc = keep_vec(h, "encoder_norm.bias", C))) return rc;
     for (int l = 0; l < 4; ++l) {
         int sg[1] = {h->ga_ch[l]};
         const std::string nm = "g_a." + std::to_string(2 * l);
-        if ((rc = pack_layer(h, nm, nm, h->ga_ch[l + 1], h->ga_ch[l], 1, 1, sg, 0))) return rc;
+        if ((rc = pack_layer(h, nm, nm, h->ga_ch[l + 1], h->ga_ch[l], 1, 1, sg, 0, h->precise_rate))) return rc;
     }
     {
         int ci[5], co[5], aux[5];
@@ -1263,7 +1231,7 @@ int tmae_finalize_weights(tmae_handle* h) {
         for (int l = 0; l < 5; ++l) {
             int sg[1] = {ci[l]};
             const std::string nm = "h_a." + std::to_string(2 * l);
-            if ((rc = pack_layer(h, nm, nm, co[l], ci[l], 9, 1, sg, 0))) return rc;
+            if ((rc = pack_layer(h, nm, nm, co[l], ci[l], 9, 1, sg, 0, h->precise_rate))) return rc;
         }
         hs_layers(h, ci, co, aux);
         for (const char* net : {"h_s_mean", "h_s_scale"})
@@ -1271,7 +1239,7 @@ int tmae_finalize_weights(tmae_handle* h) {
                 int sg[1] = {ci[l]};
                 const std::string key = std::string(net) + "." + std::to_string(2 * l);
                 const std::string wname = aux[l] == 2 ? key + ".0" : key;      // subpel = Sequential(conv, PixelShuffle)
-                if ((rc = pack_layer(h, key, wname, co[l] * aux[l] * aux[l], ci[l], 9, 1, sg, aux[l] == 2))) return rc;
+                if ((rc = pack_layer(h, key, wname, co[l] * aux[l] * aux[l], ci[l], 9, 1, sg, aux[l] == 2, h->precise_rate))) return rc;
             }
     }
     for (int i = 0; i < h->nsl; ++i) {
@@ -1284,7 +1252,7 @@ int tmae_finalize_weights(tmae_handle* h) {
                 int sg[3] = {ch[l], 0, 0};
                 int nseg = 1;
                 if (l == 0 && sup > 0) { sg[0] = h->Cy; sg[1] = h->sc * sup; nseg = 2; }
-                if ((rc = pack_layer(h, nm, nm, ch[l + 1], ch[l], 9, nseg, sg, 0))) return rc;
+                if ((rc = pack_layer(h, nm, nm, ch[l + 1], ch[l], 9, nseg, sg, 0, h->precise_rate))) return rc;
             }
         int lch[6];
         cc_channels(h, lch, i, true);
@@ -1297,7 +1265,7 @@ int tmae_finalize_weights(tmae_handle* h) {
                 if (i < h->nsl / 2) { sg[1] = h->sc * (i + 1); nseg = 2; }
                 else { sg[1] = h->sc * sup; sg[2] = h->sc; nseg = 3; }
             }
-            if ((rc = pack_layer(h, nm, nm, lch[l + 1], lch[l], 9, nseg, sg, 0))) return rc;
+            if ((rc = pack_layer(h, nm, nm, lch[l + 1], lch[l], 9, nseg, sg, 0, h->precise_rate))) return rc;
         }
     }
     {   // factorized prior table
@@ -1386,7 +1354,7 @@ int tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_o
     const size_t rk = (size_t)N * h->K;
     CUDA_TRY(h, cudaMemsetAsync(w.rate_acc, 0, sizeof(double) * N, st));
     CUDA_TRY(h, cudaMemcpyAsync(w.y, y, rk * h->Cy * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(h, launch_f32_to_bf16(w.y, w.y_bf, (long long)rk * h->Cy, st));
+    CUDA_TRY(h, launch_f32_to_bf16(w.y, w.y_bf.p, (long long)rk * h->Cy, w.y_bf.lo, st));
     RunArgs a;
     a.out = out; a.begin = pl->first_rate_step; a.end = (int)pl->steps.size();
     if (h->profiling) h->prof_used = 0;
@@ -1446,7 +1414,7 @@ int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* li
                          void* stream) {
     if (!h || !h->finalized) return fail(h, TMAE_ESTATE, "weights not finalized");
     if (!z || rows < 0) return fail(h, TMAE_EINVAL, "invalid argument");
-    CUDA_TRY(h, launch_bottleneck(z, h->eb_tab, rows, h->Cz, likelihood, symbols, z_hat, nullptr, 1, nullptr, 1,
+    CUDA_TRY(h, launch_bottleneck(z, h->eb_tab, rows, h->Cz, likelihood, symbols, z_hat, nullptr, 0, 1, nullptr, 1,
                                   reinterpret_cast<cudaStream_t>(stream)));
     return TMAE_OK;
 }
@@ -1501,7 +1469,7 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
         int smem = 0, kgroup = 1; const int stages = gemm_pick_stages(p.block_n, ctas, false, &smem, &kgroup);
         fprintf(stderr, "[gemm timing] M=%d N=%d Kb=%d taps=%d bn=%d ctas=%d stages=%d x%d smem=%d | kernel %.1f us (events), first-start..last-end %.1f us | "
                 "per-CTA avg ns since entry: setup %.0f, tma0 %.0f, full0 %.0f, mma_done_issue %.0f, accum_seen %.0f, epi_done %.0f | first chunk: ldtm_done %.0f, staged %.0f, batch0 %.0f, batch1 %.0f\n",
-                p.M, p.N, p.seg_kblocks[0] + p.seg_kblocks[1] + p.seg_kblocks[2], p.num_taps, p.block_n, ctas, stages, kgroup, smem, ms * 1e3,
+                p.M, p.N, p.b_kb_per_tap, p.num_taps, p.block_n, ctas, stages, kgroup, smem, ms * 1e3,
                 (tend - tmin) * 1e-3, avg[1], avg[2], avg[3], avg[4], avg[5], avg[6], avg[8], avg[9], avg[10], avg[11]);
         // steady-state cost of back-to-back dependent launches of this kernel: plain stream vs CUDA graph
         {
@@ -1581,7 +1549,7 @@ int tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* Cmat,
     cudaMemcpy2DAsync(wp, (size_t)Kp * 2, B, (size_t)K * 2, (size_t)K * 2, N, cudaMemcpyDeviceToDevice, st);
     if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
     Layer L;
-    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.Kp = Kp;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.Kp = Kp; L.kb_tap = Kp / 64;
     GemmDesc d;
     d.layer = &L;
     d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(A), K, K);
@@ -1609,16 +1577,92 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
         g_create_error = tmp->err; free_pool(pool); return rc;
     }
     int sg[1] = {Cin};
-    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, st);
+    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, 1, st);
     if (bias) cudaMemcpyAsync(bz, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "conv3x3 staging: %s", cudaGetErrorString(e)); }
     Layer L;
-    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.Kp = Kp;
+    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.Kp = Kp; L.kb_tap = pad64(Cin) / 64;
     ConvGeom cg;
     if (!conv_geom(s, N, &cg)) { free_pool(pool); return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_bf16: grid side %d unsupported (1..128)", s); }
     GemmDesc d;
     d.layer = &L;
     d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(x), Cin, Cin);      // compact NHWC, read in place by 4-D TMA boxes
+    d.a_rows = (long long)N * s * s; d.M = cg.m_tiles * kBlockM; d.in_mode = IN_CONV; d.side = s; d.n_img = N;
+    d.act = gelu ? ACT_GELU : ACT_NONE;
+    d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);
+    rc = engine_common(tmp.get(), d, 0, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+// Precise (split-bf16) engine self-tests: fp32 operands in, split into (hi, lo) bf16 planes here, three tensor-core
+// terms per product - the configuration every TMAE_FLAG_PRECISE_* layer runs in.
+int tmae_gemm_split(const float* A, const float* B, const float* bias, float* Cmat, int M, int N, int K, int block_n,
+                    int impl, void* stream) {
+    if (!A || !B || !Cmat || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "tmae_gemm_split: invalid shape (need K %% 8 == 0, N %% 8 == 0)");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int Kp = pad64(K);
+    __nv_bfloat16 *wp = nullptr, *ap = nullptr;
+    float* bz = nullptr;
+    std::vector<void*> pool;
+    const size_t a_plane = ((size_t)M * K + 63) / 64 * 64;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp * 2)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N)) ||
+        (rc = dev_alloc(tmp.get(), pool, &ap, a_plane * 2))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    int sg[1] = {K};
+    cudaError_t e = launch_prepack_weight(B, wp, N, K, 1, 1, sg, 0, 2, st);
+    if (e == cudaSuccess) e = launch_f32_to_bf16(A, ap, (long long)M * K, (long long)a_plane, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "gemm_split staging: %s", cudaGetErrorString(e)); }
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.planes = 2; L.kb_tap = Kp / 64; L.Kp = Kp * 2;
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(ap, K, K, (long long)a_plane);
+    d.a_rows = M; d.M = M;
+    d.out0 = outspec(Cmat, N, OUT_F32, MAP_SAME);
+    rc = engine_common(tmp.get(), d, block_n, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+int tmae_conv3x3_split(const float* x, const float* wgt, const float* bias, float* out, int N, int s, int Cin, int Cout,
+                       int gelu, int impl, void* stream) {
+    if (!x || !wgt || !out || N <= 0 || s <= 0 || Cin % 8 != 0 || Cout % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_split: invalid shape");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int kp_tap = pad64(Cin);
+    std::vector<void*> pool;
+    __nv_bfloat16 *wp = nullptr, *xp = nullptr;
+    float* bz = nullptr;
+    const size_t x_plane = ((size_t)N * s * s * Cin + 63) / 64 * 64;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * kp_tap * 9 * 2)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout)) ||
+        (rc = dev_alloc(tmp.get(), pool, &xp, x_plane * 2))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    int sg[1] = {Cin};
+    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, 2, st);
+    if (e == cudaSuccess) e = launch_f32_to_bf16(x, xp, (long long)N * s * s * Cin, (long long)x_plane, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "conv3x3_split staging: %s", cudaGetErrorString(e)); }
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.planes = 2; L.kb_tap = kp_tap / 64;
+    L.Kp = kp_tap * 9 * 2;
+    ConvGeom cg;
+    if (!conv_geom(s, N, &cg)) { free_pool(pool); return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_split: grid side %d unsupported (1..128)", s); }
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(xp, Cin, Cin, (long long)x_plane);
     d.a_rows = (long long)N * s * s; d.M = cg.m_tiles * kBlockM; d.in_mode = IN_CONV; d.side = s; d.n_img = N;
     d.act = gelu ? ACT_GELU : ACT_NONE;
     d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);

@@ -32,7 +32,8 @@ class MCM(nn.Module):
                  encoder_num_heads=12, decoder_embed_dim=512, decoder_depth=8, decoder_num_heads=16, mlp_ratio=4.0,
                  norm_layer=None, norm_pix_loss=False, latent_depth=384, hyperprior_depth=192, num_slices=12,
                  num_keep_patches=144, *, skip_dead_lrp: bool = False, debug_simt: bool = False,
-                 softmax_isa: Optional[int] = None, extra_outputs: bool = False, share_sm: bool = False):
+                 softmax_isa: Optional[int] = None, extra_outputs: bool = False, share_sm: bool = False,
+                 precise: Optional[str] = None):
         super().__init__()
         self.cfg = PathConfig(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
                               encoder_embed_dim=encoder_embed_dim, encoder_depth=encoder_depth,
@@ -47,6 +48,11 @@ class MCM(nn.Module):
         self.debug_simt = debug_simt
         self.share_sm = share_sm                 # several handles/streams in flight on this GPU (see TMAE_FLAG_SHARE_SM)
         self.extra_outputs = extra_outputs       # also return y, z, mu, sigma, x_remain (parity tests)
+        # accuracy mode: None = bf16 operands everywhere (throughput); "rate" = split-bf16 (fp32-equivalent products) for
+        # g_a and every entropy-model conv; "all" = the encoder too -> symbols match the fp32 reference up to ties
+        if precise not in (None, "rate", "all"):
+            raise ValueError("precise must be None, 'rate' or 'all'")
+        self.precise = precise
         if softmax_isa is None:
             # lane order of the ATen CPU softmax the reference's host routine would have used on this machine
             softmax_isa = 16 if "AVX512" in torch.backends.cpu.get_cpu_capability().upper() else 8
@@ -116,7 +122,8 @@ class MCM(nn.Module):
         self._release()
         c = self.cfg
         flags = ((_native.FLAG_SKIP_DEAD_LRP if self.skip_dead_lrp else 0) | (_native.FLAG_DEBUG_SIMT if self.debug_simt else 0)
-                 | (_native.FLAG_SHARE_SM if self.share_sm else 0))
+                 | (_native.FLAG_SHARE_SM if self.share_sm else 0)
+                 | {None: 0, "rate": _native.FLAG_PRECISE_RATE, "all": _native.FLAG_PRECISE_ALL}[self.precise])
         cfg = _native.TmaeConfig(c.img_size, c.patch_size, c.in_chans, c.encoder_embed_dim, c.encoder_depth,
                                  c.encoder_num_heads, c.decoder_embed_dim, c.mlp_ratio, c.latent_depth,
                                  c.hyperprior_depth, c.num_slices, c.num_keep_patches, c.ln_eps, self.softmax_isa, flags)
