@@ -2,17 +2,26 @@
 """Benchmark of the compression forward path (encode + rate), BASELINE.json metric:
 images/s masked-ViT encode+rate.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload B64|B144|L256]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME] [--precise all|rate]
+                    [--scaling weak|strong]
 
 One "step" = one pass of the path (mask-select -> gather -> ViT encoder -> g_a/h_a/h_s/slice nets -> quantise ->
-likelihoods -> bpp) over one batch of synthetic images.  Default workload = BASELINE.json configs[1]:
-synthetic 224x224, batch 64 per GPU, ViT-B/16, K=64 kept patches (nearest valid value to mask ratio 0.75; the
-reference needs sqrt(K) % 4 == 0), bf16 tensor-core operands, fp32 accumulate.
-Images are sharded across ranks (weak scaling, weights replicated); the only collective is the 16-byte rate
-all-reduce per step.
+likelihoods -> bpp) over one batch of images.  Default workload = BASELINE.json configs[1]: synthetic 224x224, batch 64
+per GPU, ViT-B/16, K=64 kept patches (nearest valid value to mask ratio 0.75; the reference needs sqrt(K) % 4 == 0,
+SURVEY 0.2 #4), bf16 tensor-core operands, fp32 accumulate.  The other BASELINE configs are `--workload` names:
+  KODAK24 / KODAK24_K64   the 24 bundled Kodak images through the reference's test transform (224x224) + reference-generated
+                          scores (tests/golden), ViT-B/16, K=144 (shipped) / K=64; also reports the batch-1 latency (config 1)
+  TILES288                config 3 native-resolution extension: 24 images x 12 tiles of 224x224 = 288 tiles (synthetic pixels
+                          and Kodak-like heavy-tie scores: the native PNGs and the score generator do not travel)
+  L256                    config 4: synthetic 512x512, ViT-L/16, K=256, 32 images per GPU (256 over 8 GPUs)
+  DIV2K_L400/_L256/_L144  config 5: one 2048x1080 image = 12 tiles of 512x512, ViT-L/16, K = 400 / 256 / 144
+Images are sharded across ranks, weights replicated; the only collective is the 16-byte rate all-reduce per step.
+`--scaling weak` (default): every rank runs the workload's batch; `--scaling strong`: the workload's batch is the
+GLOBAL batch, sharded with distributed.shard_range.
 
---impl reference: the reference's CPU implementation of the same path (the in-repo fp32 oracle; the reference module
-itself cannot be imported - timm/compressai absent) on the host cores, on a bounded sample of the same workload.
+--impl reference: the reference's CPU implementation of the same path (the in-repo fp32 oracle, bit-identical to the
+reference's MCM.forward executed from /root/reference - tests/test_reference_exec.py; the reference tree itself does not
+exist on the GPU box) on all host cores, same images per step.
 """
 from __future__ import annotations
 
@@ -30,16 +39,32 @@ sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402
 
+VIT_L = dict(img_size=512, encoder_embed_dim=1024, encoder_depth=24, encoder_num_heads=16)
 WORKLOADS = {
-    # name: (model kwargs, per-GPU batch, description)
+    # name: (model kwargs, batch, description, input kind)
     "B64": (dict(img_size=224, num_keep_patches=64), 64,
-            "synthetic 224x224 batch 64/GPU, ViT-B/16, K=64 (67% masked; nearest valid to 0.75), bf16"),
+            "synthetic 224x224 batch 64/GPU, ViT-B/16, K=64 (67% masked; nearest valid to 0.75)", "uniform"),
     "B144": (dict(img_size=224, num_keep_patches=144), 64,
-             "synthetic 224x224 batch 64/GPU, ViT-B/16, K=144 (shipped test.sh value), bf16"),
-    "L256": (dict(img_size=512, encoder_embed_dim=1024, encoder_depth=24, encoder_num_heads=16, num_keep_patches=256), 32,
-             "synthetic 512x512 batch 32/GPU, ViT-L/16, K=256 (75% masked), bf16"),
+             "synthetic 224x224 batch 64/GPU, ViT-B/16, K=144 (shipped test.sh value)", "uniform"),
+    "L256": (dict(num_keep_patches=256, **VIT_L), 32,
+             "synthetic 512x512 batch 32/GPU, ViT-L/16, K=256 (75% masked)", "uniform"),
+    "KODAK24": (dict(img_size=224, num_keep_patches=144), 24,
+                "24 Kodak images, reference test transform (224x224) + reference-generated scores, ViT-B/16, K=144", "kodak"),
+    "KODAK24_K64": (dict(img_size=224, num_keep_patches=64), 24,
+                    "24 Kodak images, reference test transform (224x224) + reference-generated scores, ViT-B/16, K=64", "kodak"),
+    "TILES288": (dict(img_size=224, num_keep_patches=144), 288,
+                 "Kodak native-resolution tiling shape: 24 images x 12 tiles of 224x224 = 288 tiles (synthetic pixels, "
+                 "heavy-tie scores), ViT-B/16, K=144", "ties"),
+    "DIV2K_L400": (dict(num_keep_patches=400, **VIT_L), 12,
+                   "DIV2K-shaped 2048x1080 -> 12 tiles of 512x512, ViT-L/16, K=400 (mask ratio 0.61)", "uniform"),
+    "DIV2K_L256": (dict(num_keep_patches=256, **VIT_L), 12,
+                   "DIV2K-shaped 2048x1080 -> 12 tiles of 512x512, ViT-L/16, K=256 (mask ratio 0.75)", "uniform"),
+    "DIV2K_L144": (dict(num_keep_patches=144, **VIT_L), 12,
+                   "DIV2K-shaped 2048x1080 -> 12 tiles of 512x512, ViT-L/16, K=144 (mask ratio 0.86)", "uniform"),
 }
-ALGO_GFLOP_PER_IMG = {"B64": 20.761, "B144": 46.636, "L256": 201.005}     # SURVEY 6.2 (reference-algorithmic)
+# reference-algorithmic GFLOP per image (embed all L patches, all 12 LRP nets); closed forms for the others
+ALGO_GFLOP_PER_IMG = {"B64": 20.761, "B144": 46.636, "L256": 201.005, "KODAK24": 46.636, "KODAK24_K64": 20.761,
+                      "TILES288": 46.636, "DIV2K_L256": 201.005}
 
 
 def load_peaks():
@@ -105,18 +130,56 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_inputs(kwargs, batch, seed, n_rot):
+def make_inputs(kwargs, batch, seed, n_rot, kind="uniform"):
+    """n_rot batches of (imgs [batch,3,S,S], scores [batch,L]) on the host."""
     g = torch.Generator().manual_seed(seed)
     S = kwargs["img_size"]
     L = (S // 16) ** 2
+    if kind == "kodak":
+        import numpy as np
+        z = np.load(ROOT / "tests" / "golden" / "kodak_224.npz")
+        imgs = torch.from_numpy(z["imgs"]).permute(0, 3, 1, 2).float() / 255.0          # reference test transform, no normalise
+        scores = torch.load(ROOT / "tests" / "golden" / "kodak_scores.pt")               # reference score generator
+        reps = (batch + imgs.shape[0] - 1) // imgs.shape[0]
+        imgs, scores = imgs.repeat(reps, 1, 1, 1)[:batch].contiguous(), scores.repeat(reps, 1)[:batch].contiguous()
+        return [imgs.clone() for _ in range(n_rot)], [scores.clone() for _ in range(n_rot)]
     imgs = [torch.rand(batch, 3, S, S, generator=g) for _ in range(n_rot)]
-    scores = [torch.rand(batch, L, generator=g) for _ in range(n_rot)]
+    if kind == "ties":          # Kodak-like heavy-tie integer products, min-max normalised (SURVEY 8d config 2)
+        scores = []
+        for _ in range(n_rot):
+            a = torch.randint(0, 40, (batch, L), generator=g).float() * torch.randint(0, 165, (batch, L), generator=g).float()
+            lo, hi = a.min(1, keepdim=True)[0], a.max(1, keepdim=True)[0]
+            scores.append((a - lo) / (hi - lo).clamp_min(1.0))
+    else:
+        scores = [torch.rand(batch, L, generator=g) for _ in range(n_rot)]
     return imgs, scores
 
 
+def algo_gflop_per_image(cfg, wl):
+    """Reference-algorithmic GFLOP per image (2 x MAC; SURVEY 6.2 closed forms)."""
+    if wl in ALGO_GFLOP_PER_IMG:
+        return ALGO_GFLOP_PER_IMG[wl]
+    K, T, C, D, L = cfg.num_keep_patches, cfg.tokens, cfg.encoder_embed_dim, cfg.encoder_depth, cfg.num_patches
+    f = 2.0 * L * cfg.patch_dim * C + 24.0 * D * T * C * C + 4.0 * D * T * T * C
+    ch = cfg.g_a_channels()
+    f += 2.0 * K * sum(ch[i] * ch[i + 1] for i in range(4))
+    side = cfg.side
+    for cin, cout, st in cfg.h_a_layers():
+        side = side // st
+        f += 2.0 * side * side * 9 * cin * cout
+    side = cfg.side // 4
+    for cin, cout, r in cfg.h_s_layers():
+        f += 2 * (2.0 * side * side * 9 * cin * cout * r * r)
+        side *= r
+    for i in range(cfg.num_slices):
+        for chans, mult in ((cfg.cc_channels(i), 2), (cfg.lrp_channels(i), 1)):
+            f += mult * sum(2.0 * K * 9 * chans[j] * chans[j + 1] for j in range(5))
+    return f / 1e9
+
+
 # ----------------------------------------------------------------------------------------------------------
-def run_reference(args, kwargs, batch, desc):
-    """The reference's CPU path (fp32 oracle == reference math) on the host cores; rank 0 only."""
+def run_reference(args, kwargs, batch, desc, kind):
+    """The reference's CPU path (fp32 oracle == reference MCM.forward bit for bit) on the host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -126,23 +189,43 @@ def run_reference(args, kwargs, batch, desc):
     sd = make_state_dict(cfg, seed=0)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample = min(batch, args.ref_sample)
-    imgs, scores = make_inputs(kwargs, sample, 0, 1)
-    for _ in range(max(args.warmup, 1) if args.warmup < 2 else 1):
-        ref_model.forward_rate(sd, cfg, imgs[0], scores[0])
+    imgs, scores = make_inputs(kwargs, batch, 0, 1, kind)
+    sample = batch if args.ref_sample <= 0 else min(batch, args.ref_sample)
+    t0 = time.perf_counter()
+    ref_model.forward_rate(sd, cfg, imgs[0][:sample], scores[0][:sample])                 # warm-up step (also sizes the run)
+    t_step = time.perf_counter() - t0
+    budget = 240.0                                                                         # the whole run ends within a few minutes
+    planned = (args.steps + max(args.warmup - 1, 0)) * t_step
+    if planned > budget:
+        sample = max(1, int(sample * budget / planned))
+    for _ in range(max(min(args.warmup, 2) - 1, 0)):
+        ref_model.forward_rate(sd, cfg, imgs[0][:sample], scores[0][:sample])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ref_model.forward_rate(sd, cfg, imgs[0], scores[0])
+        ref_model.forward_rate(sd, cfg, imgs[0][:sample], scores[0][:sample])
     dt = time.perf_counter() - t0
     val = sample * args.steps / dt
+    # the testing.py:29 configuration: one thread, batch 1
+    torch.set_num_threads(1)
+    ref_model.forward_rate(sd, cfg, imgs[0][:1], scores[0][:1])
+    t1 = time.perf_counter()
+    reps = 0
+    while reps < 2 or (time.perf_counter() - t1 < 6.0 and reps < 10):
+        ref_model.forward_rate(sd, cfg, imgs[0][:1], scores[0][:1])
+        reps += 1
+    one_thread = reps / (time.perf_counter() - t1)
+    torch.set_num_threads(cores)
     line = {
         "impl": "reference", "metric": "images/s masked-ViT encode+rate", "value": val, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "sample": f"{sample} of {batch} images per step"},
-        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} images/step x {args.steps} steps, fp32 oracle (oracle/ref_model.py), "
-                                   f"host python mask routine included"},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic" if kind != "kodak" else "kodak",
+        "config": {"workload": desc, "name": args.workload, "per_gpu_batch": batch, "sample": f"{sample} of {batch} images per step",
+                   "same_config": sample == batch},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images/step x {args.steps} steps, fp32 oracle (oracle/ref_model.py; bit-identical to the "
+                                   f"reference MCM.forward executed in the build container), host python mask routine included",
+                         "single_thread_batch1": {"value": one_thread, "unit": "images/s", "cores": 1,
+                                                  "note": "testing.py:29 torch.set_num_threads(1), batch 1"}},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -150,9 +233,59 @@ def run_reference(args, kwargs, batch, desc):
 
 
 # ----------------------------------------------------------------------------------------------------------
-def run_b200(args, kwargs, batch, desc, wl):
+class Runner:
+    """S handles / streams of one model configuration on this rank's GPU and the timed loops over them."""
+
+    def __init__(self, kwargs, batch, S, precise, dev, world):
+        from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
+        self.cfg = PathConfig(**kwargs)
+        sd = make_state_dict(self.cfg, seed=0)                     # replicated weights
+        self.models = []
+        for _ in range(S):
+            m_ = MCM(**kwargs, skip_dead_lrp=False, share_sm=S > 1, precise=precise)
+            m_.load_state_dict(sd)
+            m_.cuda().eval()
+            m_.reserve(batch)
+            self.models.append(m_)
+        self.S, self.batch, self.dev, self.world = S, batch, dev, world
+        self.stream = torch.cuda.current_stream()
+        self.side = [torch.cuda.Stream(device=dev) for _ in range(S)]
+
+    def fork(self, ev):
+        ev.record(self.stream)
+        for s_ in self.side:
+            s_.wait_event(ev)
+
+    def join(self, ev):
+        for s_ in self.side:
+            self.stream.wait_stream(s_)
+        ev.record(self.stream)
+
+    def barrier(self):
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, step_fn, steps):
+        """EXACTLY `steps` steps between a barrier + synchronize on both sides; device time, max over ranks (ms)."""
+        import torch.distributed as dist
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        self.fork(e0)
+        out = None
+        for i in range(steps):
+            out = step_fn(i)
+        self.join(e1)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+
+
+def run_b200(args, kwargs, batch_named, desc, wl, kind):
     import torch.distributed as dist
-    from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
     from textmae_image_compression_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,49 +296,30 @@ def run_b200(args, kwargs, batch, desc, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = PathConfig(**kwargs)
-    sd = make_state_dict(cfg, seed=0)                         # replicated weights
+    strong = args.scaling == "strong"
+    if strong:                                      # the named batch is the GLOBAL batch: this rank's shard of it
+        lo, hi = D.shard_range(batch_named, rank, world)
+        batch = hi - lo
+        global_batch = batch_named
+    else:
+        batch, global_batch = batch_named, batch_named * world
     # `--streams S` pipelines S batches through S independent handles (own workspace, own CUDA stream): the serial
     # slice chain of one batch leaves most SMs idle, a second batch in flight fills them.  A step is still one batch.
     S = max(1, args.streams)
-    models = []
-    for _ in range(S):
-        m_ = MCM(**kwargs, skip_dead_lrp=False, share_sm=S > 1)
-        m_.load_state_dict(sd)
-        m_.cuda().eval()
-        models.append(m_)
-    model = models[0]
-    del sd
-    n_rot = 8                                                 # rotating input batches: 8 x 38.5 MB > 126 MB L2
-    imgs_h, scores_h = make_inputs(kwargs, batch, 1000 + rank, n_rot)
+    R = Runner(kwargs, max(batch, 1), S, args.precise, dev, world)
+    cfg, models, model = R.cfg, R.models, R.models[0]
+    img_bytes = batch * 3 * kwargs["img_size"] ** 2 * 4
+    n_rot = max(2, min(8, int(320e6 // max(img_bytes, 1)) + 1))   # rotating input batches: together > 126 MB L2 (with the weights)
+    imgs_h, scores_h = make_inputs(kwargs, batch, 1000 + rank, n_rot, kind)
     imgs_d = [t.cuda() for t in imgs_h]
     scores_d = [t.cuda() for t in scores_h]
-    for m_ in models:
-        m_.reserve(batch)
-    stream = torch.cuda.current_stream()
-    side = [torch.cuda.Stream(device=dev) for _ in range(S)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def step_dev(i):
-        with torch.cuda.stream(side[i % S]):
-            out = models[i % S](imgs_d[i % n_rot], scores_d[i % n_rot])
+        with torch.cuda.stream(R.side[i % S]):
+            out = models[i % S](imgs_d[i % n_rot], scores_d[i % n_rot], need_recon=False)
             if world > 1:
                 D.aggregate_rate(out["rate_sums"])            # the path's only collective (16 bytes)
         return out
-
-    def fork(ev):
-        ev.record(stream)
-        for s_ in side:
-            s_.wait_event(ev)
-
-    def join(ev):
-        for s_ in side:
-            stream.wait_stream(s_)
-        ev.record(stream)
 
     # ---- device-resident throughput -------------------------------------------------------------------
     # every handle needs 3 forwards before it is in steady state (plain launches, graph capture, first replay) and its
@@ -235,131 +349,178 @@ def run_b200(args, kwargs, batch, desc, wl):
     for i in range(extra):
         step_dev(warm_eff + i)
     warm_eff += extra
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    fork(e0)
-    for i in range(args.steps):
-        out = step_dev(i)
-    join(e1)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = t.item()
-    value = world * batch * args.steps / (ms_max / 1e3)
+    ms_max, out = R.timed(step_dev, args.steps)
+    value = global_batch * args.steps / (ms_max / 1e3)
 
-    # ---- end to end through the host-buffer entry (pinned host inputs, H2D + forward + D2H bpp each step) ----
-    pin_i = [t.pin_memory() for t in imgs_h[:3]]
-    pin_s = [t.pin_memory() for t in scores_h[:3]]
-    bpp_pin = [torch.empty(batch, dtype=torch.float32).pin_memory() for _ in range(3)]
+    # ---- end to end through the host-buffer entry -------------------------------------------------------------------
+    # pinned host images + scores -> H2D -> forward -> D2H of what the reference's forward returns to its caller
+    # (likelihoods y / z, MCM.py:801) plus the int16 symbols, ids_restore and the per-image bpp, every step, all on the
+    # step's stream.
+    n_pin = min(3, n_rot)
+    pin_i = [t.pin_memory() for t in imgs_h[:n_pin]]
+    pin_s = [t.pin_memory() for t in scores_h[:n_pin]]
+    res_pin = [[m_.host_result_buffers(batch) for _ in range(2)] for m_ in models]     # two result sets per handle
+
     def step_host(i):
-        # pinned host inputs -> H2D -> forward -> D2H of the per-image bpp, all on the step's stream
-        models[i % S].forward_host(pin_i[i % 3], pin_s[i % 3], bpp_pin[i % 3], stream=side[i % S])
+        models[i % S].forward_host(pin_i[i % n_pin], pin_s[i % n_pin], res_pin[i % S][(i // S) % 2], stream=R.side[i % S])
+        if world > 1:
+            pass                                              # rate_sums travel to the host with the step; no device collective here
+        return None
 
-    for i in range(max(args.warmup, S)):
+    for i in range(max(args.warmup, 2 * S)):
         step_host(i)
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fork(e2)
-    for i in range(args.steps):
-        step_host(i)
-    join(e3)
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
-    t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * args.steps / (t.item() / 1e3)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = R.timed(step_host, args.steps)
+    e2e_value = global_batch * args.steps / (ms_e2e / 1e3)
     h2d = imgs_h[0].numel() * 4 + scores_h[0].numel() * 4
-    d2h = batch * 4
+    d2h = sum(v.numel() * v.element_size() for v in res_pin[0][0].values())
+    e2e_check = {"bpp_equal_device_path": bool(torch.allclose(res_pin[(args.steps - 1) % S][((args.steps - 1) // S) % 2]["bpp"],
+                                                              models[(args.steps - 1) % S](imgs_d[(args.steps - 1) % n_pin],
+                                                                                           scores_d[(args.steps - 1) % n_pin],
+                                                                                           need_recon=False)["bpp"].cpu(), rtol=1e-5)),
+                 "returns": sorted(res_pin[0][0].keys())}
+
+    # ---- batch-1 latency (config 1: the testing.py call pattern) ------------------------------------------------------
+    latency = None
+    if rank == 0 and kind == "kodak":
+        one_i, one_s = imgs_d[0][:1].contiguous(), scores_d[0][:1].contiguous()
+        for _ in range(5):
+            model(one_i, one_s, need_recon=False)
+        torch.cuda.synchronize()
+        ts = []
+        for k in range(24):
+            a = imgs_d[0][k % batch: k % batch + 1].contiguous(); b = scores_d[0][k % batch: k % batch + 1].contiguous()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            o1 = model(a, b, need_recon=False)
+            o1["bpp"].cpu()                                    # the caller reads the rate: host-visible latency
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts.sort()
+        latency = {"batch1_ms_median": ts[len(ts) // 2], "batch1_ms_min": ts[0], "images_per_s": 1e3 / ts[len(ts) // 2],
+                   "note": "wall clock, one image per call, device inputs -> bpp read on the host (testing.py call pattern)"}
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel family: CUDA events inside the library --------------------------------
     peaks = load_peaks()
-    # events bracket every RUN of consecutive launches of one kernel family (132 of the 133 GEMM-engine launches sit in
-    # runs of 2..5: fc1+fc2, g_a, h_a, h_s, the five layers of a cc / lrp net), so the launch-to-launch overlap (PDL) inside
-    # a run is kept and the event gap between its members is not charged to the kernel.  The stricter every-launch
-    # bracketing is reported next to it as `per_launch_events`.
-    def profiled(by_run):
+    peak = peaks["bf16_tflops_sustained"]
+    # events bracket every RUN of consecutive launches of one kernel family (the launch-to-launch overlap (PDL) inside
+    # a run is kept and the event gap between its members is not charged to the kernel).  `isolated`: one stream, nothing
+    # else on the GPU.  `in_mode`: the same profiled forwards while the other S-1 handles keep running their forwards on
+    # their own streams, i.e. under the contention of the benchmarked configuration.
+    def profiled(by_run, loaded):
         model.profile(True, by_run=by_run)
-        for i in range(2):
-            model(imgs_d[i % n_rot], scores_d[i % n_rot])
+        if loaded:
+            for rep in range(3):
+                for k in range(1, S):
+                    with torch.cuda.stream(R.side[k]):
+                        models[k](imgs_d[k % n_rot], scores_d[k % n_rot], need_recon=False)
+        with torch.cuda.stream(R.side[0]):
+            for i in range(2):
+                model(imgs_d[i % n_rot], scores_d[i % n_rot], need_recon=False)
         torch.cuda.synchronize()
         f_ = model.profile_read()
         model.profile(False)
         return f_
-    fams_launch = profiled(False)
-    fams = profiled(True)
+    fams_launch = profiled(False, False)
+    fams = profiled(True, False)
+    fams_mode = profiled(True, True) if S > 1 else fams
     tot_ms = sum(f["ms"] for f in fams) or 1.0
     gemm = next((f for f in fams if f["name"] == "gemm_tc"), None)
+    gemm_mode = next((f for f in fams_mode if f["name"] == "gemm_tc"), None)
+    gemm_launch = next((f for f in fams_launch if f["name"] == "gemm_tc"), None)
     roofline = None
     traffic = None
-    tr_path = ROOT / "profiles" / f"r01_launches_{wl}.json"      # ncu dram__bytes_read+write per launch (cold cache)
+    tr_path = ROOT / "profiles" / f"r02_launches_{wl}.json"      # ncu dram__bytes_read+write per launch (--cache-control none)
     if tr_path.exists():
         try:
             traffic = json.loads(tr_path.read_text())["families"]["gemm_tc_kernel"]["dram_MB_per_launch"] * 1e6
         except Exception:
             traffic = None
+    exec_flops_step = 0.0
     if gemm and gemm["ms"] > 0:
-        achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12
-        peak = peaks["bf16_tflops_sustained"]
+        exec_flops_step = gemm["flops"] / 2.0                  # the profile ran 2 forwards
+        mma_flops_step = gemm["mma_flops"] / 2.0
+        achieved = gemm["mma_flops"] / (gemm["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": traffic, "traffic_note": "bytes per launch, ncu dram__bytes_read+write averaged over the gemm_tc "
-                    "launches of one forward (profiles/r01_launches_*.json); algorithmic_flops_per_launch below",
-                    "algorithmic_flops_per_launch": gemm["flops"] / gemm["launches"], "peak_source": f"{peaks['source']} bf16_tflops_sustained (of measured)",
-                    "launches_per_step": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / gemm["launches"],
+                    "traffic": traffic, "traffic_note": "bytes per launch, ncu dram__bytes_read+write averaged over the gemm_tc launches of "
+                    "one forward (profiles/r02_launches_*.json, --cache-control none); null until that capture exists",
+                    "flops": "EXECUTED tensor-core flops (patch embed counts the K kept patches; precise layers count their 3 terms)",
+                    "executed_flops_per_launch": mma_flops_step / (gemm["launches"] / 2.0),
+                    "useful_frac": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / peak,
+                    "peak_source": f"{peaks['source']} bf16_tflops_sustained (of measured)",
+                    "launches_per_step": gemm["launches"] // 2, "avg_launch_us": gemm["ms"] * 1e3 / gemm["launches"],
                     "share_of_step": gemm["ms"] / tot_ms,
-                    "timing": "CUDA events around each run of consecutive gemm_tc launches, inside the library, on the launching stream",
-                    "per_launch_events": (lambda g_: {"avg_launch_us": g_["ms"] * 1e3 / g_["launches"],
-                                                      "frac": g_["flops"] / (g_["ms"] * 1e-3) / 1e12 / peak})(
-                        next(f for f in fams_launch if f["name"] == "gemm_tc")),
-                    "families": {f["name"]: {"ms": round(f["ms"], 4), "launches": f["launches"]} for f in fams}}
+                    "timing": "CUDA events around each run of consecutive gemm_tc launches, inside the library, on the launching stream; "
+                              "isolated = one stream, plain launches",
+                    "per_launch_events": {"avg_launch_us": gemm_launch["ms"] * 1e3 / gemm_launch["launches"],
+                                          "frac": gemm_launch["mma_flops"] / (gemm_launch["ms"] * 1e-3) / 1e12 / peak},
+                    "in_mode": {"streams": S, "avg_launch_us": gemm_mode["ms"] * 1e3 / gemm_mode["launches"],
+                                "frac": gemm_mode["mma_flops"] / (gemm_mode["ms"] * 1e-3) / 1e12 / peak,
+                                "note": "same events while the other handles run their forwards concurrently (the benchmarked mode): "
+                                        "a launch shares the SMs, so its own duration grows while the step's throughput rises"},
+                    # the timed region itself: executed tensor-core flops of one step / measured ms_per_step (graph replay, S streams)
+                    "step_aggregate": {"achieved": mma_flops_step * world / (ms_max / args.steps * 1e-3) / 1e12 / world,
+                                       "frac": mma_flops_step / (ms_max / args.steps * 1e-3) / 1e12 / peak,
+                                       "note": "executed flops of one step / ms_per_step of the timed region (CUDA graph + S streams)"},
+                    "families": {f["name"]: {"ms": round(f["ms"] / 2, 4), "launches": f["launches"] // 2} for f in fams}}
 
     # memory-bound kernel families against the measured HBM peak (algorithmic bytes / per-launch event time; these
     # launches move 0.1-19 MB each, i.e. they are launch-latency bound at batch 64 - SURVEY 8d)
-    hbm_kernels = {f["name"]: {"GB/s": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1), "launches": f["launches"],
+    hbm_kernels = {f["name"]: {"GB/s": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1), "launches": f["launches"] // 2,
                                "MB_per_launch": round(f["bytes"] / f["launches"] / 1e6, 3),
                                "frac_of_hbm_peak": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
                    for f in fams_launch if f["bytes"] > 0 and f["ms"] > 0}
-    launches = model.launch_count(batch)
+    launches = model.launch_count(max(batch, 1))
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ---------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import ref_model
+        from textmae_image_compression_b200 import make_state_dict
         sdc = make_state_dict(cfg, seed=0)
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        sample = min(batch, args.ref_sample)
+        sample = min(batch, 16)
         ref_model.forward_rate(sdc, cfg, imgs_h[0][:sample], scores_h[0][:sample])          # warm-up
         reps, t0 = 0, time.perf_counter()
-        while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 50):
+        while reps < 2 or (time.perf_counter() - t0 < 10.0 and reps < 50):
             ref_model.forward_rate(sdc, cfg, imgs_h[0][:sample], scores_h[0][:sample])
             reps += 1
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": sample * reps / dt, "unit": "images/s", "cores": torch.get_num_threads(),
                         "kind": "port", "sample": f"{sample} images x {reps} reps of the same workload, fp32 oracle "
-                                                  f"(oracle/ref_model.py) incl. the host python mask routine"}
+                                                  f"(oracle/ref_model.py == reference MCM.forward bit for bit) incl. the host python mask routine"}
+        torch.set_num_threads(1)
+        ref_model.forward_rate(sdc, cfg, imgs_h[0][:1], scores_h[0][:1])
+        reps, t0 = 0, time.perf_counter()
+        while reps < 2 or (time.perf_counter() - t0 < 5.0 and reps < 10):
+            ref_model.forward_rate(sdc, cfg, imgs_h[0][:1], scores_h[0][:1])
+            reps += 1
+        cpu_baseline["single_thread_batch1"] = {"value": reps / (time.perf_counter() - t0), "unit": "images/s", "cores": 1,
+                                                "note": "testing.py:29 torch.set_num_threads(1), batch 1"}
+        torch.set_num_threads(cores)
 
     if rank == 0:
+        gfl = algo_gflop_per_image(cfg, wl)
         line = {
             "metric": "images/s masked-ViT encode+rate", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": desc, "name": wl, "per_gpu_batch": batch, "global_batch": batch * world,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precise is None else "bf16x3 (split-bf16 operands, fp32-equivalent products)",
+            "data": "kodak (tests/golden fixtures)" if kind == "kodak" else "synthetic",
+            "config": {"workload": desc, "name": wl, "per_gpu_batch": batch, "global_batch": global_batch,
                        "parallelism": f"dp{world} (images sharded, weights replicated, 16-byte rate all-reduce)",
-                       "streams_per_gpu": S, "warmup_effective": warm_eff,
+                       "precise": args.precise, "streams_per_gpu": S, "warmup_effective": warm_eff,
                        "l2_policy": f"inputs rotate over {n_rot} batches ({n_rot * imgs_h[0].numel() * 4 / 1e6:.0f} MB) "
-                                    "+ 350 MB of weights per step > 126 MB L2",
-                       "algorithmic_gflop_per_image": ALGO_GFLOP_PER_IMG.get(wl)},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                                    "+ >= 350 MB of weights per step > 126 MB L2",
+                       "algorithmic_gflop_per_image": gfl, "executed_gflop_per_image": exec_flops_step / max(batch, 1) / 1e9},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps, "check": e2e_check},
             "gpu_launches": launches * args.steps,
             "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "model_tflops": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3,
-            "model_tflops_frac_of_peak": value * (ALGO_GFLOP_PER_IMG.get(wl) or 0) / 1e3 / peaks["bf16_tflops_sustained"],
+            "latency": latency,
+            "model_tflops": value * gfl / 1e3,
+            "model_tflops_frac_of_peak": value / world * gfl / 1e3 / peak,
             "bpp_mean_last_step": out["bpp"].mean().item(),
         }
         print(json.dumps(line), flush=True)
@@ -374,21 +535,25 @@ def main():
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B64", choices=sorted(WORKLOADS))
-    ap.add_argument("--ref-sample", type=int, default=8, help="images per step for the CPU reference arm")
+    ap.add_argument("--precise", default=None, choices=["all", "rate"],
+                    help="accuracy mode: split-bf16 operands for the rate half / the whole path (symbols match the fp32 reference)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the workload's batch per GPU; strong: the workload's batch is the global batch, sharded over the GPUs")
+    ap.add_argument("--ref-sample", type=int, default=0, help="images per step for the CPU reference arm (0 = the full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (independent handles/streams)")
     ap.add_argument("--batch", type=int, default=0, help="experiment only: images per step instead of the workload's batch")
     args = ap.parse_args()
-    kwargs, batch, desc = WORKLOADS[args.workload]
+    kwargs, batch, desc, kind = WORKLOADS[args.workload]
     if args.batch > 0:
         desc = desc.replace(f"batch {batch}", f"batch {args.batch} (EXPERIMENT, not the named workload)")
         batch = args.batch
     if args.impl == "reference":
-        run_reference(args, kwargs, batch, desc)
+        run_reference(args, kwargs, batch, desc, kind)
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_b200(args, kwargs, batch, desc, args.workload)
+        run_b200(args, kwargs, batch, desc, args.workload, kind)
 
 
 if __name__ == "__main__":

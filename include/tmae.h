@@ -93,7 +93,23 @@ typedef struct {
     int64_t* ids_shuffle;     /* [N, L]             MCM.get_ids_shuffle return value (MCM.py:423) */
     int64_t* ids_restore;     /* [N, L]             argsort(ids_shuffle) (MCM.py:580) */
     int64_t* ids_keep;        /* [N, K]             ids_shuffle[:, :K]   (MCM.py:583) */
+    int16_t* y_symbols_i16;   /* [N, s, s, Cy]      y_symbols saturated to int16 (compact form for the host / the coder) */
+    int16_t* z_symbols_i16;   /* [N, s/4, s/4, Cz]  z_symbols saturated to int16 */
+    int32_t* y_indexes;       /* [N, s, s, Cy]      GaussianConditional.build_indexes(sigma): scale-table bucket of every
+                                                    element (MCM.py:839; needs tmae_set_scale_table) */
 } tmae_outputs;
+
+/* HOST destinations of tmae_forward_host (pinned memory for full speed); any pointer may be NULL.  This is what the
+ * reference's forward hands back to its caller - likelihoods (MCM.py:801) - plus the symbols and the per-image rate. */
+typedef struct {
+    float*   bpp;             /* [N] */
+    double*  rate_sums;       /* [2] */
+    float*   y_likelihoods;   /* [N, s, s, Cy] */
+    float*   z_likelihoods;   /* [N, s/4, s/4, Cz] */
+    int16_t* y_symbols;       /* [N, s, s, Cy] */
+    int16_t* z_symbols;       /* [N, s/4, s/4, Cz] */
+    int64_t* ids_restore;     /* [N, L] (the reference returns it on the CPU, MCM.py:580) */
+} tmae_host_outputs;
 
 typedef struct tmae_handle tmae_handle;
 
@@ -115,6 +131,11 @@ TMAE_API int  tmae_set_weight(tmae_handle* h, const char* name, const void* data
  * softplus/tanh of the factorized-prior parameters.  Synchronises the device. */
 TMAE_API int  tmae_finalize_weights(tmae_handle* h);
 
+/* Scale table of the reference's GaussianConditional (testing.py:223 model.update(force=True) builds it with
+ * compressai's get_scale_table(): 64 log-spaced scales 0.11..256): enables out->y_indexes.  Host or device pointer,
+ * ascending, n <= 256. */
+TMAE_API int  tmae_set_scale_table(tmae_handle* h, const float* table, int n);
+
 /* Workspace: grown on demand inside tmae_forward; this makes the growth explicit (e.g. before CUDA-graph capture). */
 TMAE_API size_t tmae_workspace_bytes(const tmae_handle* h, int N);
 TMAE_API int  tmae_reserve(tmae_handle* h, int N);
@@ -124,9 +145,10 @@ TMAE_API int  tmae_reserve(tmae_handle* h, int N);
 TMAE_API int  tmae_forward(tmae_handle* h, const float* imgs, const float* scores, int N,
                   const tmae_outputs* out, void* stream);
 /* Same call with HOST buffers: h_imgs / h_scores (pinned for full speed) are copied in on `stream`, the
- * forward runs, and h_bpp [N] (+ optional h_rate_sums [2]) is copied back; `out` (device pointers) may be NULL. */
+ * forward runs, and every non-NULL member of `hout` (likelihoods, int16 symbols, ids_restore, per-image bpp) is
+ * copied back on the same stream; `out` (device pointers, optional) as in tmae_forward. */
 TMAE_API int  tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores, int N,
-                       float* h_bpp, double* h_rate_sums, const tmae_outputs* out, void* stream);
+                       const tmae_host_outputs* hout, const tmae_outputs* out, void* stream);
 /* Teacher-forced entry for parity tests: run the rate half only (MCM.py:739-787) from a given latent
  * y f32 [N, s, s, Cy]. */
 TMAE_API int  tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_outputs* out, void* stream);
@@ -144,6 +166,10 @@ TMAE_API int  tmae_gaussian_rate(const float* y, const float* mu, const float* s
 /* EntropyBottleneck eval forward + quantize_ste (MCM.py:741-744): z f32 [rows, Cz] channels-last. */
 TMAE_API int  tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows,
                           float* likelihood, int32_t* symbols, float* z_hat, void* stream);
+
+/* [N, hw, C] channels-last int32 -> [N, C, hw]: the order the reference feeds its range coder, slice by slice in
+ * (c, y, x) order (MCM.py:867-873), for symbols and indexes alike. */
+TMAE_API int  tmae_pack_nchw_i32(const int32_t* nhwc, int32_t* nchw, int N, int hw, int C, void* stream);
 
 /* Tensor-core GEMM/conv engine self-test hook (tests): C[M,N] = A[M,K] * B[N,K]^T (+bias) with bf16 inputs,
  * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */
@@ -167,8 +193,10 @@ typedef struct {
     char   name[32];
     int32_t launches;
     float  ms;           /* summed device time */
-    double flops;        /* algorithmic flops of those launches (0 for non-GEMM families) */
+    double flops;        /* flops of those launches as the reference counts them for the rows actually computed (executed
+                            work: patch embed = the K kept patches; 0 for non-GEMM families) */
     double bytes;        /* algorithmic bytes moved (0 if not tracked) */
+    double mma_flops;    /* tensor-core flops issued: flops x 3 for precise (split-bf16) layers, else = flops */
 } tmae_profile_entry;
 TMAE_API int  tmae_profile_enable(tmae_handle* h, int enable);
 TMAE_API int  tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entries, int* n_entries);

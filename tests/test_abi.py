@@ -31,8 +31,9 @@ def test_header_symbols_are_exported(lib):
 def test_struct_layouts_match_header():
     from textmae_image_compression_b200 import _native
     assert C.sizeof(_native.TmaeConfig) == 15 * 4
-    assert C.sizeof(_native.TmaeOutputs) == 16 * 8
-    assert C.sizeof(_native.TmaeProfileEntry) == 32 + 4 + 4 + 8 + 8
+    assert C.sizeof(_native.TmaeOutputs) == 19 * 8
+    assert C.sizeof(_native.TmaeHostOutputs) == 7 * 8
+    assert C.sizeof(_native.TmaeProfileEntry) == 32 + 4 + 4 + 8 + 8 + 8
     header = (ROOT / "include" / "tmae.h").read_text()
     body = header[header.index("typedef struct {\n    float*   y_likelihoods"):header.index("} tmae_outputs;")]
     fields = re.findall(r"\*\s+(\w+);", body)

@@ -29,16 +29,23 @@ class TmaeConfig(C.Structure):
 
 
 OUTPUT_FIELDS = ("y_likelihoods", "z_likelihoods", "y_symbols", "z_symbols", "y_hat", "z_hat", "y", "z", "mu",
-                 "sigma", "x_remain", "bpp", "rate_sums", "ids_shuffle", "ids_restore", "ids_keep")
+                 "sigma", "x_remain", "bpp", "rate_sums", "ids_shuffle", "ids_restore", "ids_keep", "y_symbols_i16",
+                 "z_symbols_i16", "y_indexes")
+
+HOST_OUTPUT_FIELDS = ("bpp", "rate_sums", "y_likelihoods", "z_likelihoods", "y_symbols", "z_symbols", "ids_restore")
 
 
 class TmaeOutputs(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in OUTPUT_FIELDS]
 
 
+class TmaeHostOutputs(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in HOST_OUTPUT_FIELDS]
+
+
 class TmaeProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("ms", C.c_float), ("flops", C.c_double),
-                ("bytes", C.c_double)]
+                ("bytes", C.c_double), ("mma_flops", C.c_double)]
 
 
 class TmaeProfileStep(C.Structure):
@@ -58,7 +65,9 @@ SIGNATURES = {
     "tmae_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
     "tmae_reserve": (C.c_int, [_P, C.c_int]),
     "tmae_forward": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(TmaeOutputs), _P]),
-    "tmae_forward_host": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, C.POINTER(TmaeOutputs), _P]),
+    "tmae_forward_host": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(TmaeHostOutputs), C.POINTER(TmaeOutputs), _P]),
+    "tmae_set_scale_table": (C.c_int, [_P, _P, C.c_int]),
+    "tmae_pack_nchw_i32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_forward_from_latent": (C.c_int, [_P, _P, C.c_int, C.POINTER(TmaeOutputs), _P]),
     "tmae_forward_encoder": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(TmaeOutputs), _P]),
     "tmae_mask_select": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),

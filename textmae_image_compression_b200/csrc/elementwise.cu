@@ -186,10 +186,10 @@ __global__ void __launch_bounds__(256)
 bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab, long long total, int Cz,
                   float* __restrict__ lik_out, int32_t* __restrict__ sym_out, float* __restrict__ zhat_out,
                   __nv_bfloat16* __restrict__ zhat_bf, long long lo_off, int s4, double* __restrict__ rate_acc, int rows_per_image,
-                  const IoBlock* __restrict__ io) {
+                  int16_t* __restrict__ sym16_out, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
-    if (io) { lik_out = io->out.z_likelihoods; sym_out = io->out.z_symbols; zhat_out = io->out.z_hat; }
+    if (io) { lik_out = io->out.z_likelihoods; sym_out = io->out.z_symbols; zhat_out = io->out.z_hat; sym16_out = io->out.z_symbols_i16; }
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float lg = 0.f;
     int n = 0;
@@ -208,6 +208,7 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
         lik = fmaxf(lik, 1e-9f);
         if (lik_out) lik_out[idx] = lik;
         if (sym_out) sym_out[idx] = (int32_t)sym;
+        if (sym16_out) sym16_out[idx] = (int16_t)fminf(fmaxf(sym, -32768.f), 32767.f);
         if (zhat_out) zhat_out[idx] = zh;
         n = (int)(row / rows_per_image);
         if (zhat_bf) {
@@ -232,13 +233,13 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
 
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
                               float* zhat, __nv_bfloat16* zhat_bf, long long lo_off, int s4, double* rate_acc, int rows_per_image,
-                              cudaStream_t st, const IoBlock* io) {
+                              int16_t* sym16, cudaStream_t st, const IoBlock* io) {
     const long long total = rows * Cz;
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(bottleneck_kernel);
     return launch_k(bottleneck_kernel, dim3(blocks), dim3(256), 0, st, true, z, eb_tab, total, Cz, lik, sym, zhat, zhat_bf, lo_off, s4,
-                    rate_acc, rows_per_image, io);
+                    rate_acc, rows_per_image, sym16, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -262,10 +263,11 @@ __global__ void __launch_bounds__(256)
 gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
                       int32_t* __restrict__ sym_out, float* __restrict__ yhat_out, __nv_bfloat16* __restrict__ yhat_bf,
-                      long long lo_off, int ld_bf, int s, double* __restrict__ rate_acc, const IoBlock* __restrict__ io) {
+                      long long lo_off, int ld_bf, int s, double* __restrict__ rate_acc, const float* __restrict__ scale_table,
+                      int n_table, int16_t* __restrict__ sym16_out, int32_t* __restrict__ idx_out, const IoBlock* __restrict__ io) {
     pdl_wait();
     pdl_launch_dependents();
-    if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; }
+    if (io) { lik_out = io->out.y_likelihoods; sym_out = io->out.y_symbols; sym16_out = io->out.y_symbols_i16; idx_out = io->out.y_indexes; }
     const int vec_per_row = cs >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = rows * vec_per_row;
@@ -285,6 +287,24 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
         gaussian_elem(yv.w, mv.w, sv.w, lk.w, sy.w, yh.w);
         if (lik_out) *reinterpret_cast<float4*>(lik_out + off) = lk;
         if (sym_out) *reinterpret_cast<int4*>(sym_out + off) = make_int4((int)sy.x, (int)sy.y, (int)sy.z, (int)sy.w);
+        if (sym16_out) {
+            auto sat = [](float v) { return (int16_t)fminf(fmaxf(v, -32768.f), 32767.f); };
+            short4 s4v;
+            s4v.x = sat(sy.x); s4v.y = sat(sy.y); s4v.z = sat(sy.z); s4v.w = sat(sy.w);
+            *reinterpret_cast<short4*>(sym16_out + off) = s4v;
+        }
+        if (idx_out && scale_table) {
+            // compressai GaussianConditional.build_indexes (MCM.py:839): scales lower-bounded at 0.11, then
+            // index = (len - 1) - #{t in table[:-1] : scale <= t}  ==  #{t in table[:-1] : t < scale}
+            const float sc[4] = {fmaxf(sv.x, 0.11f), fmaxf(sv.y, 0.11f), fmaxf(sv.z, 0.11f), fmaxf(sv.w, 0.11f)};
+            int id[4] = {0, 0, 0, 0};
+            for (int t = 0; t < n_table - 1; ++t) {
+                const float tv = __ldg(scale_table + t);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) id[e] += (tv < sc[e]) ? 1 : 0;
+            }
+            *reinterpret_cast<int4*>(idx_out + off) = make_int4(id[0], id[1], id[2], id[3]);
+        }
         if (yhat_out) *reinterpret_cast<float4*>(yhat_out + off) = yh;
         const int K = s * s;
         n = (int)(row / K);
@@ -319,13 +339,14 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
 
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
                                   int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, long long lo_off,
-                                  int ld_bf, int s, double* rate_acc, cudaStream_t st, const IoBlock* io) {
+                                  int ld_bf, int s, double* rate_acc, const float* scale_table, int n_table, int16_t* sym16,
+                                  int32_t* idx, cudaStream_t st, const IoBlock* io) {
     const long long total = rows * (cs / 4);
     if (total == 0) return cudaSuccess;
     const int blocks = (int)((total + 255) / 256);
     TMAE_CARVEOUT_ONCE(gaussian_slice_kernel);
     return launch_k(gaussian_slice_kernel, dim3(blocks), dim3(256), 0, st, true, y, mu, sigma, rows, ld, col0, cs, lik, sym, yhat,
-                    yhat_bf, lo_off, ld_bf, s, rate_acc, io);
+                    yhat_bf, lo_off, ld_bf, s, rate_acc, scale_table, n_table, sym16, idx, io);
 }
 
 // flat variant for the stand-alone operator (n elements, no layout)
@@ -412,6 +433,31 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
                     reinterpret_cast<const float4*>(yhat), ids_keep, n_y / 4, n_z / 4, n_ids);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Symbol / index packing for the entropy coder: the reference hands `encode_with_indexes` the symbols of
+// slice 0, 1, ... each flattened in (c, y, x) order (MCM.py:867-873) == the NCHW order of the whole [Cy, s, s] latent of
+// an image.  The path keeps everything channels-last, so this transposes [N, hw, C] -> [N, C, hw] through a 32x32 tile.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_nchw_i32_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int hw, int C) {
+    __shared__ int32_t tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int32_t* s = src + (size_t)n * hw * C;
+    int32_t* d = dst + (size_t)n * hw * C;
+    for (int r = ty; r < 32; r += 8)
+        if (p0 + r < hw && c0 + tx < C) tile[r][tx] = s[(size_t)(p0 + r) * C + c0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (c0 + r < C && p0 + tx < hw) d[(size_t)(c0 + r) * hw + p0 + tx] = tile[tx][r];
+}
+cudaError_t launch_pack_nchw_i32(const int32_t* src, int32_t* dst, int N, int hw, int C, cudaStream_t st) {
+    if (N == 0) return cudaSuccess;
+    dim3 grid((hw + 31) / 32, (C + 31) / 32, N);
+    pack_nchw_i32_kernel<<<grid, 256, 0, st>>>(src, dst, hw, C);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Weight prepack: fp32 [Cout, Cin_total, kh, kw] (or [Cout, Cin] linear) -> bf16 [Cout, Kp], K index =

@@ -48,10 +48,13 @@ cudaError_t launch_layernorm(const float* x, const float* gamma, const float* be
                              const IoBlock* io = nullptr);
 cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long rows, int Cz, float* lik, int32_t* sym,
                               float* zhat, __nv_bfloat16* zhat_bf, long long lo_off, int s4, double* rate_acc, int rows_per_image,
+                              int16_t* sym16,
                               cudaStream_t st, const IoBlock* io = nullptr);
 cudaError_t launch_gaussian_slice(const float* y, const float* mu, const float* sigma, long long rows, int ld, int col0,
                                   int cs, float* lik, int32_t* sym, float* yhat, __nv_bfloat16* yhat_bf, long long lo_off,
-                                  int ld_bf, int s, double* rate_acc, cudaStream_t st, const IoBlock* io = nullptr);
+                                  int ld_bf, int s, double* rate_acc, const float* scale_table, int n_table, int16_t* sym16,
+                                  int32_t* idx, cudaStream_t st, const IoBlock* io = nullptr);
+cudaError_t launch_pack_nchw_i32(const int32_t* src, int32_t* dst, int N, int hw, int C, cudaStream_t st);
 cudaError_t launch_gaussian_flat(const float* y, const float* mu, const float* sigma, long long n, float* lik,
                                  int32_t* sym, float* yhat, cudaStream_t st);
 cudaError_t launch_rate_finalize(const double* rate_acc, int N, double pixels_per_image, float* bpp,

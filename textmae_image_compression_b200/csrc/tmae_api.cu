@@ -106,6 +106,9 @@ struct Workspace {
     double* rate_sums = nullptr;
     // host-buffer entry staging
     float *st_imgs = nullptr, *st_scores = nullptr;
+    float *st_ylik = nullptr, *st_zlik = nullptr;          // device staging of the host-returned results (tmae_forward_host)
+    int16_t *st_ysym = nullptr, *st_zsym = nullptr;
+    int64_t* st_ids_restore = nullptr;
     IoBlock* io = nullptr;           // per-call pointers for graph replays
 };
 
@@ -120,6 +123,8 @@ struct tmae_handle {
     std::map<std::string, Layer> layers;
     std::map<std::string, float*> vecs;       // fp32 vectors kept as-is (LN params, cls, pos-embed)
     float* eb_tab = nullptr;
+    float* scale_table = nullptr;    // GaussianConditional scale table (tmae_set_scale_table) for y_indexes
+    int n_scale_table = 0;
     bool finalized = false;
     Workspace ws;
     std::map<int, std::unique_ptr<Plan>> plans;
@@ -135,7 +140,7 @@ struct tmae_handle {
     std::vector<int> prof_launches;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     std::vector<int> prof_family;
-    std::vector<double> prof_flops, prof_bytes;
+    std::vector<double> prof_flops, prof_bytes, prof_mma;
     std::vector<std::string> prof_tag;
     std::vector<int> prof_ctas, prof_bn;
     size_t prof_used = 0;
@@ -281,6 +286,15 @@ int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname,
     if (rc) return rc;
     rc = need_raw(h, wname + ".bias", (size_t)Cout, &b);
     if (rc) return rc;
+    {   // layout check, not only the element count: [Cout, Cin] / [Cout, Cin, k, k] (a transposed tensor must not pass)
+        const std::vector<int64_t>& sh = w->shape;
+        const int k = taps == 9 ? 3 : 0;
+        bool ok = sh.size() >= 2 && sh[0] == Cout;
+        if (ok && taps == 9) ok = sh.size() == 4 && sh[1] == Cin && sh[2] == k && sh[3] == k;
+        if (ok && taps == 1) { int64_t rest = 1; for (size_t i = 1; i < sh.size(); ++i) rest *= sh[i]; ok = rest == Cin && (sh.size() == 2 || sh.size() == 4); }
+        if (!ok) return fail(h, TMAE_EINVAL, "weight '%s.weight' has the wrong shape (expected [%d, %d%s])", wname.c_str(), Cout, Cin,
+                             taps == 9 ? ", 3, 3" : "");
+    }
     Layer L;
     L.Cout = Cout; L.Cin = Cin; L.taps = taps; L.nseg = nseg; L.shuffle = shuffle;
     int kp_tap = 0, csum = 0;
@@ -590,6 +604,11 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.rate_sums, (size_t)2);
     WS_ALLOC(w.st_imgs, (size_t)N * h->cfg.in_chans * h->cfg.img_size * h->cfg.img_size);
     WS_ALLOC(w.st_scores, (size_t)N * h->L);
+    WS_ALLOC(w.st_ylik, rk * Cy);
+    WS_ALLOC(w.st_zlik, rz * Cz);
+    WS_ALLOC(w.st_ysym, rk * Cy);
+    WS_ALLOC(w.st_zsym, rz * Cz);
+    WS_ALLOC(w.st_ids_restore, (size_t)N * h->L);
     WS_ALLOC(w.io, (size_t)1);
 #undef WS_ALLOC_BF
 #undef WS_ALLOC
@@ -961,6 +980,7 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
         h->prof_family.push_back(0);
         h->prof_flops.push_back(0);
         h->prof_bytes.push_back(0);
+        h->prof_mma.push_back(0);
         h->prof_tag.push_back("");
         h->prof_ctas.push_back(0);
         h->prof_bn.push_back(0);
@@ -971,6 +991,7 @@ int prof_slot(tmae_handle* h, const Step& st, cudaEvent_t* a, cudaEvent_t* b) {
     h->prof_family[h->prof_used] = st.family;
     h->prof_flops[h->prof_used] = st.flops;
     h->prof_bytes[h->prof_used] = st.bytes;
+    h->prof_mma[h->prof_used] = st.flops * st.mma_terms;
     h->prof_tag[h->prof_used] = st.tag;
     h->prof_ctas[h->prof_used] = st.kind == ST_GEMM ? ((st.max_M + kBlockM - 1) / kBlockM) * ((st.max_N + st.block_n - 1) / st.block_n) * st.groups : 0;
     h->prof_bn[h->prof_used] = st.kind == ST_GEMM ? st.block_n : 0;
@@ -1000,6 +1021,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
             const size_t cur = h->prof_used - 1;
             h->prof_flops[cur] += sp.flops;
             h->prof_bytes[cur] += sp.bytes;
+            h->prof_mma[cur] += sp.flops * sp.mma_terms;
             h->prof_launches[cur] += 1;
         }
         switch (sp.kind) {
@@ -1033,11 +1055,13 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_EB:
                 CUDA_TRY(h, launch_bottleneck(w.z, h->eb_tab, (long long)N * h->s4 * h->s4, h->Cz, o.z_likelihoods,
-                                              o.z_symbols, o.z_hat, w.zhat_bf.p, w.zhat_bf.lo, h->s4, w.rate_acc, h->s4 * h->s4, st, a.io));
+                                              o.z_symbols, o.z_hat, w.zhat_bf.p, w.zhat_bf.lo, h->s4, w.rate_acc, h->s4 * h->s4,
+                                              o.z_symbols_i16, st, a.io));
                 break;
             case ST_GC:
                 CUDA_TRY(h, launch_gaussian_slice(w.y, w.mu, w.sigma, (long long)N * K, h->Cy, sp.slice * h->sc, h->sc * sp.gc_slices,
-                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_bf.p, w.yhat_bf.lo, h->Cy, s, w.rate_acc, st, a.io));
+                                                  o.y_likelihoods, o.y_symbols, w.yhat, w.yhat_bf.p, w.yhat_bf.lo, h->Cy, s, w.rate_acc,
+                                                  h->scale_table, h->n_scale_table, o.y_symbols_i16, o.y_indexes, st, a.io));
                 break;
             case ST_RATE:
                 CUDA_TRY(h, launch_rate_finalize(w.rate_acc, N, (double)h->cfg.img_size * h->cfg.img_size,
@@ -1165,6 +1189,7 @@ void tmae_destroy(tmae_handle* h) {
     for (auto& kv : h->raw) cudaFree(kv.second.ptr);
     for (auto& kv : h->plans) { if (kv.second->d_params) cudaFree(kv.second->d_params); if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph); }
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->scale_table) cudaFree(h->scale_table);
     free_pool(h->ws.allocs);
     free_pool(h->weight_allocs);
     for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1362,8 +1387,8 @@ int tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_o
     return copy_outputs(h, N, out, true, false, st);
 }
 
-int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores, int N, float* h_bpp,
-                      double* h_rate_sums, const tmae_outputs* out, void* stream) {
+int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores, int N, const tmae_host_outputs* hout,
+                      const tmae_outputs* out, void* stream) {
     int rc = check_ready(h, N);
     if (rc) return rc;
     if (!h_imgs || !h_scores) return fail(h, TMAE_EINVAL, "h_imgs / h_scores must not be null");
@@ -1375,8 +1400,16 @@ int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores
     CUDA_TRY(h, cudaMemcpyAsync(w.st_imgs, h_imgs, img_elems * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpyAsync(w.st_scores, h_scores, (size_t)N * h->L * sizeof(float), cudaMemcpyHostToDevice, st));
     tmae_outputs o = out ? *out : tmae_outputs{};
+    static const tmae_host_outputs kNoHost = {};
+    const tmae_host_outputs& ho = hout ? *hout : kNoHost;
     if (!o.bpp) o.bpp = w.bpp;
     if (!o.rate_sums) o.rate_sums = w.rate_sums;
+    // results the host asked for are produced into device staging buffers (unless the caller also gave device buffers)
+    if (ho.y_likelihoods && !o.y_likelihoods) o.y_likelihoods = w.st_ylik;
+    if (ho.z_likelihoods && !o.z_likelihoods) o.z_likelihoods = w.st_zlik;
+    if (ho.y_symbols && !o.y_symbols_i16) o.y_symbols_i16 = w.st_ysym;
+    if (ho.z_symbols && !o.z_symbols_i16) o.z_symbols_i16 = w.st_zsym;
+    if (ho.ids_restore && !o.ids_restore) o.ids_restore = w.st_ids_restore;
     bool done = false;
     if ((rc = run_full_graph(h, *pl, w.st_imgs, w.st_scores, &o, st, &done))) return rc;
     if (!done) {
@@ -1386,8 +1419,29 @@ int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores
         if ((rc = run_steps(h, *pl, a, st))) return rc;
         if ((rc = copy_outputs(h, N, out, true, true, st))) return rc;
     }
-    if (h_bpp) CUDA_TRY(h, cudaMemcpyAsync(h_bpp, o.bpp, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (h_rate_sums) CUDA_TRY(h, cudaMemcpyAsync(h_rate_sums, o.rate_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const size_t ny = (size_t)N * h->K * h->Cy, nz = (size_t)N * h->s4 * h->s4 * h->Cz;
+    if (ho.bpp) CUDA_TRY(h, cudaMemcpyAsync(ho.bpp, o.bpp, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (ho.rate_sums) CUDA_TRY(h, cudaMemcpyAsync(ho.rate_sums, o.rate_sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (ho.y_likelihoods) CUDA_TRY(h, cudaMemcpyAsync(ho.y_likelihoods, o.y_likelihoods, ny * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (ho.z_likelihoods) CUDA_TRY(h, cudaMemcpyAsync(ho.z_likelihoods, o.z_likelihoods, nz * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (ho.y_symbols) CUDA_TRY(h, cudaMemcpyAsync(ho.y_symbols, o.y_symbols_i16, ny * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (ho.z_symbols) CUDA_TRY(h, cudaMemcpyAsync(ho.z_symbols, o.z_symbols_i16, nz * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    if (ho.ids_restore) CUDA_TRY(h, cudaMemcpyAsync(ho.ids_restore, o.ids_restore, (size_t)N * h->L * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    return TMAE_OK;
+}
+
+int tmae_set_scale_table(tmae_handle* h, const float* table, int n) {
+    if (!h || !table || n < 2 || n > 256) return fail(h, TMAE_EINVAL, "scale table: need 2..256 ascending entries");
+    if (!h->scale_table) CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->scale_table), 256 * sizeof(float)));
+    CUDA_TRY(h, cudaMemcpy(h->scale_table, table, (size_t)n * sizeof(float), cudaMemcpyDefault));
+    h->n_scale_table = n;
+    return TMAE_OK;
+}
+
+int tmae_pack_nchw_i32(const int32_t* nhwc, int32_t* nchw, int N, int hw, int C, void* stream) {
+    if (!nhwc || !nchw || N < 0 || hw <= 0 || C <= 0) return fail(nullptr, TMAE_EINVAL, "invalid argument");
+    cudaError_t e = launch_pack_nchw_i32(nhwc, nchw, N, hw, C, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "pack_nchw: %s", cudaGetErrorString(e));
     return TMAE_OK;
 }
 
@@ -1414,7 +1468,7 @@ int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* li
                          void* stream) {
     if (!h || !h->finalized) return fail(h, TMAE_ESTATE, "weights not finalized");
     if (!z || rows < 0) return fail(h, TMAE_EINVAL, "invalid argument");
-    CUDA_TRY(h, launch_bottleneck(z, h->eb_tab, rows, h->Cz, likelihood, symbols, z_hat, nullptr, 0, 1, nullptr, 1,
+    CUDA_TRY(h, launch_bottleneck(z, h->eb_tab, rows, h->Cz, likelihood, symbols, z_hat, nullptr, 0, 1, nullptr, 1, nullptr,
                                   reinterpret_cast<cudaStream_t>(stream)));
     return TMAE_OK;
 }
@@ -1695,6 +1749,7 @@ int tmae_profile_read(tmae_handle* h, tmae_profile_entry* entries, int max_entri
         f.ms += ms;
         f.flops += h->prof_flops[i];
         f.bytes += h->prof_bytes[i];
+        f.mma_flops += h->prof_mma[i];
     }
     int n = 0;
     for (int f = 0; f < FAM_COUNT && n < max_entries; ++f)

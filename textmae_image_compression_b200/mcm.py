@@ -7,12 +7,21 @@ include/tmae.h.  PyTorch is used for device memory, streams and the module plumb
 
 `forward` returns a superset of the reference dict:
     "likelihoods": {"y": f32 [N,Cy,s,s], "z": f32 [N,Cz,s/4,s/4]}   (same keys / shapes as MCM.py:801,
-                    channels-last strides) - `RateDistortionLoss` (loss/rd_loss.py:15-20) consumes it unchanged
+                    channels-last strides); `RateDistortionLoss.forward` reads it at loss/rd_loss.py:19-20
     "latents":     {"y_sym": i32, "z_sym": i32, "y_hat": f32, "z_hat": f32}
     "bpp":         f32 [N]   per-image rate (rd_loss.py formula with N = 1)
     "rate_sums":   f64 [2]   {sum log2 likelihood, pixels} for the data-parallel aggregate
     "ids_restore": i64 [N,L], "ids_keep": i64 [N,K], "ids_shuffle": i64 [N,L]
-The reconstruction half ("loss", "x_hat": g_s, MAE decoder, SSIM/L1/VGG) is outside this path.
+    "loss": (ssim_loss, l1_loss, vgg_loss), "x_hat": f32 [N,3,S,S]   when the reconstruction half is requested
+                    (`need_recon=True`, or by default when the loaded state dict carries the decoder-side tensors):
+                    g_s + MAE decoder + unpatchify + distortion terms (MCM.py:789-797) in stock PyTorch on the
+                    library's y_hat (recon.py) - with them `RateDistortionLoss` (rd_loss.py:21-23) and
+                    `utils/engine.py:189-199 val_one_epoch` run against this module unchanged
+                    (tests/test_recon_cpu.py drives both, executed from /root/reference).  The VGG term is a hook
+                    (`feature_loss`), 0 when unset: the reference downloads pretrained weights for it.
+`compress_symbols` is the front half of `MCM.compress` (MCM.py:805-873): symbols and scale-table indexes of y in the
+order `encode_with_indexes` consumes, z symbols / channel indexes for `entropy_bottleneck.compress` (SURVEY 8f-1);
+the rANS coder itself (compressai C++) stays outside.
 """
 from __future__ import annotations
 
@@ -23,8 +32,17 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _native
+from . import _native, recon
 from .config import PathConfig
+
+
+_NATIVE_PREFIXES = ("cls_token", "encoder_pos_embed", "encoder_embed.", "encoder_blocks.", "encoder_norm.", "g_a.", "h_a.",
+                    "h_s_mean.", "h_s_scale.", "cc_transform_mean.", "cc_transform_scale.", "lrp_transform.",
+                    "entropy_bottleneck.")
+
+
+def _native_needs(name: str) -> bool:
+    return name.startswith(_NATIVE_PREFIXES)
 
 
 class MCM(nn.Module):
@@ -57,6 +75,10 @@ class MCM(nn.Module):
             # lane order of the ATen CPU softmax the reference's host routine would have used on this machine
             softmax_isa = 16 if "AVX512" in torch.backends.cpu.get_cpu_capability().upper() else 8
         self.softmax_isa = softmax_isa
+        self.feature_loss = None                 # optional callable(preds, imgs) -> scalar: the VGG term of forward_loss
+        self._scale_table = None                 # GaussianConditional scale table for compress_symbols (update())
+        self._last_stream = None                 # stream of the previous call on this handle (one workspace per handle)
+        self._last_event = None
         self._weights: Dict[str, torch.Tensor] = {}
         self._handle = None
         self._handle_device = None
@@ -136,12 +158,16 @@ class MCM(nn.Module):
             for name, t in self._weights.items():
                 if not t.is_floating_point():
                     continue
-                t = t.contiguous()
+                if not _native_needs(name):           # decoder-side tensors stay with recon.py (stock PyTorch)
+                    continue
+                t = t.float().contiguous()            # .half() / .bfloat16() modules: the ABI takes fp32 (dtype 0)
                 shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
                 _native.check(lib.tmae_set_weight(hp, name.encode(), C.c_void_p(t.data_ptr()), 0, t.dim(), shape,
                                                   C.byref(ign)), hp)
             _native.check(lib.tmae_finalize_weights(hp), hp, RuntimeError)
         self._dirty = False
+        self._scale_table_dirty = True           # a fresh handle has no scale table yet
+        self._last_stream = None
 
     # ------------------------------------------------------------------ helpers
     def _check_inputs(self, imgs, total_scores):
@@ -156,34 +182,61 @@ class MCM(nn.Module):
         if total_scores.shape[1] != c.num_patches or total_scores.shape[0] != imgs.shape[0]:
             raise ValueError(f"total_scores must be [N,{c.num_patches}], got {tuple(total_scores.shape)}")
 
-    def _alloc_outputs(self, N, dev, encoder=True, rate=True, extra=False):
+    def _alloc_outputs(self, N, dev, encoder=True, rate=True, extra=False, indexes=False):
+        """Every output of one call is a view into ONE fresh allocation (a single caching-allocator request per forward
+        instead of 11-15: it matters at the batch-1 `testing.py` configuration)."""
         c = self.cfg
         s, s4 = c.side, c.side // 4
-        t: Dict[str, torch.Tensor] = {}
+        spec = []          # (name, shape, dtype)
+        f32, i32, i64, f64 = torch.float32, torch.int32, torch.int64, torch.float64
         if rate:
-            t["y_likelihoods"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.float32, device=dev)
-            t["z_likelihoods"] = torch.empty((N, s4, s4, c.hyperprior_depth), dtype=torch.float32, device=dev)
-            t["y_symbols"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.int32, device=dev)
-            t["z_symbols"] = torch.empty((N, s4, s4, c.hyperprior_depth), dtype=torch.int32, device=dev)
-            t["y_hat"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.float32, device=dev)
-            t["z_hat"] = torch.empty((N, s4, s4, c.hyperprior_depth), dtype=torch.float32, device=dev)
-            t["bpp"] = torch.empty((N,), dtype=torch.float32, device=dev)
-            t["rate_sums"] = torch.empty((2,), dtype=torch.float64, device=dev)
+            spec += [("y_likelihoods", (N, s, s, c.latent_depth), f32), ("z_likelihoods", (N, s4, s4, c.hyperprior_depth), f32),
+                     ("y_symbols", (N, s, s, c.latent_depth), i32), ("z_symbols", (N, s4, s4, c.hyperprior_depth), i32),
+                     ("y_hat", (N, s, s, c.latent_depth), f32), ("z_hat", (N, s4, s4, c.hyperprior_depth), f32),
+                     ("bpp", (N,), f32), ("rate_sums", (2,), f64)]
+            if indexes:
+                spec += [("y_indexes", (N, s, s, c.latent_depth), i32)]
             if extra:
-                t["y"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.float32, device=dev)
-                t["z"] = torch.empty((N, s4, s4, c.hyperprior_depth), dtype=torch.float32, device=dev)
-                t["mu"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.float32, device=dev)
-                t["sigma"] = torch.empty((N, s, s, c.latent_depth), dtype=torch.float32, device=dev)
+                spec += [("y", (N, s, s, c.latent_depth), f32), ("z", (N, s4, s4, c.hyperprior_depth), f32),
+                         ("mu", (N, s, s, c.latent_depth), f32), ("sigma", (N, s, s, c.latent_depth), f32)]
         if encoder:
-            t["ids_shuffle"] = torch.empty((N, c.num_patches), dtype=torch.int64, device=dev)
-            t["ids_restore"] = torch.empty((N, c.num_patches), dtype=torch.int64, device=dev)
-            t["ids_keep"] = torch.empty((N, c.num_keep_patches), dtype=torch.int64, device=dev)
+            spec += [("ids_shuffle", (N, c.num_patches), i64), ("ids_restore", (N, c.num_patches), i64),
+                     ("ids_keep", (N, c.num_keep_patches), i64)]
             if extra or not rate:
-                t["x_remain"] = torch.empty((N, c.num_keep_patches, c.encoder_embed_dim), dtype=torch.float32, device=dev)
+                spec += [("x_remain", (N, c.num_keep_patches, c.encoder_embed_dim), f32)]
+        sizes = []
+        for _, shape, dt in spec:
+            n = 1
+            for d in shape:
+                n *= d
+            sizes.append((n * dt.itemsize + 255) // 256 * 256)
+        arena = torch.empty((sum(sizes),), dtype=torch.uint8, device=dev)
+        t: Dict[str, torch.Tensor] = {}
+        off = 0
+        for (name, shape, dt), sz in zip(spec, sizes):
+            n = 1
+            for d in shape:
+                n *= d
+            t[name] = arena[off: off + n * dt.itemsize].view(dt).view(shape)
+            off += sz
         o = _native.TmaeOutputs()
         for k, v in t.items():
             setattr(o, k, v.data_ptr())
         return t, o
+
+    def _enter_stream(self, dev, stream=None):
+        """One handle owns one workspace, one device IoBlock and one captured graph, so its calls must be ordered: when
+        a call arrives on a different stream than the previous one, the new stream first waits for that call's event."""
+        cur = stream or torch.cuda.current_stream(dev)
+        if self._last_stream is not None and self._last_stream != cur:
+            cur.wait_event(self._last_event)
+        return cur
+
+    def _leave_stream(self, cur):
+        if self._last_event is None:
+            self._last_event = torch.cuda.Event()
+        self._last_event.record(cur)
+        self._last_stream = cur
 
     @staticmethod
     def _nchw(t):          # channels-last storage viewed with the reference's [N,C,h,w] shape
@@ -199,31 +252,52 @@ class MCM(nn.Module):
         for k in ("ids_restore", "ids_keep", "ids_shuffle", "x_remain"):
             if k in t:
                 out[k] = t[k]
-        for k in ("y", "z", "mu", "sigma"):
+        for k in ("y", "z", "mu", "sigma", "y_indexes"):
             if k in t:
                 out[k] = self._nchw(t[k])
         return out
 
     # ------------------------------------------------------------------ the path
+    def _native_forward(self, imgs, total_scores, indexes=False):
+        """imgs / scores on the handle's device -> dict of channels-last result tensors (one C-ABI call)."""
+        dev = self._handle_device
+        N = imgs.shape[0]
+        lib = _native.load()
+        with torch.cuda.device(dev):
+            t, o = self._alloc_outputs(N, dev, extra=self.extra_outputs, indexes=indexes)
+            cur = self._enter_stream(dev)
+            _native.check(lib.tmae_forward(self._handle, C.c_void_p(imgs.data_ptr()), C.c_void_p(total_scores.data_ptr()),
+                                           N, C.byref(o), C.c_void_p(cur.cuda_stream)), self._handle, RuntimeError)
+            self._leave_stream(cur)
+        return t
+
     @torch.no_grad()
-    def forward(self, imgs: torch.Tensor, total_scores: torch.Tensor, need_recon: bool = False):
-        """MCM.forward (MCM.py:714-803), rate half."""
-        if need_recon:
-            raise NotImplementedError("reconstruction (g_s, MAE decoder, losses) is outside the compression forward "
-                                      "path of this library (SURVEY 8f-2)")
+    def forward(self, imgs: torch.Tensor, total_scores: torch.Tensor, need_recon: Optional[bool] = None):
+        """MCM.forward (MCM.py:714-803).  The rate half runs in the library; with `need_recon` (default: whenever the
+        decoder-side weights are loaded) the reconstruction half follows in stock PyTorch and the dict also carries
+        the reference's "loss" 3-tuple and "x_hat"."""
+        if need_recon is None:
+            need_recon = recon.has_decoder_weights(self._weights)
+        if need_recon and not recon.has_decoder_weights(self._weights):
+            raise RuntimeError("need_recon=True but the loaded state dict has no g_s / decoder tensors")
         self._ensure_handle()
         dev = self._handle_device
         self._check_inputs(imgs, total_scores)
         imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
         total_scores = total_scores.to(device=dev, dtype=torch.float32).contiguous()
+        t = self._native_forward(imgs, total_scores)
+        out = self._pack_result(t)
+        if need_recon:
+            self._add_recon(out, t, imgs)
+        return out
+
+    def _add_recon(self, out, t, imgs):
+        c = self.cfg
         N = imgs.shape[0]
-        lib = _native.load()
-        with torch.cuda.device(dev):
-            t, o = self._alloc_outputs(N, dev, extra=self.extra_outputs)
-            st = torch.cuda.current_stream(dev).cuda_stream
-            _native.check(lib.tmae_forward(self._handle, C.c_void_p(imgs.data_ptr()), C.c_void_p(total_scores.data_ptr()),
-                                           N, C.byref(o), C.c_void_p(st)), self._handle, RuntimeError)
-        return self._pack_result(t)
+        y_hat_tokens = t["y_hat"].reshape(N, c.num_keep_patches, c.latent_depth)      # NHWC == token matrix
+        loss, x_hat = recon.reconstruct(self._weights, c, y_hat_tokens, t["ids_restore"], imgs, self.feature_loss)
+        out["loss"] = loss
+        out["x_hat"] = x_hat
 
     @torch.no_grad()
     def forward_encoder(self, imgs, total_scores) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -238,10 +312,11 @@ class MCM(nn.Module):
         lib = _native.load()
         with torch.cuda.device(dev):
             t, o = self._alloc_outputs(N, dev, encoder=True, rate=False)
-            st = torch.cuda.current_stream(dev).cuda_stream
+            cur = self._enter_stream(dev)
             _native.check(lib.tmae_forward_encoder(self._handle, C.c_void_p(imgs.data_ptr()),
-                                                   C.c_void_p(total_scores.data_ptr()), N, C.byref(o), C.c_void_p(st)),
-                          self._handle, RuntimeError)
+                                                   C.c_void_p(total_scores.data_ptr()), N, C.byref(o),
+                                                   C.c_void_p(cur.cuda_stream)), self._handle, RuntimeError)
+            self._leave_stream(cur)
         self._last_encoder = t
         return t["x_remain"], t["ids_restore"]
 
@@ -255,17 +330,32 @@ class MCM(nn.Module):
         lib = _native.load()
         with torch.cuda.device(dev):
             t, o = self._alloc_outputs(N, dev, encoder=False, rate=True, extra=True)
-            st = torch.cuda.current_stream(dev).cuda_stream
+            cur = self._enter_stream(dev)
             _native.check(lib.tmae_forward_from_latent(self._handle, C.c_void_p(y.data_ptr()), N, C.byref(o),
-                                                       C.c_void_p(st)), self._handle, RuntimeError)
+                                                       C.c_void_p(cur.cuda_stream)), self._handle, RuntimeError)
+            self._leave_stream(cur)
         return self._pack_result(t)
 
+    def host_result_buffers(self, N: int) -> Dict[str, torch.Tensor]:
+        """Pinned host buffers for `forward_host`: what the reference's forward hands its caller (likelihoods,
+        MCM.py:801) + int16 symbols + ids_restore + per-image bpp."""
+        c = self.cfg
+        s, s4 = c.side, c.side // 4
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        return {"bpp": mk((N,), torch.float32), "rate_sums": mk((2,), torch.float64),
+                "y_likelihoods": mk((N, s, s, c.latent_depth), torch.float32),
+                "z_likelihoods": mk((N, s4, s4, c.hyperprior_depth), torch.float32),
+                "y_symbols": mk((N, s, s, c.latent_depth), torch.int16),
+                "z_symbols": mk((N, s4, s4, c.hyperprior_depth), torch.int16),
+                "ids_restore": mk((N, c.num_patches), torch.int64)}
+
     @torch.no_grad()
-    def forward_host(self, imgs_cpu: torch.Tensor, scores_cpu: torch.Tensor, bpp_out: Optional[torch.Tensor] = None,
-                     stream: Optional[torch.cuda.Stream] = None):
-        """End-to-end call with HOST buffers (pinned for full speed): H2D copies, forward and the D2H read of the
-        per-image bpp are all enqueued on `stream`; returns the (pinned) CPU bpp tensor - valid after the stream
-        is synchronised."""
+    def forward_host(self, imgs_cpu: torch.Tensor, scores_cpu: torch.Tensor, result: Optional[Dict[str, torch.Tensor]] = None,
+                     stream: Optional[torch.cuda.Stream] = None) -> Dict[str, torch.Tensor]:
+        """End-to-end call with HOST buffers (pinned for full speed): H2D copies, the forward and the D2H read of the
+        results - likelihoods, int16 symbols, ids_restore, per-image bpp - are all enqueued on `stream`.  `result` is a
+        dict of host tensors (see `host_result_buffers`; a subset is fine, e.g. {"bpp": ...}); returned as is, valid
+        after the stream is synchronised."""
         self._ensure_handle()
         dev = self._handle_device
         if imgs_cpu.device.type != "cpu" or scores_cpu.device.type != "cpu":
@@ -274,15 +364,21 @@ class MCM(nn.Module):
         imgs_cpu = imgs_cpu.contiguous()
         scores_cpu = scores_cpu.contiguous()
         N = imgs_cpu.shape[0]
-        if bpp_out is None:
-            bpp_out = torch.empty((N,), dtype=torch.float32).pin_memory()
+        if result is None:
+            result = self.host_result_buffers(N)
+        ho = _native.TmaeHostOutputs()
+        for k, v in result.items():
+            if k not in _native.HOST_OUTPUT_FIELDS:
+                raise KeyError(f"unknown host result '{k}'")
+            setattr(ho, k, v.data_ptr())
         lib = _native.load()
         with torch.cuda.device(dev):
-            st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+            cur = self._enter_stream(dev, stream)
             _native.check(lib.tmae_forward_host(self._handle, C.c_void_p(imgs_cpu.data_ptr()),
-                                                C.c_void_p(scores_cpu.data_ptr()), N, C.c_void_p(bpp_out.data_ptr()),
-                                                None, None, C.c_void_p(st)), self._handle, RuntimeError)
-        return bpp_out
+                                                C.c_void_p(scores_cpu.data_ptr()), N, C.byref(ho), None,
+                                                C.c_void_p(cur.cuda_stream)), self._handle, RuntimeError)
+            self._leave_stream(cur)
+        return result
 
     @torch.no_grad()
     def get_ids_shuffle(self, total_scores: torch.Tensor) -> torch.Tensor:
@@ -325,11 +421,63 @@ class MCM(nn.Module):
         target = torch.tensor([-t, 0.0, t], device=q.device, dtype=q.dtype)
         return torch.abs(logits - target).sum()
 
-    def update(self, *args, **kwargs):
-        raise NotImplementedError("CDF-table construction for rANS coding is outside this path (SURVEY 8f-1)")
+    @staticmethod
+    def get_scale_table(min_scale: float = 0.11, max_scale: float = 256.0, levels: int = 64) -> torch.Tensor:
+        """compressai.models.utils / google.get_scale_table: the table `CompressionModel.update()` installs when
+        called without one (testing.py:223 `model.update(force=True)`)."""
+        import math
+        return torch.exp(torch.linspace(math.log(min_scale), math.log(max_scale), levels))
+
+    def update(self, scale_table=None, force: bool = False):
+        """The part of `CompressionModel.update(scale_table, force)` that the symbol / index emission needs: install the
+        GaussianConditional scale table (default `get_scale_table()`).  Building the quantised CDF tables for the range
+        coder is compressai's C++ `pmf_to_quantized_cdf` - outside this library."""
+        self._scale_table = (self.get_scale_table() if scale_table is None else torch.as_tensor(scale_table)).float().contiguous()
+        self._scale_table_dirty = True
+        return True
+
+    @torch.no_grad()
+    def compress_symbols(self, imgs: torch.Tensor, total_scores: torch.Tensor):
+        """Front half of `MCM.compress` (MCM.py:805-873), everything up to the `encode_with_indexes` call:
+            "y_symbols", "y_indexes": i32 [N, Cy*s*s]  - per image, slice by slice in (c, y, x) order, exactly the lists the
+                          reference extends per slice (MCM.py:872-873) and passes to the coder (:882-884);
+                          indexes = GaussianConditional.build_indexes(sigma) (:867)
+            "z_symbols": i32 [N, Cz, s/4, s/4], "z_indexes": i32 [same] - what `entropy_bottleneck.compress(z)` codes
+                          (:827): quantize(z, "symbols", medians) and the channel index of every element
+            "shape": z spatial size (:890), "ids_restore" (:891)
+        The range coder itself (compressai's C++ rANS) is not part of this library."""
+        if self._scale_table is None:
+            self.update()
+        self._ensure_handle()
+        dev = self._handle_device
+        lib = _native.load()
+        if getattr(self, "_scale_table_dirty", True):
+            tab = self._scale_table
+            with torch.cuda.device(dev):
+                _native.check(lib.tmae_set_scale_table(self._handle, C.c_void_p(tab.data_ptr()), tab.numel()), self._handle)
+            self._scale_table_dirty = False
+        self._check_inputs(imgs, total_scores)
+        imgs = imgs.to(device=dev, dtype=torch.float32).contiguous()
+        total_scores = total_scores.to(device=dev, dtype=torch.float32).contiguous()
+        t = self._native_forward(imgs, total_scores, indexes=True)
+        c = self.cfg
+        N, s, s4 = imgs.shape[0], c.side, c.side // 4
+        packed = torch.empty((2, N, c.latent_depth * s * s), dtype=torch.int32, device=dev)
+        zpacked = torch.empty((N, c.hyperprior_depth, s4, s4), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            for k, name in enumerate(("y_symbols", "y_indexes")):
+                _native.check(lib.tmae_pack_nchw_i32(C.c_void_p(t[name].data_ptr()), C.c_void_p(packed[k].data_ptr()), N, s * s,
+                                                     c.latent_depth, st))
+            _native.check(lib.tmae_pack_nchw_i32(C.c_void_p(t["z_symbols"].data_ptr()), C.c_void_p(zpacked.data_ptr()), N, s4 * s4,
+                                                 c.hyperprior_depth, st))
+        z_idx = torch.arange(c.hyperprior_depth, dtype=torch.int32, device=dev).view(1, -1, 1, 1).expand(N, -1, s4, s4)
+        return {"y_symbols": packed[0], "y_indexes": packed[1], "z_symbols": zpacked, "z_indexes": z_idx,
+                "shape": (s4, s4), "ids_restore": t["ids_restore"], "bpp": t["bpp"]}
 
     def compress(self, *args, **kwargs):
-        raise NotImplementedError("bitstream emission is outside this path (north_star; SURVEY 8f-1)")
+        raise NotImplementedError("bitstream emission (compressai's C++ rANS coder) is outside this library; "
+                                  "compress_symbols() returns the symbol / index lists the coder consumes (SURVEY 8f-1)")
 
     def decompress(self, *args, **kwargs):
         raise NotImplementedError("bitstream decoding is outside this path (SURVEY 8f-1)")
@@ -345,7 +493,7 @@ class MCM(nn.Module):
         n = C.c_int(0)
         _native.check(_native.load().tmae_profile_read(self._handle, arr, 16, C.byref(n)), self._handle, RuntimeError)
         return [{"name": arr[i].name.decode(), "launches": arr[i].launches, "ms": arr[i].ms, "flops": arr[i].flops,
-                 "bytes": arr[i].bytes} for i in range(n.value)]
+                 "bytes": arr[i].bytes, "mma_flops": arr[i].mma_flops} for i in range(n.value)]
 
     def profile_read_steps(self):
         arr = (_native.TmaeProfileStep * 512)()

@@ -69,9 +69,52 @@ def _conv(sd, name, cout, cin, k, gen, gain=1.0):
     sd[name + ".bias"] = _uniform(gen, (cout,), 0.05)
 
 
-def make_state_dict(cfg: PathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """fp32 CPU tensors keyed by the reference's parameter names (hot-path subset)."""
+def make_decoder_state_dict(cfg: PathConfig, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Reconstruction-side tensors of the reference state dict: g_s (MCM.py:96-112, ConvTranspose2d
+    1x1: weight [cin, cout, 1, 1]), decoder_embed / mask_token / decoder_pos_embed / decoder_blocks / decoder_norm /
+    decoder_pred (MCM.py:325-354).  Drawn from its own generator so the hot-path tensors of `make_state_dict` (and the
+    goldens frozen from them) do not depend on whether the decoder is requested."""
+    g = torch.Generator().manual_seed(seed + 10007)
+    sd: Dict[str, torch.Tensor] = {}
+    E, Dd = cfg.encoder_embed_dim, cfg.decoder_embed_dim
+    ch = cfg.g_a_channels()                                   # [E, c1, c2, Dd, Cy]; g_s walks it backwards
+    gs = [ch[4], ch[3], ch[2], ch[1], ch[0]]
+    for li, idx in enumerate((0, 2, 4, 6)):
+        cin, cout = gs[li], gs[li + 1]
+        bound = GAIN * math.sqrt(3.0 / cin)
+        sd[f"g_s.{idx}.weight"] = _uniform(g, (cin, cout, 1, 1), bound)
+        sd[f"g_s.{idx}.bias"] = _uniform(g, (cout,), 0.05)
+    sd["g_s.0.weight"] *= 0.3                                  # y_hat has a std of a few bins
+    _linear(sd, "decoder_embed", Dd, E, g)
+    sd["mask_token"] = torch.randn(1, 1, Dd, generator=g) * 0.02
+    sd["decoder_pos_embed"] = sincos_pos_embed(Dd, cfg.grid)
+    hidden = int(Dd * cfg.mlp_ratio)
+    for i in range(cfg.decoder_depth):
+        pre = f"decoder_blocks.{i}"
+        sd[pre + ".norm1.weight"] = 1.0 + _uniform(g, (Dd,), 0.1)
+        sd[pre + ".norm1.bias"] = _uniform(g, (Dd,), 0.05)
+        _linear(sd, pre + ".attn.qkv", 3 * Dd, Dd, g)
+        sd[pre + ".attn.qkv.weight"] *= 2.0
+        _linear(sd, pre + ".attn.proj", Dd, Dd, g)
+        sd[pre + ".norm2.weight"] = 1.0 + _uniform(g, (Dd,), 0.1)
+        sd[pre + ".norm2.bias"] = _uniform(g, (Dd,), 0.05)
+        _linear(sd, pre + ".mlp.fc1", hidden, Dd, g)
+        _linear(sd, pre + ".mlp.fc2", Dd, hidden, g)
+    sd["decoder_norm.weight"] = 1.0 + _uniform(g, (Dd,), 0.1)
+    sd["decoder_norm.bias"] = _uniform(g, (Dd,), 0.05)
+    _linear(sd, "decoder_pred", cfg.patch_size ** 2 * cfg.in_chans, Dd, g)
+    sd["decoder_pred.bias"] = sd["decoder_pred.bias"] + 0.5    # predictions centred in the [0, 1] pixel range
+    return sd
+
+
+def make_state_dict(cfg: PathConfig, seed: int = 0, include_decoder: bool = False) -> Dict[str, torch.Tensor]:
+    """fp32 CPU tensors keyed by the reference's parameter names (hot-path subset; + the reconstruction side when
+    `include_decoder`)."""
     cfg.validate()
+    if include_decoder:
+        sd = make_state_dict(cfg, seed)
+        sd.update(make_decoder_state_dict(cfg, seed))
+        return sd
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     C, D = cfg.encoder_embed_dim, cfg.encoder_depth
