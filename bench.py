@@ -437,18 +437,18 @@ def run_b200(args, kwargs, batch_named, desc, wl, kind):
             traffic = None
     exec_flops_step = 0.0
     if gemm and gemm["ms"] > 0:
-        exec_flops_step = gemm["flops"] / 2.0                  # the profile ran 2 forwards
-        mma_flops_step = gemm["mma_flops"] / 2.0
+        exec_flops_step = gemm["flops"]                        # the library keeps the events of the LAST forward it profiled
+        mma_flops_step = gemm["mma_flops"]
         achieved = gemm["mma_flops"] / (gemm["ms"] * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv engine)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": traffic, "traffic_note": "bytes per launch, ncu dram__bytes_read+write averaged over the gemm_tc launches of "
                     "one forward (profiles/r02_launches_*.json, --cache-control none); null until that capture exists",
                     "flops": "EXECUTED tensor-core flops (patch embed counts the K kept patches; precise layers count their 3 terms)",
-                    "executed_flops_per_launch": mma_flops_step / (gemm["launches"] / 2.0),
+                    "executed_flops_per_launch": mma_flops_step / gemm["launches"],
                     "useful_frac": gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 / peak,
                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (of measured)",
-                    "launches_per_step": gemm["launches"] // 2, "avg_launch_us": gemm["ms"] * 1e3 / gemm["launches"],
+                    "launches_per_step": gemm["launches"], "avg_launch_us": gemm["ms"] * 1e3 / gemm["launches"],
                     "share_of_step": gemm["ms"] / tot_ms,
                     "timing": "CUDA events around each run of consecutive gemm_tc launches, inside the library, on the launching stream; "
                               "isolated = one stream, plain launches",
@@ -462,11 +462,11 @@ def run_b200(args, kwargs, batch_named, desc, wl, kind):
                     "step_aggregate": {"achieved": mma_flops_step * world / (ms_max / args.steps * 1e-3) / 1e12 / world,
                                        "frac": mma_flops_step / (ms_max / args.steps * 1e-3) / 1e12 / peak,
                                        "note": "executed flops of one step / ms_per_step of the timed region (CUDA graph + S streams)"},
-                    "families": {f["name"]: {"ms": round(f["ms"] / 2, 4), "launches": f["launches"] // 2} for f in fams}}
+                    "families": {f["name"]: {"ms": round(f["ms"], 4), "launches": f["launches"]} for f in fams}}
 
     # memory-bound kernel families against the measured HBM peak (algorithmic bytes / per-launch event time; these
     # launches move 0.1-19 MB each, i.e. they are launch-latency bound at batch 64 - SURVEY 8d)
-    hbm_kernels = {f["name"]: {"GB/s": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1), "launches": f["launches"] // 2,
+    hbm_kernels = {f["name"]: {"GB/s": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9, 1), "launches": f["launches"],
                                "MB_per_launch": round(f["bytes"] / f["launches"] / 1e6, 3),
                                "frac_of_hbm_peak": round(f["bytes"] / (f["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)}
                    for f in fams_launch if f["bytes"] > 0 and f["ms"] > 0}
@@ -506,7 +506,8 @@ def run_b200(args, kwargs, batch_named, desc, wl, kind):
             "metric": "images/s masked-ViT encode+rate", "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "bf16" if args.precise is None else "bf16x3 (split-bf16 operands, fp32-equivalent products)",
+            "dtype": "bf16" if args.precise is None else ("bf16x6 (three bf16 planes per operand, fp32-exact products)" if args.precise.endswith("x6")
+                                                           else "bf16x3 (two bf16 planes per operand, ~2^-17 products)"),
             "data": "kodak (tests/golden fixtures)" if kind == "kodak" else "synthetic",
             "config": {"workload": desc, "name": wl, "per_gpu_batch": batch, "global_batch": global_batch,
                        "parallelism": f"dp{world} (images sharded, weights replicated, 16-byte rate all-reduce)",
@@ -535,7 +536,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="B64", choices=sorted(WORKLOADS))
-    ap.add_argument("--precise", default=None, choices=["all", "rate"],
+    ap.add_argument("--precise", default=None, choices=["all", "rate", "all-x6", "rate-x6"],
                     help="accuracy mode: split-bf16 operands for the rate half / the whole path (symbols match the fp32 reference)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the workload's batch per GPU; strong: the workload's batch is the global batch, sharded over the GPUs")

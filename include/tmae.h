@@ -73,6 +73,8 @@ typedef struct {
  * arithmetic up to rounding-boundary ties (north_star; MCM.py:735, 761-783). */
 #define TMAE_FLAG_PRECISE_RATE  8u   /* g_a, h_a, h_s_*, cc_transform_*, lrp_transform: everything after the encoder */
 #define TMAE_FLAG_PRECISE_ALL   16u  /* the encoder as well (patch embed, Block linears, fp32 softmax attention) */
+#define TMAE_FLAG_PRECISE_X6    32u  /* with either of the above: three bf16 planes per operand (24 mantissa bits = fp32
+                                        carried exactly) and six terms per product - fp32-equivalent arithmetic */
 
 /* Outputs of one forward; any pointer may be NULL (that output is skipped).
  * N = batch, L = (img/patch)^2, K = num_keep_patches, s = sqrt(K), Cy = latent_depth, Cz = hyperprior_depth. */
@@ -152,6 +154,11 @@ TMAE_API int  tmae_forward_host(tmae_handle* h, const float* h_imgs, const float
 /* Teacher-forced entry for parity tests: run the rate half only (MCM.py:739-787) from a given latent
  * y f32 [N, s, s, Cy]. */
 TMAE_API int  tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_outputs* out, void* stream);
+/* Slice-wise teacher forcing for parity tests: as above, but every slice reads the GIVEN y_hat f32 [N, s, s, Cy] (the
+ * reference's) as the support of the slices before it (MCM.py:756-761, 780) instead of this run's own, so one
+ * rounding-boundary flip cannot cascade through mu of the later slices. */
+TMAE_API int  tmae_forward_from_latent_forced(tmae_handle* h, const float* y, const float* y_hat_support, int N,
+                                     const tmae_outputs* out, void* stream);
 /* Encoder only (MCM.forward_encoder, MCM.py:590-634): fills out->x_remain / ids_*. */
 TMAE_API int  tmae_forward_encoder(tmae_handle* h, const float* imgs, const float* scores, int N,
                           const tmae_outputs* out, void* stream);
@@ -179,12 +186,12 @@ TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, fl
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
                        int Cin, int Cout, int gelu, int impl, void* stream);
 
-/* The same two self-tests in the precise configuration (TMAE_FLAG_PRECISE_*): fp32 operands, split into (hi, lo) bf16
- * planes inside, three tensor-core terms per product, fp32 accumulate -> results agree with an fp32 GEMM / conv to ~1e-5. */
+/* The same two self-tests in the precise configurations (TMAE_FLAG_PRECISE_*): fp32 operands, split into `planes` bf16
+ * planes inside (2: three tensor-core terms per product, ~1e-5 of an fp32 GEMM / conv; 3: six terms, fp32-equivalent). */
 TMAE_API int  tmae_gemm_split(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,
-                     int block_n, int impl, void* stream);
+                     int block_n, int planes, int impl, void* stream);
 TMAE_API int  tmae_conv3x3_split(const float* x, const float* w, const float* bias, float* out, int N, int s,
-                        int Cin, int Cout, int gelu, int impl, void* stream);
+                        int Cin, int Cout, int gelu, int planes, int impl, void* stream);
 
 /* Per-kernel-family device timing (bench.py roofline): enable = 1 brackets every launch of tmae_forward with CUDA
  * events on `stream`; enable = 2 brackets every RUN of consecutive launches of one kernel family (keeps the

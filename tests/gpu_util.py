@@ -36,24 +36,24 @@ def conv3x3(x_nhwc_bf16, w, bias, gelu=False, impl=0):
     return out
 
 
-def gemm_split(A_f32, B_f32, bias, block_n=0, impl=0):
+def gemm_split(A_f32, B_f32, bias, block_n=0, impl=0, planes=2):
     """Precise engine configuration: fp32 operands, split-bf16 planes, three tensor-core terms per product."""
     M, K = A_f32.shape
     N = B_f32.shape[0]
     out = torch.zeros(M, N, dtype=torch.float32, device=A_f32.device)
     rc = _native.load().tmae_gemm_split(ptr(A_f32.contiguous()), ptr(B_f32.contiguous()), ptr(bias), ptr(out), M, N, K, block_n,
-                                        impl, stream())
+                                        planes, impl, stream())
     _native.check(rc, None, RuntimeError)
     torch.cuda.synchronize()
     return out
 
 
-def conv3x3_split(x_nhwc_f32, w, bias, gelu=False, impl=0):
+def conv3x3_split(x_nhwc_f32, w, bias, gelu=False, impl=0, planes=2):
     N, s, _, Cin = x_nhwc_f32.shape
     Cout = w.shape[0]
     out = torch.zeros(N, s, s, Cout, dtype=torch.float32, device=w.device)
     rc = _native.load().tmae_conv3x3_split(ptr(x_nhwc_f32.contiguous()), ptr(w.contiguous()), ptr(bias), ptr(out), N, s,
-                                           Cin, Cout, 1 if gelu else 0, impl, stream())
+                                           Cin, Cout, 1 if gelu else 0, planes, impl, stream())
     _native.check(rc, None, RuntimeError)
     torch.cuda.synchronize()
     return out

@@ -54,23 +54,29 @@ def test_conv3x3_matches_torch(cuda_dev, N, s, Cin, Cout, gelu, impl):
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 224, 384, 0), (1000, 2304, 768, 256), (4160, 768, 3072, 0),
                                        (257, 80, 176, 0), (130, 32, 80, 32)])
 @pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
-def test_gemm_split_matches_fp64(cuda_dev, M, N, K, bn, impl):
+@pytest.mark.parametrize("planes", [2, 3])
+def test_gemm_split_matches_fp64(cuda_dev, M, N, K, bn, impl, planes):
     g = torch.Generator(device="cpu").manual_seed(M + N + K + 7)
     A = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev)
     B = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev)
     bias = torch.randn(N, generator=g).to(cuda_dev)
     ref = (A.double() @ B.double().t() + bias.double())
-    out = G.gemm_split(A, B, bias, block_n=bn, impl=impl)
+    out = G.gemm_split(A, B, bias, block_n=bn, impl=impl, planes=planes)
     err = G.rel_err(out, ref)
     bf16_err = G.rel_err(A.bfloat16().double() @ B.bfloat16().double().t() + bias.double(), ref)
-    assert err < 2e-5 and err < bf16_err / 50, f"impl={impl} rel err {err} (plain bf16 operands: {bf16_err})"
+    fp32_err = G.rel_err(A @ B.t() + bias, ref)                    # what plain fp32 arithmetic gives on the same operands
+    if planes == 2:
+        assert err < 2e-5 and err < bf16_err / 50, f"impl={impl} rel err {err} (plain bf16 operands: {bf16_err})"
+    else:                                                          # three planes carry fp32 exactly: fp32-level error
+        assert err < 1e-6 and err < 4 * fp32_err + 2e-7, f"impl={impl} rel err {err} (torch fp32: {fp32_err})"
 
 
 @pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (5, 8, 80, 32, False),
                                                   (1, 16, 576, 224, True), (7, 12, 64, 48, False), (40, 2, 192, 96, False),
                                                   (64, 8, 352, 224, True), (40, 6, 128, 64, True), (21, 4, 64, 48, False)])
 @pytest.mark.parametrize("impl", [1, 0], ids=["checker", "tcgen05"])
-def test_conv3x3_split_matches_fp64(cuda_dev, N, s, Cin, Cout, gelu, impl):
+@pytest.mark.parametrize("planes", [2, 3])
+def test_conv3x3_split_matches_fp64(cuda_dev, N, s, Cin, Cout, gelu, impl, planes):
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin + 3)
     x = torch.randn(N, s, s, Cin, generator=g).to(cuda_dev)
     w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))).to(cuda_dev)
@@ -79,6 +85,6 @@ def test_conv3x3_split_matches_fp64(cuda_dev, N, s, Cin, Cout, gelu, impl):
     if gelu:
         ref = F.gelu(ref)
     ref = ref.permute(0, 2, 3, 1)
-    out = G.conv3x3_split(x, w, b, gelu=gelu, impl=impl)
+    out = G.conv3x3_split(x, w, b, gelu=gelu, impl=impl, planes=planes)
     err = G.rel_err(out, ref)
-    assert err < 2e-5, f"impl={impl} rel err {err}"
+    assert err < (2e-5 if planes == 2 else 1e-6), f"impl={impl} planes={planes} rel err {err}"

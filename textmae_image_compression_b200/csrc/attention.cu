@@ -213,7 +213,7 @@ attention_f32_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_lo, __
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t ld = (size_t)3 * C;
     const __nv_bfloat16* base = qkv + (size_t)n * T * ld + (size_t)h * HD;
-    auto ldf = [&](const __nv_bfloat16* p) { return __bfloat162float(p[0]) + __bfloat162float(p[qkv_lo]); };
+    auto ldf = [&](const __nv_bfloat16* p) { return load_bf16_planes(p, qkv_lo); };
     for (int e = tid; e < T * HD; e += blockDim.x) {
         const int key = e / HD, d = e - key * HD;
         sK[key * KP32 + d] = ldf(base + (size_t)key * ld + C + d);
@@ -254,11 +254,8 @@ attention_f32_kernel(const __nv_bfloat16* __restrict__ qkv, long long qkv_lo, __
         const float inv = 1.f / sum;
         o0 *= inv; o1 *= inv;
         __nv_bfloat16* dst = out + ((size_t)n * T + q) * C + (size_t)h * HD;
-        const __nv_bfloat16 h0 = __float2bfloat16(o0), h1 = __float2bfloat16(o1);
-        dst[lane] = h0;
-        dst[lane + 32] = h1;
-        dst[out_lo + lane] = __float2bfloat16(o0 - __bfloat162float(h0));
-        dst[out_lo + lane + 32] = __float2bfloat16(o1 - __bfloat162float(h1));
+        store_bf16_planes(dst + lane, out_lo, o0);
+        store_bf16_planes(dst + lane + 32, out_lo, o1);
         __syncwarp();
     }
 }

@@ -38,6 +38,54 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Store 4 consecutive bf16 outputs, as 1, 2 or 3 planes.  `lo_off` encodes the plane layout of the destination buffer:
+//   0  one plane (plain bf16);  > 0  two planes (hi, lo) `lo_off` elements apart (split-bf16, 16 mantissa bits);
+//   < 0  three planes (hi, mid, lo) `-lo_off` elements apart (24 mantissa bits: fp32 carried exactly).
+__device__ __forceinline__ void store_bf16x4_planes(__nv_bfloat16* dst, long long lo_off, float v0, float v1, float v2, float v3) {
+    if (lo_off == 0) {
+        uint2 pk;
+        pk.x = pack_bf16x2(v0, v1);
+        pk.y = pack_bf16x2(v2, v3);
+        *reinterpret_cast<uint2*>(dst) = pk;
+        return;
+    }
+    const long long stride = lo_off > 0 ? lo_off : -lo_off;
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+    const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+    const float r0 = v0 - f0.x, r1 = v1 - f0.y, r2 = v2 - f1.x, r3 = v3 - f1.y;       // exact in fp32
+    const __nv_bfloat162 m0 = __floats2bfloat162_rn(r0, r1), m1 = __floats2bfloat162_rn(r2, r3);
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&h0); pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(dst) = pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&m0); pk.y = *reinterpret_cast<const uint32_t*>(&m1);
+    *reinterpret_cast<uint2*>(dst + stride) = pk;
+    if (lo_off < 0) {
+        const float2 g0 = __bfloat1622float2(m0), g1 = __bfloat1622float2(m1);
+        pk.x = pack_bf16x2(r0 - g0.x, r1 - g0.y);
+        pk.y = pack_bf16x2(r2 - g1.x, r3 - g1.y);
+        *reinterpret_cast<uint2*>(dst + 2 * stride) = pk;
+    }
+}
+// scalar form of the same layout
+__device__ __forceinline__ void store_bf16_planes(__nv_bfloat16* dst, long long lo_off, float v) {
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    dst[0] = h;
+    if (lo_off == 0) return;
+    const long long stride = lo_off > 0 ? lo_off : -lo_off;
+    const float r = v - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16(r);
+    dst[stride] = m;
+    if (lo_off < 0) dst[2 * stride] = __float2bfloat16(r - __bfloat162float(m));
+}
+// sum of the planes of one element (precise attention reads q, k, v this way)
+__device__ __forceinline__ float load_bf16_planes(const __nv_bfloat16* src, long long lo_off) {
+    float v = __bfloat162float(src[0]);
+    if (lo_off == 0) return v;
+    const long long stride = lo_off > 0 ? lo_off : -lo_off;
+    v += __bfloat162float(src[stride]);
+    if (lo_off < 0) v += __bfloat162float(src[2 * stride]);
+    return v;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

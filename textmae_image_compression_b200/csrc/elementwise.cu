@@ -40,18 +40,7 @@ gather_patches_kernel(const float* __restrict__ imgs, const int64_t* __restrict_
         const int p = rem / patch, q = rem - p * patch;
         const float4 v = __ldg(reinterpret_cast<const float4*>(
             imgs + (((size_t)n * in_chans + c) * S + (py * patch + p)) * S + px * patch + q));
-        if (lo_off != 0) {                 // precise patch embed: second plane bf16(v - bf16(v))
-            uint2 hi, lo;
-            split_bf16x2(v.x, v.y, hi.x, lo.x);
-            split_bf16x2(v.z, v.w, hi.y, lo.y);
-            *reinterpret_cast<uint2*>(dst + e) = hi;
-            *reinterpret_cast<uint2*>(dst + lo_off + e) = lo;
-        } else {
-            uint2 pk;
-            pk.x = pack_bf16x2(v.x, v.y);
-            pk.y = pack_bf16x2(v.z, v.w);
-            *reinterpret_cast<uint2*>(dst + e) = pk;
-        }
+        store_bf16x4_planes(dst + e, lo_off, v.x, v.y, v.z, v.w);     // precise patch embed: extra planes of the residual
     }
 }
 
@@ -113,18 +102,7 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
         const float o2 = (v[i].z - mean) * rstd * g.z + b.z;
         const float o3 = (v[i].w - mean) * rstd * g.w + b.w;
         __nv_bfloat16* dst = out + (size_t)orow * C + (i * 32 + lane) * 4;
-        if (lo_off != 0) {                 // the consumer is a precise layer: second plane bf16(v - bf16(v))
-            uint2 hi, lo;
-            split_bf16x2(o0, o1, hi.x, lo.x);
-            split_bf16x2(o2, o3, hi.y, lo.y);
-            *reinterpret_cast<uint2*>(dst) = hi;
-            *reinterpret_cast<uint2*>(dst + lo_off) = lo;
-        } else {
-            uint2 pk;
-            pk.x = pack_bf16x2(o0, o1);
-            pk.y = pack_bf16x2(o2, o3);
-            *reinterpret_cast<uint2*>(dst) = pk;
-        }
+        store_bf16x4_planes(dst, lo_off, o0, o1, o2, o3);             // extra planes when the consumer is a precise layer
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)orow * C + (i * 32 + lane) * 4) = make_float4(o0, o1, o2, o3);
     }
 }
@@ -211,11 +189,7 @@ bottleneck_kernel(const float* __restrict__ z, const float* __restrict__ eb_tab,
         if (sym16_out) sym16_out[idx] = (int16_t)fminf(fmaxf(sym, -32768.f), 32767.f);
         if (zhat_out) zhat_out[idx] = zh;
         n = (int)(row / rows_per_image);
-        if (zhat_bf) {
-            const __nv_bfloat16 hi = __float2bfloat16(zh);
-            zhat_bf[idx] = hi;
-            if (lo_off != 0) zhat_bf[idx + lo_off] = __float2bfloat16(zh - __bfloat162float(hi));
-        }
+        if (zhat_bf) store_bf16_planes(zhat_bf + idx, lo_off, zh);
         lg = log2f(lik);
     }
     if (rate_acc) {
@@ -310,18 +284,7 @@ gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu,
         n = (int)(row / K);
         if (yhat_bf) {
             __nv_bfloat16* dst = yhat_bf + (size_t)row * ld_bf + c;
-            if (lo_off != 0) {
-                uint2 hi, lo;
-                split_bf16x2(yh.x, yh.y, hi.x, lo.x);
-                split_bf16x2(yh.z, yh.w, hi.y, lo.y);
-                *reinterpret_cast<uint2*>(dst) = hi;
-                *reinterpret_cast<uint2*>(dst + lo_off) = lo;
-            } else {
-                uint2 pk;
-                pk.x = pack_bf16x2(yh.x, yh.y);
-                pk.y = pack_bf16x2(yh.z, yh.w);
-                *reinterpret_cast<uint2*>(dst) = pk;
-            }
+            store_bf16x4_planes(dst, lo_off, yh.x, yh.y, yh.z, yh.w);
         }
         lg = (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
     }
@@ -463,8 +426,8 @@ cudaError_t launch_pack_nchw_i32(const int32_t* src, int32_t* dst, int N, int hw
 // Weight prepack: fp32 [Cout, Cin_total, kh, kw] (or [Cout, Cin] linear) -> bf16 [Cout, Kp], K index =
 // tap-major, then channel segment (each padded to a multiple of 64 with zeros), then channel.
 // shuffle = 1: output row q*Cq + c takes source channel c*4 + q (PixelShuffle(2) made contiguous per quadrant).
-// planes = 2 (precise layers): every tap holds its segments twice - the hi planes bf16(w), then the lo planes
-// bf16(w - bf16(w)).
+// planes = 2 / 3 (precise layers): every tap holds its segments once per plane - the hi planes bf16(w), then
+// bf16(w - hi) (and bf16(w - hi - mid) for the three-plane / fp32-exact form).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
                                       int Cin_total, int taps, int nseg, int seg_c0, int seg_c1, int seg_c2,
@@ -503,7 +466,9 @@ __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16
         float v = 0.f;
         if (ci >= 0) v = w[((size_t)co * Cin_total + ci) * taps + tap];
         const __nv_bfloat16 hi = __float2bfloat16(v);
-        out[idx] = plane == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16(r1);
+        out[idx] = plane == 0 ? hi : (plane == 1 ? mid : __float2bfloat16(r1 - __bfloat162float(mid)));
     }
 }
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
@@ -565,15 +530,28 @@ cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaSt
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o, long long n, long long lo_off) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const __nv_bfloat16 hi = __float2bfloat16(a[i]);
-        o[i] = hi;
-        if (lo_off != 0) o[i + lo_off] = __float2bfloat16(a[i] - __bfloat162float(hi));
-    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        store_bf16_planes(o + i, lo_off, a[i]);
 }
 cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     f32_to_bf16_kernel<<<512, 256, 0, st>>>(a, o, n, lo_off);
+    return cudaGetLastError();
+}
+
+// strided form: `cols` consecutive columns of every row (row pitch `ld` in both tensors)
+__global__ void f32_to_bf16_cols_kernel(const float* __restrict__ a, __nv_bfloat16* __restrict__ o, long long rows, int cols, int ld,
+                                        long long lo_off) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cols;
+        const int c = (int)(i - r * cols);
+        store_bf16_planes(o + r * ld + c, lo_off, a[r * ld + c]);
+    }
+}
+cudaError_t launch_f32_to_bf16_cols(const float* a, __nv_bfloat16* o, long long rows, int cols, int ld, long long lo_off, cudaStream_t st) {
+    if (rows == 0) return cudaSuccess;
+    f32_to_bf16_cols_kernel<<<256, 256, 0, st>>>(a, o, rows, cols, ld, lo_off);
     return cudaGetLastError();
 }
 

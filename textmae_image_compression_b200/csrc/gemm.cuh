@@ -10,7 +10,7 @@ namespace tmae {
 
 constexpr int kBlockM = 128;      // UMMA M (cta_group::1)
 constexpr int kBlockK = 64;       // 64 bf16 = 128 B = one 128B-swizzle atom row
-constexpr int kMaxSegs = 9;       // 3 concatenated channel segments x 3 split-bf16 terms (precise layers)
+constexpr int kMaxSegs = 18;      // 3 concatenated channel segments x up to 6 split-bf16 terms (precise layers)
 constexpr int kMaxTaps = 9;
 
 // Row spaces.  Every activation matrix is COMPACT channels-last: pixel (n, y, x) of an s x s grid is row n*s*s + y*s + x.
@@ -28,6 +28,8 @@ constexpr int kMaxTaps = 9;
 // (relative error ~2^-17 instead of 2^-9; the dropped a_lo*w_lo term is ~2^-18).  The terms are simply MORE K SEGMENTS
 // of the same main loop: segment list (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) per concatenated source, the weights hold
 // the hi planes of a tap followed by its lo planes (seg_b_kb0 points each segment at its weight columns).
+// TMAE_FLAG_PRECISE_X6 carries fp32 exactly: three planes (hi, mid, lo = 24 mantissa bits) and the six terms
+// hi*hi + mid*hi + hi*mid + mid*mid + lo*hi + hi*lo (dropped terms ~2^-24).
 enum InMode : int { IN_LINEAR = 0, IN_COMPACT = 1, IN_CONV = 2 };
 enum RowMap : int {
     MAP_SAME = 0,        // out row = the pixel's / token's own compact row
@@ -44,7 +46,8 @@ struct OutSpec {
     int ld;        // elements per row
     int dtype;     // OutType
     int map;       // RowMap
-    long long lo_off;   // bf16 outputs feeding a precise layer: element offset of the "lo" plane holding bf16(v - bf16(v)); 0 = none
+    long long lo_off;   // bf16 outputs feeding a precise layer: plane layout, see store_bf16x4_planes (0 one plane, > 0 two planes
+                        // that many elements apart, < 0 three planes -lo_off apart)
 };
 
 struct alignas(64) GemmParams {
@@ -89,7 +92,7 @@ struct alignas(64) GemmParams {
     const int64_t* gather_ids;        // MAP_GATHER1
     OutSpec out[2];
     double flops;                     // flops of this GEMM as the reference would count them for the rows computed (profiling)
-    int mma_terms;                    // tensor-core products issued per algorithmic product: 1, or 3 for precise (split-bf16) layers
+    int mma_terms;                    // tensor-core products issued per algorithmic product: 1, or 3 / 6 for precise (split-bf16) layers
     long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)
 };
 

@@ -33,7 +33,7 @@ struct EpiCtx {
     const int64_t* gather_ids;
     OutSpec out[2];
     const void* out_map;
-    int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used;
+    int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used, exact_act;
 };
 
 __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
@@ -44,6 +44,7 @@ __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
     e.act = p.act; e.resid_ld = p.resid_ld; e.resid_map = p.resid_map;
     e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.K = p.K; e.T = p.T;
     e.n_img = p.n_img; e.box_y = p.box_y; e.box_n = p.box_n; e.y_tiles = p.y_tiles; e.rows_used = p.rows_used;
+    e.exact_act = p.mma_terms > 1;
     return e;
 }
 
@@ -159,13 +160,7 @@ __device__ __forceinline__ void finish_store(const EpiCtx& p, float (&v)[NV], in
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(os.ptr) + orow * os.ld + ocol;
             if (os.lo_off != 0) {
 #pragma unroll
-                for (int i = 0; i < NV; i += 4) {
-                    uint2 hi, lo;
-                    split_bf16x2(v[i], v[i + 1], hi.x, lo.x);
-                    split_bf16x2(v[i + 2], v[i + 3], hi.y, lo.y);
-                    *reinterpret_cast<uint2*>(dst + i) = hi;
-                    *reinterpret_cast<uint2*>(dst + os.lo_off + i) = lo;
-                }
+                for (int i = 0; i < NV; i += 4) store_bf16x4_planes(dst + i, os.lo_off, v[i], v[i + 1], v[i + 2], v[i + 3]);
             } else if (NV == 8) {
                 uint4 pk;
                 pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
@@ -189,18 +184,7 @@ __device__ __forceinline__ void store_out4(const OutSpec& os, int orow, int ocol
     if (os.dtype == OUT_NONE || orow < 0) return;
     if (os.dtype == OUT_BF16) {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(os.ptr) + (long long)orow * os.ld + ocol;
-        if (os.lo_off != 0) {
-            uint2 hi, lo;
-            split_bf16x2(v[0], v[1], hi.x, lo.x);
-            split_bf16x2(v[2], v[3], hi.y, lo.y);
-            *reinterpret_cast<uint2*>(dst) = hi;
-            *reinterpret_cast<uint2*>(dst + os.lo_off) = lo;
-        } else {
-            uint2 pk;
-            pk.x = pack_bf16x2(v[0], v[1]);
-            pk.y = pack_bf16x2(v[2], v[3]);
-            *reinterpret_cast<uint2*>(dst) = pk;
-        }
+        store_bf16x4_planes(dst, os.lo_off, v[0], v[1], v[2], v[3]);
     } else {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(os.ptr) + (long long)orow * os.ld + ocol) =
             make_float4(v[0], v[1], v[2], v[3]);
@@ -255,6 +239,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                                               uint32_t wait_parity, long long* ticks, int nsub = 2) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;                  // which of the `nsub` warps of this TMEM lane quarter
+    // precise layers evaluate GELU with erff (the fast form's 1.5e-7 absolute error is visible next to fp32-exact products)
+    const bool exact = e.exact_act != 0;
+    auto act = [exact](float x) { return (ACT == ACT_GELU && exact) ? gelu_erf(x) : act_fast<ACT>(x); };
     const int cstride = 32 * nsub;
     const int m0 = m_tile * kBlockM;                   // first row of the tile in a linear row space
     if (EPI == EPI_BF16_TMA) {
@@ -285,8 +272,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
             for (int g4 = 0; g4 < 8; ++g4) {
                 const int col = n0 + c0 + g4 * 4;
                 const float4 bb = col < e.N ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                pk[g4 * 2] = pack_bf16x2(act_fast<ACT>(__uint_as_float(acc[g4 * 4]) + bb.x), act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 1]) + bb.y));
-                pk[g4 * 2 + 1] = pack_bf16x2(act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 2]) + bb.z), act_fast<ACT>(__uint_as_float(acc[g4 * 4 + 3]) + bb.w));
+                pk[g4 * 2] = pack_bf16x2(act(__uint_as_float(acc[g4 * 4]) + bb.x), act(__uint_as_float(acc[g4 * 4 + 1]) + bb.y));
+                pk[g4 * 2 + 1] = pack_bf16x2(act(__uint_as_float(acc[g4 * 4 + 2]) + bb.z), act(__uint_as_float(acc[g4 * 4 + 3]) + bb.w));
             }
             const uint32_t buf = buf0 + (uint32_t)(it & 1) * kStoreBoxBytes;
             if (it >= 2) {                                 // the store that last read this buffer must be done with it
@@ -368,21 +355,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                 const int orow = __shfl_sync(0xffffffffu, r.lin, rr);
                 if (col_ok && ((valid_mask >> rr) & 1u)) {
                     const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                    const float v0 = act_fast<ACT>(t4.x + b4.x), v1 = act_fast<ACT>(t4.y + b4.y);
-                    const float v2 = act_fast<ACT>(t4.z + b4.z), v3 = act_fast<ACT>(t4.w + b4.w);
+                    const float v0 = act(t4.x + b4.x), v1 = act(t4.y + b4.y);
+                    const float v2 = act(t4.z + b4.z), v3 = act(t4.w + b4.w);
                     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e.out[0].ptr) + (long long)orow * e.out[0].ld + col;
-                    if (lo_off != 0) {
-                        uint2 hi, lo;
-                        split_bf16x2(v0, v1, hi.x, lo.x);
-                        split_bf16x2(v2, v3, hi.y, lo.y);
-                        *reinterpret_cast<uint2*>(dst) = hi;
-                        *reinterpret_cast<uint2*>(dst + lo_off) = lo;
-                    } else {
-                        uint2 pk;
-                        pk.x = pack_bf16x2(v0, v1);
-                        pk.y = pack_bf16x2(v2, v3);
-                        *reinterpret_cast<uint2*>(dst) = pk;
-                    }
+                    store_bf16x4_planes(dst, lo_off, v0, v1, v2, v3);
                 }
             }
             __syncwarp();
@@ -398,20 +374,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                     const int rr = it * 4 + rsub;
                     if ((valid_mask >> rr) & 1u) {
                         const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                        const float v0 = act_fast<ACT>(t4.x + b4.x), v1 = act_fast<ACT>(t4.y + b4.y);
-                        const float v2 = act_fast<ACT>(t4.z + b4.z), v3 = act_fast<ACT>(t4.w + b4.w);
-                        if (lo_off != 0) {
-                            uint2 hi, lo;
-                            split_bf16x2(v0, v1, hi.x, lo.x);
-                            split_bf16x2(v2, v3, hi.y, lo.y);
-                            *reinterpret_cast<uint2*>(dst) = hi;
-                            *reinterpret_cast<uint2*>(dst + lo_off) = lo;
-                        } else {
-                            uint2 pk;
-                            pk.x = pack_bf16x2(v0, v1);
-                            pk.y = pack_bf16x2(v2, v3);
-                            *reinterpret_cast<uint2*>(dst) = pk;
-                        }
+                        const float v0 = act(t4.x + b4.x), v1 = act(t4.y + b4.y);
+                        const float v2 = act(t4.z + b4.z), v3 = act(t4.w + b4.w);
+                        store_bf16x4_planes(dst, lo_off, v0, v1, v2, v3);
                     }
                 }
             }
@@ -440,8 +405,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
                         if ((valid_mask >> rr) & 1u) {
                             const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
                             *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) =
-                                make_float4(act_fast<ACT>(t4.x + b4.x) + rs[j].x, act_fast<ACT>(t4.y + b4.y) + rs[j].y,
-                                            act_fast<ACT>(t4.z + b4.z) + rs[j].z, act_fast<ACT>(t4.w + b4.w) + rs[j].w);
+                                make_float4(act(t4.x + b4.x) + rs[j].x, act(t4.y + b4.y) + rs[j].y,
+                                            act(t4.z + b4.z) + rs[j].z, act(t4.w + b4.w) + rs[j].w);
                         }
                     }
                 }
@@ -471,10 +436,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float v[4];
-                    v[0] = act_fast<ACT>(t4[j].x + b4.x) + rs[j].x;
-                    v[1] = act_fast<ACT>(t4[j].y + b4.y) + rs[j].y;
-                    v[2] = act_fast<ACT>(t4[j].z + b4.z) + rs[j].z;
-                    v[3] = act_fast<ACT>(t4[j].w + b4.w) + rs[j].w;
+                    v[0] = act(t4[j].x + b4.x) + rs[j].x;
+                    v[1] = act(t4[j].y + b4.y) + rs[j].y;
+                    v[2] = act(t4[j].z + b4.z) + rs[j].z;
+                    v[3] = act(t4[j].w + b4.w) + rs[j].w;
                     store_out4(e.out[0], orow0[j], ocol, v);
                     store_out4(e.out[1], orow1[j], ocol, v);
                 }

@@ -68,5 +68,6 @@ cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, 
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st);
 cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st);
+cudaError_t launch_f32_to_bf16_cols(const float* a, __nv_bfloat16* o, long long rows, int cols, int ld, long long lo_off, cudaStream_t st);
 
 }  // namespace tmae

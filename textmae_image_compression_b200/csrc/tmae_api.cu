@@ -39,18 +39,18 @@ struct Layer {                      // one prepacked linear / conv
     __nv_bfloat16* w = nullptr;     // [Cout, Kp]
     float* bias = nullptr;          // [Cout] (permuted for PixelShuffle layers)
     int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
-    int planes = 1;                 // 2 = precise layer: every tap holds the hi planes of its segments, then the lo planes
+    int planes = 1;                 // 2 / 3 = precise layer: every tap holds the hi planes of its segments, then the lo (mid, lo) planes
     int kb_tap = 0;                 // k-blocks of one plane of one tap
 };
 
-// bf16 activation buffer of the workspace; `lo` = element offset of its second (lo) plane when the layer that reads it
-// is precise (split-bf16), else 0
+// bf16 activation buffer of the workspace; `lo` = plane layout when the layer that reads it is precise (split-bf16):
+// 0 one plane, > 0 two planes `lo` elements apart, < 0 three planes `-lo` apart (store_bf16x4_planes in common.cuh)
 struct Bf {
     __nv_bfloat16* p = nullptr;
     long long lo = 0;
 };
 
-enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE };
+enum StepKind { ST_MASK, ST_GATHER, ST_GEMM, ST_FORCE, ST_LN, ST_ATTN, ST_EB, ST_GC, ST_RATE, ST_ZERO_RATE };
 enum Family { FAM_GEMM = 0, FAM_ATTN, FAM_LN, FAM_MASK, FAM_GATHER, FAM_ENTROPY, FAM_MISC, FAM_COUNT };
 const char* kFamilyNames[FAM_COUNT] = {"gemm_tc", "attention", "layernorm", "mask_select", "gather_patches",
                                        "entropy_elementwise", "misc"};
@@ -96,6 +96,7 @@ struct Workspace {
     // g_a
     Bf ga1, ga2, ga3, y_bf;
     float *y = nullptr, *z = nullptr, *mu = nullptr, *sigma = nullptr, *yhat = nullptr;
+    float* yhat_force = nullptr;     // slice-wise teacher forcing: the caller's y_hat (support of every later slice)
     // h_a / h_s
     Bf ha1, ha2, ha3, ha4, zhat_bf;
     Bf hs1[2], hs2[2], hs3[2], hs4[2], lat[2];     // 0 = means, 1 = scales
@@ -133,6 +134,7 @@ struct tmae_handle {
     bool use_graph = true;           // TMAE_NO_GRAPH=1 disables CUDA-graph replay
     bool precise_rate = false;       // TMAE_FLAG_PRECISE_RATE / _ALL: split-bf16 layers after the encoder
     bool precise_enc = false;        // TMAE_FLAG_PRECISE_ALL: the encoder as well
+    int planes = 2;                  // bf16 planes per operand of a precise layer: 2 (3 terms) or 3 (TMAE_FLAG_PRECISE_X6, 6 terms)
     cudaStream_t cap_stream = nullptr;
     // profiling
     bool profiling = false;
@@ -300,7 +302,7 @@ int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname,
     int kp_tap = 0, csum = 0;
     for (int i = 0; i < nseg; ++i) { L.segc[i] = segc[i]; kp_tap += pad64(segc[i]); csum += segc[i]; }
     if (csum != Cin) return fail(h, TMAE_EINVAL, "layer %s: segments sum %d != Cin %d", key.c_str(), csum, Cin);
-    L.planes = precise ? 2 : 1;
+    L.planes = precise ? h->planes : 1;
     L.kb_tap = kp_tap / 64;
     L.Kp = kp_tap * taps * L.planes;
     rc = dev_alloc(h, h->weight_allocs, &L.w, (size_t)Cout * L.Kp);
@@ -467,25 +469,33 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
         if (d.M != cg.m_tiles * kBlockM || d.a_rows != (long long)d.n_img * d.side * d.side)
             return fail(h, TMAE_EINVAL, "conv descriptor rows inconsistent with its geometry");
     }
-    // K segments: one per concatenated source, or three per source for a precise layer: (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
-    const bool precise = L.planes == 2;
+    // K segments: one per concatenated source; a precise layer issues several split-bf16 terms per source, each one more
+    // segment (activation plane pa x weight plane pw): 2 planes -> hi*hi, lo*hi, hi*lo; 3 planes -> + mid*mid, lo*hi, hi*lo
+    static const int kTerms2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    static const int kTerms3[6][2] = {{2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};      // small terms first
+    const int nterm = L.planes == 1 ? 1 : (L.planes == 2 ? 3 : 6);
     p->num_segs = 0;
     p->b_kb_per_tap = L.kb_tap * L.planes;
-    p->mma_terms = precise ? 3 : 1;
+    p->mma_terms = nterm;
     int kb0 = 0;
     for (int i = 0; i < d.nseg; ++i) {
         if (d.seg[i].cols != L.segc[i]) return fail(h, TMAE_EINVAL, "segment %d width %d != packed %d", i, d.seg[i].cols, L.segc[i]);
-        if (precise && d.seg[i].lo == 0) return fail(h, TMAE_EINVAL, "precise layer: segment %d has no lo plane", i);
+        const long long stride = d.seg[i].lo > 0 ? d.seg[i].lo : -d.seg[i].lo;
+        const int have = d.seg[i].lo == 0 ? 1 : (d.seg[i].lo > 0 ? 2 : 3);
+        if (have != L.planes) return fail(h, TMAE_EINVAL, "layer with %d planes: segment %d has %d", L.planes, i, have);
         const int skb = pad64(d.seg[i].cols) / 64;
-        for (int term = 0; term < (precise ? 3 : 1); ++term) {
+        for (int term = 0; term < nterm; ++term) {
+            const int pa = L.planes == 3 ? kTerms3[term][0] : (L.planes == 2 ? kTerms2[term][0] : 0);
+            const int pw = L.planes == 3 ? kTerms3[term][1] : (L.planes == 2 ? kTerms2[term][1] : 0);
             const int j = p->num_segs++;
-            const __nv_bfloat16* ptr = d.seg[i].ptr + (term == 1 ? d.seg[i].lo : 0);
+            if (j >= kMaxSegs) return fail(h, TMAE_EINVAL, "too many K segments");
+            const __nv_bfloat16* ptr = d.seg[i].ptr + pa * stride;
             p->a_ptr[j] = ptr;
             p->a_ld[j] = d.seg[i].ld;
             p->a_cols[j] = d.seg[i].cols;
             p->a_rows[j] = d.a_rows;
             p->seg_kblocks[j] = skb;
-            p->seg_b_kb0[j] = kb0 + (term == 2 ? L.kb_tap : 0);
+            p->seg_b_kb0[j] = kb0 + pw * L.kb_tap;
             int rc = conv ? make_map4d(h, &p->a_map[j], ptr, (uint64_t)d.seg[i].cols, d.side, d.n_img, (uint64_t)d.seg[i].ld, cg.box_n,
                                        cg.box_y + (d.conv_reuse ? 2 : 0))
                           : make_map(h, &p->a_map[j], ptr, (uint64_t)d.seg[i].cols, (uint64_t)d.a_rows, (uint64_t)d.seg[i].ld, kBlockM);
@@ -560,8 +570,9 @@ int ensure_workspace(tmae_handle* h, int N) {
     // bf16 activation: one plane, or two (hi, lo) when the layers that read it run split-bf16 (precise)
 #define WS_ALLOC_BF(field, count, two)                                                \
     do { const size_t _c = ((size_t)(count) + 63) / 64 * 64;                          \
-         int _rc = dev_alloc(h, w.allocs, &(field).p, _c * ((two) ? 2 : 1), &tot); if (_rc) return _rc; \
-         (field).lo = (two) ? (long long)_c : 0; } while (0)
+         const int _pl = (two) ? h->planes : 1;                                       \
+         int _rc = dev_alloc(h, w.allocs, &(field).p, _c * _pl, &tot); if (_rc) return _rc; \
+         (field).lo = _pl == 1 ? 0 : (_pl == 2 ? (long long)_c : -(long long)_c); } while (0)
     const bool pe = h->precise_enc, pr = h->precise_rate;
     WS_ALLOC(w.ids_keep, rk);
     WS_ALLOC_BF(w.patches, rk * h->patch_dim, pe);
@@ -580,6 +591,7 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC(w.mu, rk * Cy);
     WS_ALLOC(w.sigma, rk * Cy);
     WS_ALLOC(w.yhat, rk * Cy);
+    WS_ALLOC(w.yhat_force, rk * Cy);
     ha_layers(h, ci, co, aux);
     WS_ALLOC_BF(w.ha1, rp * co[0], pr);
     WS_ALLOC_BF(w.ha2, rp * co[1], pr);
@@ -726,12 +738,15 @@ const Layer* get_layer(tmae_handle* h, const std::string& key) {
     return it == h->layers.end() ? nullptr : &it->second;
 }
 
-int build_plan(tmae_handle* h, int N, Plan** out) {
-    auto it = h->plans.find(N);
+// forced = slice-wise teacher forcing (tmae_forward_from_latent_forced): after lrp_transform[i] the support columns of
+// slice i are overwritten with the caller's y_hat, so slice j > i never sees a symbol this run decided itself.
+int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
+    const int key = N * 2 + (forced ? 1 : 0);
+    auto it = h->plans.find(key);
     if (it != h->plans.end()) { *out = it->second.get(); return TMAE_OK; }
     int rc = ensure_workspace(h, N);
     if (rc) return rc;
-    it = h->plans.find(N);          // ensure_workspace may have cleared the map
+    it = h->plans.find(key);        // ensure_workspace may have cleared the map
     std::unique_ptr<Plan> plp(new Plan());
     Plan& pl = *plp;
     pl.N = N;
@@ -918,7 +933,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                         g.act = ACT_HALF_TANH;
                         g.resid = w.yhat + i * h->sc; g.resid_ld = Cy; g.resid_map = MAP_SAME;
                         g.out0 = outspec(w.yhat + i * h->sc, Cy, OUT_F32, MAP_SAME);
-                        g.out1 = outspec(w.yhat_bf, Cy, MAP_SAME, i * h->sc);
+                        if (!(forced && i < half_sl)) g.out1 = outspec(w.yhat_bf, Cy, MAP_SAME, i * h->sc);
                     }
                     g.flops = conv_flops(rk, lch[l], lch[l + 1], 9);
                 }
@@ -926,6 +941,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
                 rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc;
             }
         }
+        if (forced && i0 < half_sl) { Step f; f.kind = ST_FORCE; f.family = FAM_MISC; f.slice = i0; f.tag = "force." + std::to_string(i0); pl.steps.push_back(f); }
         i0 += cnt;
     }
     simple(ST_RATE, FAM_ENTROPY, "rate_finalize");
@@ -958,7 +974,7 @@ int build_plan(tmae_handle* h, int N, Plan** out) {
     pl.d_params = reinterpret_cast<GemmParams*>(dp);
     CUDA_TRY(h, cudaMemcpy(pl.d_params, pl.host_params.data(), pl.host_params.size() * sizeof(GemmParams), cudaMemcpyHostToDevice));
     *out = plp.get();
-    h->plans[N] = std::move(plp);
+    h->plans[key] = std::move(plp);
     return TMAE_OK;
 }
 
@@ -1040,6 +1056,10 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
                                         sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes));
+                break;
+            case ST_FORCE:
+                CUDA_TRY(h, launch_f32_to_bf16_cols(w.yhat_force + sp.slice * h->sc, w.yhat_bf.p + sp.slice * h->sc, (long long)N * K, h->sc,
+                                                    h->Cy, w.yhat_bf.lo, st));
                 break;
             case ST_LN:
                 if (sp.ln_final)
@@ -1179,6 +1199,7 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     h->use_graph = getenv("TMAE_NO_GRAPH") == nullptr;
     h->precise_enc = (h->cfg.flags & TMAE_FLAG_PRECISE_ALL) != 0;
     h->precise_rate = h->precise_enc || (h->cfg.flags & TMAE_FLAG_PRECISE_RATE) != 0;
+    h->planes = (h->cfg.flags & TMAE_FLAG_PRECISE_X6) ? 3 : 2;
     *out = h.release();
     return TMAE_OK;
 }
@@ -1384,6 +1405,31 @@ int tmae_forward_from_latent(tmae_handle* h, const float* y, int N, const tmae_o
     a.out = out; a.begin = pl->first_rate_step; a.end = (int)pl->steps.size();
     if (h->profiling) h->prof_used = 0;
     if ((rc = run_steps(h, *pl, a, st))) return rc;
+    return copy_outputs(h, N, out, true, false, st);
+}
+
+int tmae_forward_from_latent_forced(tmae_handle* h, const float* y, const float* y_hat_support, int N, const tmae_outputs* out,
+                                    void* stream) {
+    int rc = check_ready(h, N);
+    if (rc) return rc;
+    if (!y || !y_hat_support) return fail(h, TMAE_EINVAL, "y / y_hat_support must not be null");
+    if (h->cfg.flags & TMAE_FLAG_SKIP_DEAD_LRP) return fail(h, TMAE_EINVAL, "forced support needs every lrp_transform");
+    Plan* pl = nullptr;
+    if ((rc = build_plan(h, N, &pl, true))) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Workspace& w = h->ws;
+    const size_t rk = (size_t)N * h->K;
+    CUDA_TRY(h, cudaMemsetAsync(w.rate_acc, 0, sizeof(double) * N, st));
+    CUDA_TRY(h, cudaMemcpyAsync(w.y, y, rk * h->Cy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(w.yhat_force, y_hat_support, rk * h->Cy * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(h, launch_f32_to_bf16(w.y, w.y_bf.p, (long long)rk * h->Cy, w.y_bf.lo, st));
+    RunArgs a;
+    a.out = out; a.begin = pl->first_rate_step; a.end = (int)pl->steps.size();
+    const bool prof = h->profiling;
+    h->profiling = false;
+    rc = run_steps(h, *pl, a, st);
+    h->profiling = prof;
+    if (rc) return rc;
     return copy_outputs(h, N, out, true, false, st);
 }
 
@@ -1653,8 +1699,8 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
 // Precise (split-bf16) engine self-tests: fp32 operands in, split into (hi, lo) bf16 planes here, three tensor-core
 // terms per product - the configuration every TMAE_FLAG_PRECISE_* layer runs in.
 int tmae_gemm_split(const float* A, const float* B, const float* bias, float* Cmat, int M, int N, int K, int block_n,
-                    int impl, void* stream) {
-    if (!A || !B || !Cmat || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0)
+                    int planes, int impl, void* stream) {
+    if (!A || !B || !Cmat || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0 || (planes != 2 && planes != 3))
         return fail(nullptr, TMAE_EINVAL, "tmae_gemm_split: invalid shape (need K %% 8 == 0, N %% 8 == 0)");
     std::unique_ptr<tmae_handle> tmp;
     int rc = make_tmp_handle(tmp);
@@ -1665,20 +1711,21 @@ int tmae_gemm_split(const float* A, const float* B, const float* bias, float* Cm
     float* bz = nullptr;
     std::vector<void*> pool;
     const size_t a_plane = ((size_t)M * K + 63) / 64 * 64;
-    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp * 2)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N)) ||
-        (rc = dev_alloc(tmp.get(), pool, &ap, a_plane * 2))) {
+    const long long a_lo = planes == 2 ? (long long)a_plane : -(long long)a_plane;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp * planes)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N)) ||
+        (rc = dev_alloc(tmp.get(), pool, &ap, a_plane * planes))) {
         g_create_error = tmp->err; free_pool(pool); return rc;
     }
     int sg[1] = {K};
-    cudaError_t e = launch_prepack_weight(B, wp, N, K, 1, 1, sg, 0, 2, st);
-    if (e == cudaSuccess) e = launch_f32_to_bf16(A, ap, (long long)M * K, (long long)a_plane, st);
+    cudaError_t e = launch_prepack_weight(B, wp, N, K, 1, 1, sg, 0, planes, st);
+    if (e == cudaSuccess) e = launch_f32_to_bf16(A, ap, (long long)M * K, a_lo, st);
     if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "gemm_split staging: %s", cudaGetErrorString(e)); }
     Layer L;
-    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.planes = 2; L.kb_tap = Kp / 64; L.Kp = Kp * 2;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.planes = planes; L.kb_tap = Kp / 64; L.Kp = Kp * planes;
     GemmDesc d;
     d.layer = &L;
-    d.seg[0] = seg(ap, K, K, (long long)a_plane);
+    d.seg[0] = seg(ap, K, K, a_lo);
     d.a_rows = M; d.M = M;
     d.out0 = outspec(Cmat, N, OUT_F32, MAP_SAME);
     rc = engine_common(tmp.get(), d, block_n, impl, st);
@@ -1688,8 +1735,8 @@ int tmae_gemm_split(const float* A, const float* B, const float* bias, float* Cm
 }
 
 int tmae_conv3x3_split(const float* x, const float* wgt, const float* bias, float* out, int N, int s, int Cin, int Cout,
-                       int gelu, int impl, void* stream) {
-    if (!x || !wgt || !out || N <= 0 || s <= 0 || Cin % 8 != 0 || Cout % 8 != 0)
+                       int gelu, int planes, int impl, void* stream) {
+    if (!x || !wgt || !out || N <= 0 || s <= 0 || Cin % 8 != 0 || Cout % 8 != 0 || (planes != 2 && planes != 3))
         return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_split: invalid shape");
     std::unique_ptr<tmae_handle> tmp;
     int rc = make_tmp_handle(tmp);
@@ -1700,23 +1747,24 @@ int tmae_conv3x3_split(const float* x, const float* wgt, const float* bias, floa
     __nv_bfloat16 *wp = nullptr, *xp = nullptr;
     float* bz = nullptr;
     const size_t x_plane = ((size_t)N * s * s * Cin + 63) / 64 * 64;
-    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * kp_tap * 9 * 2)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout)) ||
-        (rc = dev_alloc(tmp.get(), pool, &xp, x_plane * 2))) {
+    const long long x_lo = planes == 2 ? (long long)x_plane : -(long long)x_plane;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)Cout * kp_tap * 9 * planes)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)Cout)) ||
+        (rc = dev_alloc(tmp.get(), pool, &xp, x_plane * planes))) {
         g_create_error = tmp->err; free_pool(pool); return rc;
     }
     int sg[1] = {Cin};
-    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, 2, st);
-    if (e == cudaSuccess) e = launch_f32_to_bf16(x, xp, (long long)N * s * s * Cin, (long long)x_plane, st);
+    cudaError_t e = launch_prepack_weight(wgt, wp, Cout, Cin, 9, 1, sg, 0, planes, st);
+    if (e == cudaSuccess) e = launch_f32_to_bf16(x, xp, (long long)N * s * s * Cin, x_lo, st);
     if (bias) cudaMemcpyAsync(bz, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) { free_pool(pool); return fail(nullptr, TMAE_ECUDA, "conv3x3_split staging: %s", cudaGetErrorString(e)); }
     Layer L;
-    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.planes = 2; L.kb_tap = kp_tap / 64;
-    L.Kp = kp_tap * 9 * 2;
+    L.w = wp; L.bias = bz; L.Cout = Cout; L.Cin = Cin; L.taps = 9; L.nseg = 1; L.segc[0] = Cin; L.planes = planes; L.kb_tap = kp_tap / 64;
+    L.Kp = kp_tap * 9 * planes;
     ConvGeom cg;
     if (!conv_geom(s, N, &cg)) { free_pool(pool); return fail(nullptr, TMAE_EINVAL, "tmae_conv3x3_split: grid side %d unsupported (1..128)", s); }
     GemmDesc d;
     d.layer = &L;
-    d.seg[0] = seg(xp, Cin, Cin, (long long)x_plane);
+    d.seg[0] = seg(xp, Cin, Cin, x_lo);
     d.a_rows = (long long)N * s * s; d.M = cg.m_tiles * kBlockM; d.in_mode = IN_CONV; d.side = s; d.n_img = N;
     d.act = gelu ? ACT_GELU : ACT_NONE;
     d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);

@@ -68,8 +68,9 @@ class MCM(nn.Module):
         self.extra_outputs = extra_outputs       # also return y, z, mu, sigma, x_remain (parity tests)
         # accuracy mode: None = bf16 operands everywhere (throughput); "rate" = split-bf16 (fp32-equivalent products) for
         # g_a and every entropy-model conv; "all" = the encoder too -> symbols match the fp32 reference up to ties
-        if precise not in (None, "rate", "all"):
-            raise ValueError("precise must be None, 'rate' or 'all'")
+        # "-x6" suffix: three bf16 planes / six terms per product = fp32-equivalent arithmetic (default: two planes / three terms)
+        if precise not in (None, "rate", "all", "rate-x6", "all-x6"):
+            raise ValueError("precise must be None, 'rate', 'all', 'rate-x6' or 'all-x6'")
         self.precise = precise
         if softmax_isa is None:
             # lane order of the ATen CPU softmax the reference's host routine would have used on this machine
@@ -145,7 +146,9 @@ class MCM(nn.Module):
         c = self.cfg
         flags = ((_native.FLAG_SKIP_DEAD_LRP if self.skip_dead_lrp else 0) | (_native.FLAG_DEBUG_SIMT if self.debug_simt else 0)
                  | (_native.FLAG_SHARE_SM if self.share_sm else 0)
-                 | {None: 0, "rate": _native.FLAG_PRECISE_RATE, "all": _native.FLAG_PRECISE_ALL}[self.precise])
+                 | {None: 0, "rate": _native.FLAG_PRECISE_RATE, "all": _native.FLAG_PRECISE_ALL,
+                    "rate-x6": _native.FLAG_PRECISE_RATE | _native.FLAG_PRECISE_X6,
+                    "all-x6": _native.FLAG_PRECISE_ALL | _native.FLAG_PRECISE_X6}[self.precise])
         cfg = _native.TmaeConfig(c.img_size, c.patch_size, c.in_chans, c.encoder_embed_dim, c.encoder_depth,
                                  c.encoder_num_heads, c.decoder_embed_dim, c.mlp_ratio, c.latent_depth,
                                  c.hyperprior_depth, c.num_slices, c.num_keep_patches, c.ln_eps, self.softmax_isa, flags)
@@ -321,8 +324,10 @@ class MCM(nn.Module):
         return t["x_remain"], t["ids_restore"]
 
     @torch.no_grad()
-    def forward_from_latent(self, y_nchw: torch.Tensor):
-        """Teacher-forced rate half (MCM.py:739-787) from y = g_a(...) [N,Cy,s,s]."""
+    def forward_from_latent(self, y_nchw: torch.Tensor, y_hat_support: Optional[torch.Tensor] = None):
+        """Teacher-forced rate half (MCM.py:739-787) from y = g_a(...) [N,Cy,s,s].  With `y_hat_support` (the reference's
+        y_hat, [N,Cy,s,s]) the forcing is slice-wise: every slice takes the given y_hat of the slices before it as support,
+        so a rounding-boundary flip in one slice cannot cascade into the later ones."""
         self._ensure_handle()
         dev = self._handle_device
         y = y_nchw.to(device=dev, dtype=torch.float32).permute(0, 2, 3, 1).contiguous()
@@ -331,8 +336,13 @@ class MCM(nn.Module):
         with torch.cuda.device(dev):
             t, o = self._alloc_outputs(N, dev, encoder=False, rate=True, extra=True)
             cur = self._enter_stream(dev)
-            _native.check(lib.tmae_forward_from_latent(self._handle, C.c_void_p(y.data_ptr()), N, C.byref(o),
-                                                       C.c_void_p(cur.cuda_stream)), self._handle, RuntimeError)
+            if y_hat_support is None:
+                rc = lib.tmae_forward_from_latent(self._handle, C.c_void_p(y.data_ptr()), N, C.byref(o), C.c_void_p(cur.cuda_stream))
+            else:
+                sup = y_hat_support.to(device=dev, dtype=torch.float32).permute(0, 2, 3, 1).contiguous()
+                rc = lib.tmae_forward_from_latent_forced(self._handle, C.c_void_p(y.data_ptr()), C.c_void_p(sup.data_ptr()), N,
+                                                         C.byref(o), C.c_void_p(cur.cuda_stream))
+            _native.check(rc, self._handle, RuntimeError)
             self._leave_stream(cur)
         return self._pack_result(t)
 
