@@ -186,6 +186,10 @@ TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, fl
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
                        int Cin, int Cout, int gelu, int impl, void* stream);
 
+/* C = resid + A B^T + bias (fp32 residual in, fp32 out; the proj / fc2 store phase).  pair = 1: the CTA-pair kernel
+ * (tcgen05.mma.cta_group::2, 256-row tiles over two SMs; needs block_n % 32 == 0), 0: the one-CTA kernel. */
+TMAE_API int  tmae_gemm_bf16_resid(const void* A, const void* B, const float* bias, const float* resid, float* C,
+                          int M, int N, int K, int block_n, int pair, int impl, void* stream);
 /* The same two self-tests in the precise configurations (TMAE_FLAG_PRECISE_*): fp32 operands, split into `planes` bf16
  * planes inside (2: three tensor-core terms per product, ~1e-5 of an fp32 GEMM / conv; 3: six terms, fp32-equivalent). */
 TMAE_API int  tmae_gemm_split(const float* A, const float* B, const float* bias, float* C, int M, int N, int K,

@@ -36,6 +36,18 @@ def conv3x3(x_nhwc_bf16, w, bias, gelu=False, impl=0):
     return out
 
 
+def gemm_resid(A_bf16, B_bf16, bias, resid, block_n=0, pair=0, impl=0):
+    """C = resid + A @ B^T + bias (proj / fc2 store phase); pair=1 -> CTA-pair (cta_group::2) kernel."""
+    M, K = A_bf16.shape
+    N = B_bf16.shape[0]
+    out = torch.zeros(M, N, dtype=torch.float32, device=A_bf16.device)
+    rc = _native.load().tmae_gemm_bf16_resid(ptr(A_bf16), ptr(B_bf16), ptr(bias), ptr(resid.contiguous()), ptr(out), M, N, K,
+                                             block_n, pair, impl, stream())
+    _native.check(rc, None, RuntimeError)
+    torch.cuda.synchronize()
+    return out
+
+
 def gemm_split(A_f32, B_f32, bias, block_n=0, impl=0, planes=2):
     """Precise engine configuration: fp32 operands, split-bf16 planes, three tensor-core terms per product."""
     M, K = A_f32.shape

@@ -67,8 +67,11 @@ def test_gemm_split_matches_fp64(cuda_dev, M, N, K, bn, impl, planes):
     fp32_err = G.rel_err(A @ B.t() + bias, ref)                    # what plain fp32 arithmetic gives on the same operands
     if planes == 2:
         assert err < 2e-5 and err < bf16_err / 50, f"impl={impl} rel err {err} (plain bf16 operands: {bf16_err})"
-    else:                                                          # three planes carry fp32 exactly: fp32-level error
-        assert err < 1e-6 and err < 4 * fp32_err + 2e-7, f"impl={impl} rel err {err} (torch fp32: {fp32_err})"
+    else:
+        # three planes carry the fp32 operands exactly and every product is exact; what remains is the fp32 accumulation -
+        # sequential FMA in the checker (~1e-6), truncating adds in the tensor core (measured 2-3e-6 at K = 3072, growing
+        # linearly with K) - a few times torch's blocked fp32 GEMM, 5-10x below the two-plane form
+        assert err < 6e-6 and err < 8 * fp32_err + 1e-6, f"impl={impl} rel err {err} (torch fp32: {fp32_err})"
 
 
 @pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(2, 8, 64, 32, False), (3, 12, 384, 224, True), (5, 8, 80, 32, False),
@@ -87,4 +90,23 @@ def test_conv3x3_split_matches_fp64(cuda_dev, N, s, Cin, Cout, gelu, impl, plane
     ref = ref.permute(0, 2, 3, 1)
     out = G.conv3x3_split(x, w, b, gelu=gelu, impl=impl, planes=planes)
     err = G.rel_err(out, ref)
-    assert err < (2e-5 if planes == 2 else 1e-6), f"impl={impl} planes={planes} rel err {err}"
+    tol = 2e-5 if planes == 2 else 2e-6 + 5e-9 * 9 * Cin          # accumulation error of the fp32 tensor-core adder grows with K
+    assert err < tol, f"impl={impl} planes={planes} rel err {err} (tol {tol})"
+
+
+# ---- CTA-pair kernel (tcgen05.mma.cta_group::2): 256-row tiles over two SMs, each CTA stages half of the weight tile.
+# Same k order as the one-CTA kernel -> bit-identical results; ragged M (last pair half empty / partly filled), several N tiles.
+@pytest.mark.parametrize("M,N,K,bn", [(256, 64, 64, 64), (4160, 768, 768, 192), (4160, 768, 3072, 256), (1000, 256, 384, 128),
+                                       (130, 96, 128, 96), (385, 512, 192, 256), (2049, 2304, 768, 192)])
+def test_gemm_pair_matches_single_cta_and_torch(cuda_dev, M, N, K, bn):
+    g = torch.Generator(device="cpu").manual_seed(M + N + K + 1)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(cuda_dev).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.1).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    resid = torch.randn(M, N, generator=g).to(cuda_dev)
+    ref = resid + A.float() @ B.float().t() + bias
+    one = G.gemm_resid(A, B, bias, resid, block_n=bn, pair=0)
+    two = G.gemm_resid(A, B, bias, resid, block_n=bn, pair=1)
+    assert G.rel_err(one, ref) < 2e-5
+    assert G.rel_err(two, ref) < 2e-5, f"pair rel err {G.rel_err(two, ref)}"
+    assert torch.equal(one, two)

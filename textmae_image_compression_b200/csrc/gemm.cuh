@@ -53,6 +53,7 @@ struct OutSpec {
 struct alignas(64) GemmParams {
     CUtensorMap a_map[kMaxSegs];      // linear: [rows, C_seg] box 64 x 128; conv: (C_seg, x, n, y) box 64 x s x box_n x box_y (+2 rows if conv_reuse)
     CUtensorMap b_map;                // [N, Kpacked] bf16, box 64 x block_n, SWIZZLE_128B
+    CUtensorMap b_map_pair;           // pair (cta_group::2) launches: box 64 x block_n / 2 (each CTA of the pair stages half of B)
     CUtensorMap out_map;              // TMA-store epilogue only: out[0] as [rows, N] bf16, box 32 x 128 (conv: (N, x, n, y), box 32 x s x box_n x box_y), SWIZZLE_64B
     // raw views of the same operands (CUDA-core checker kernel)
     const __nv_bfloat16* a_ptr[kMaxSegs];
@@ -80,6 +81,7 @@ struct alignas(64) GemmParams {
     int box_y, box_n;                 // conv: image rows / images per CTA tile
     int rows_used;                    // conv: s * box_y * box_n (<= 128) accumulator rows that hold pixels
     int y_tiles;                      // conv: ceil(s / box_y)
+    int pair_ok;                      // b_map_pair is valid (linear layer, block_n % 32 == 0)
     int tma_store_ok;                 // out_map is valid (linear: the tile is 128 consecutive output rows; conv: the 4-D box of the tile)
     int conv_reuse;                   // conv: one haloed A box per (channel block, dx) serves the three dy taps
     int a_halo_rows;                  // conv_reuse: (box_y + 2) * box_n * s rows of 128 B per A box

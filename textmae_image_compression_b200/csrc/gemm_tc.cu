@@ -844,6 +844,126 @@ gemm_tc_persistent_kernel(const GemmParams* __restrict__ params, int stages, int
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05.mma.cta_group::2) for the linear layers with many rows (encoder QKV / proj / fc1 / fc2):
+// a cluster of two CTAs (the two SMs of a TPC) computes ONE 256 x block_n tile.  CTA r stages rows [128 r, 128 r + 128) of
+// the A tile and rows [r block_n / 2, (r + 1) block_n / 2) of the weight tile; the leader (cluster rank 0) issues the MMAs,
+// which read both CTAs' shared memory and write each CTA's half of the accumulator into that CTA's tensor memory.
+// Per SM and k-block that is 16 KB + 64 block_n bytes through the shared-memory port instead of 16 KB + 128 block_n for
+// the same flops - the 1-CTA tile is shared-memory-bandwidth bound.
+//   full[s]   in the LEADER: armed by the leader's producer with the bytes of both CTAs, completed by both CTAs' TMA loads
+//   empty[s]  in each CTA: tcgen05.commit multicast from the leader's MMA warp frees the stage in both
+//   accum     in each CTA: multicast commit after the last MMA; each CTA's epilogue drains its own 128 TMEM lanes
+// ---------------------------------------------------------------------------------------------------------
+template <int ACT, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+gemm_tc_pair_kernel(const GemmParams* __restrict__ params, int stages, const GemmParams* __restrict__ next, int next_groups) {
+    pdl_launch_dependents();
+    if (next != nullptr && threadIdx.x == 64)
+        prefetch_next_weights(next, next_groups, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z);
+    const GemmParams& p = params[blockIdx.z];
+    const uint32_t rank = cluster_ctarank();             // cluster = 2 consecutive CTAs along x
+    const int m_tile = blockIdx.x;                       // this CTA's 128 rows: pair tile blockIdx.x / 2, half `rank`
+    const int n0 = blockIdx.y * p.block_n;
+    if ((m_tile >> 1) * 2 * kBlockM >= p.M || n0 >= p.N) return;      // uniform over the pair
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("tmae: dynamic shared memory not 1024-byte aligned\n"); __trap(); }
+    const int block_n = p.block_n;
+    const int half_n = block_n >> 1;
+    const int stage_bytes = kAStageBytes + half_n * kBlockK * 2;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* accum_bar = empty_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)block_n) tmem_cols <<= 1;
+    int total_kb = 0;
+    for (int sg = 0; sg < p.num_segs; ++sg) total_kb += p.seg_kblocks[sg];
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        for (int sg = 0; sg < p.num_segs; ++sg) tma_prefetch_desc(&p.a_map[sg]);
+        tma_prefetch_desc(&p.b_map_pair);
+    }
+    if (warp == 1) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    tc_fence_before();
+    cluster_sync_all();                                   // both CTAs' barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; warp-uniform) =====
+        const uint32_t full_leader = mapa_shared(full_a, 0);
+        const uint32_t tx = 2u * (uint32_t)stage_bytes;
+        const int row = m_tile * kBlockM;
+        const int brow = n0 + (int)rank * half_n;
+        int stage = 0, sg = 0, k = 0, skb_cur = p.seg_kblocks[0], koff = p.seg_b_kb0[0];
+        uint32_t phase = 0, stage_off = 0;
+        const void* map_cur = &p.a_map[0];
+        for (int kb = 0; kb < total_kb; ++kb) {
+            mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
+            if (elect_one()) {
+                if (rank == 0) mbar_arrive_expect_tx_a(full_a + 8u * stage, tx);
+                tma_load_2d_pair(smem_base + stage_off, map_cur, full_leader + 8u * stage, k * kBlockK, row);
+                tma_load_2d_pair(smem_base + stage_off + kAStageBytes, &p.b_map_pair, full_leader + 8u * stage, koff * kBlockK, brow);
+            }
+            __syncwarp();
+            ++koff;
+            if (++k == skb_cur) {
+                k = 0;
+                if (++sg == p.num_segs) sg = 0;
+                skb_cur = p.seg_kblocks[sg];
+                koff = p.seg_b_kb0[sg];
+                map_cur = &p.a_map[sg];
+            }
+            stage_off += (uint32_t)stage_bytes;
+            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader only; warp-uniform) =====
+            const uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, block_n);
+            const uint64_t desc0 = umma_smem_desc_sw128(smem_base);
+            const uint32_t accum_a = smem_u32(accum_bar);
+            int stage = 0;
+            uint32_t phase = 0, stage_off = 0;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                mbar_wait_a(full_a + 8u * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
+                    const uint64_t b_desc = desc0 + (uint64_t)((stage_off + (uint32_t)kAStageBytes) >> 4);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k)
+                        umma_bf16_pair(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(empty_a + 8u * stage, (uint16_t)3);
+                    if (kb + 1 == total_kb) umma_commit_pair(accum_a, (uint16_t)3);
+                }
+                __syncwarp();
+                stage_off += (uint32_t)stage_bytes;
+                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs, own TMEM lanes = own 128 rows); staging reuses the idle pipeline buffers =====
+        const EpiCtx e = load_epi(p);
+        epilogue_tile<ACT, EPI>(e, m_tile, n0, block_n, tmem_base, smem_base, warp, lane, accum_bar, 0u, nullptr);
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // neither CTA leaves while the other may still signal its barriers
+    if (warp == 1) tmem_dealloc_pair(tmem_base, tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // CUDA-core checker: same parameter block, same epilogue, plain loads.  Bring-up / tests only.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -937,6 +1057,17 @@ cudaError_t gemm_tc_configure() {
     if ((e = configure_one<ACT_NONE, EPI_F32_SAME_RESID>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_NONE, EPI_BF16_TMA>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_GELU, EPI_BF16_TMA>()) != cudaSuccess) return e;
+    {
+        auto cfgp = [](auto kern) {
+            prefer_max_smem_carveout(kern);
+            return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        };
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_TMA>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_TMA>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_SAME>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_SAME>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_F32_SAME_RESID>)) != cudaSuccess) return e;
+    }
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>);
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>);
     if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
@@ -967,9 +1098,18 @@ int gemm_epi_kind(const GemmParams& p) {
 }
 
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
+// CTA-pair launches: linear layers with one bf16 / fp32+residual same-row output, block_n % 32 == 0, enough rows to fill
+// the machine with pairs.  TMAE_NO_PAIR=1 switches them off (A/B).
+bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok) {
+    static const bool off = getenv("TMAE_NO_PAIR") != nullptr;
+    if (off || !pair_ok || groups != 1 || (block_n & 31) != 0 || max_M < 8 * kBlockM) return false;
+    if (epi == EPI_F32_SAME_RESID) return act == ACT_NONE;
+    return (epi == EPI_BF16_SAME || epi == EPI_BF16_TMA) && (act == ACT_NONE || act == ACT_GELU);
+}
+
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups,
-                        int conv_reuse_stage_bytes) {
+                        int conv_reuse_stage_bytes, bool pair) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
         gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
@@ -977,6 +1117,25 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     }
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
+    if (pair) {                                               // the plan's policy (gemm_use_pair) decided; hard requirements only
+        if (groups != 1 || (block_n & 31) != 0 || !(epi == EPI_BF16_SAME || epi == EPI_BF16_TMA || epi == EPI_F32_SAME_RESID) ||
+            act == ACT_HALF_TANH || (epi == EPI_F32_SAME_RESID && act != ACT_NONE))
+            return cudaErrorInvalidConfiguration;
+        dim3 pgrid((grid.x + 1) / 2 * 2, grid.y, 1);           // whole pairs along x
+        const int stage_bytes = kAStageBytes + (block_n / 2) * kBlockK * 2;
+        const int overhead = 256;
+        const bool whole_sm = (int)(pgrid.x * pgrid.y) <= 148 && !share_sm;
+        const int budget = (whole_sm ? 226 : 113) * 1024 - overhead;
+        int pst = budget / stage_bytes;
+        if (pst > 8) pst = 8;
+        if (pst < 2) return cudaErrorInvalidConfiguration;
+        const int psmem = overhead + pst * stage_bytes;
+        if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_TMA>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+        if (epi == EPI_BF16_TMA) return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_TMA>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+        if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_SAME>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+        if (epi == EPI_BF16_SAME) return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_SAME>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+        return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_F32_SAME_RESID>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+    }
     if (conv_reuse_stage_bytes == 0 && gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y), share_sm)) {
         const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;
         const int overhead = 1024 + 256 + kEpiStageBytes;

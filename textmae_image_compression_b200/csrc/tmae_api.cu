@@ -62,6 +62,7 @@ struct Step {
     int param_index = 0, groups = 1, max_M = 0, max_N = 0, block_n = 0, act = 0, epi = 0;
     int next_index = -1, next_groups = 0;      // parameter blocks of the next GEMM step (weight prefetch target)
     int conv_reuse_stage_bytes = 0;            // > 0: 3x3 conv launch with haloed-box A reuse, stage size in bytes
+    bool pair = false;                         // CTA-pair (cta_group::2) launch
     double flops = 0, bytes = 0;
     int mma_terms = 1;                         // 3 for precise (split-bf16) GEMM steps
     // LN
@@ -519,6 +520,12 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->block_n = force_block_n > 0 ? force_block_n : pick_block_n(m_tiles, L.Cout, groups_for_tiling);
     int rc = make_map(h, &p->b_map, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)p->block_n);
     if (rc) return rc;
+    p->pair_ok = 0;
+    if (!conv && (p->block_n & 31) == 0) {               // CTA-pair launches stage half of the weight tile per CTA
+        rc = make_map(h, &p->b_map_pair, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)(p->block_n / 2));
+        if (rc) return rc;
+        p->pair_ok = 1;
+    }
     p->in_mode = d.in_mode;
     // TMA-store epilogue: one bf16 output at the accumulator's own rows, and those rows are 128 consecutive output rows
     {
@@ -719,10 +726,11 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         st.mma_terms = p.mma_terms;
     }
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
+    st.pair = !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && gemm_use_pair(groups, st.epi, st.act, max_M, bn, pl.host_params[st.param_index].pair_ok != 0);
     static const bool plan_debug = getenv("TMAE_PLAN_DEBUG") != nullptr;
     if (plan_debug)
-        fprintf(stderr, "[plan] %-14s groups %2d M %6d N %4d bn %3d ctas %4d epi %d conv_reuse_stage %6d B\n", tag, groups, max_M, max_N, bn,
-                m_tiles * ((max_N + bn - 1) / bn) * groups, st.epi, st.conv_reuse_stage_bytes);
+        fprintf(stderr, "[plan] %-14s groups %2d M %6d N %4d bn %3d ctas %4d epi %d conv_reuse_stage %6d B pair %d\n", tag, groups, max_M, max_N, bn,
+                m_tiles * ((max_N + bn - 1) / bn) * groups, st.epi, st.conv_reuse_stage_bytes, (int)st.pair);
     for (int g = 1; g < groups; ++g) if (descs[g].act != descs[0].act) return fail(h, TMAE_EINVAL, "grouped GEMM members must share the activation");
     pl.steps.push_back(st);
     return TMAE_OK;
@@ -1055,7 +1063,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
-                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes));
+                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes, sp.pair));
                 break;
             case ST_FORCE:
                 CUDA_TRY(h, launch_f32_to_bf16_cols(w.yhat_force + sp.slice * h->sc, w.yhat_bf.p + sp.slice * h->sc, (long long)N * K, h->sc,
@@ -1520,7 +1528,7 @@ int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* li
 }
 
 // ---- engine self-tests ---------------------------------------------------------------------------------
-static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st) {
+static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st, bool pair = false) {
     GemmParams p;
     GemmDesc d = d_in;
     int reuse_bytes = 0;
@@ -1551,7 +1559,8 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
         p.dbg_ticks = dticks;
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
-    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes);
+    if (pair && !p.pair_ok) { cudaFree(dp); return fail(tmp, TMAE_EINVAL, "pair launch needs a linear layer with block_n %% 32 == 0"); }
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes, pair && impl == 0);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
         cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -1691,6 +1700,39 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
     d.act = gelu ? ACT_GELU : ACT_NONE;
     d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);
     rc = engine_common(tmp.get(), d, 0, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+// x_out = resid + A B^T + bias (fp32 in / out, bf16 operands): the encoder's proj / fc2 epilogue.  pair = 1 runs the CTA-pair
+// (cta_group::2) kernel, 0 the one-CTA kernel, impl 1 the CUDA-core checker.
+int tmae_gemm_bf16_resid(const void* A, const void* B, const float* bias, const float* resid, float* Cmat, int M, int N, int K,
+                         int block_n, int pair, int impl, void* stream) {
+    if (!A || !B || !Cmat || !resid || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0)
+        return fail(nullptr, TMAE_EINVAL, "tmae_gemm_bf16_resid: invalid shape (need K %% 8 == 0, N %% 8 == 0)");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int Kp = pad64(K);
+    __nv_bfloat16* wp = nullptr;
+    float* bz = nullptr;
+    std::vector<void*> pool;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    cudaMemcpy2DAsync(wp, (size_t)Kp * 2, B, (size_t)K * 2, (size_t)K * 2, N, cudaMemcpyDeviceToDevice, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.Kp = Kp; L.kb_tap = Kp / 64;
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(A), K, K);
+    d.a_rows = M; d.M = M;
+    d.resid = resid; d.resid_ld = N; d.resid_map = MAP_SAME;
+    d.out0 = outspec(Cmat, N, OUT_F32, MAP_SAME);
+    rc = engine_common(tmp.get(), d, block_n, impl, st, pair != 0);
     if (rc) g_create_error = tmp->err;
     free_pool(pool);
     return rc;
