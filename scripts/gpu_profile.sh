@@ -10,9 +10,11 @@ WL=${1:-B64}
 python scripts/ncu_target.py $WL 2 > $O/ncu_plain.log 2>&1 || { echo "plain run failed"; tail -5 $O/ncu_plain.log; exit 1; }
 NL=$(grep -o "launches_per_forward [0-9]*" $O/ncu_plain.log | awk '{print $2}')
 echo "kernel launches per forward: $NL"
-KRE='regex:gemm_tc|attention_kernel|layernorm_kernel|mask_select|gather_patches|bottleneck_kernel|gaussian_slice|rate_finalize'
+KRE='regex:gemm_tc|attention|layernorm_kernel|mask_select|gather_patches|bottleneck_kernel|gaussian_slice|rate_finalize'
+# --cache-control none: the caches are NOT flushed between kernels, so L2-resident activations and the just-prefetched
+# next-layer weights count as hits like in a real forward; few metrics -> one or two replay passes
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed \
-    --clock-control none -k "$KRE" --launch-skip $NL --launch-count $NL --csv --log-file $O/launches_$WL.csv \
+    --clock-control none --cache-control none -k "$KRE" --launch-skip $NL --launch-count $NL --csv --log-file $O/launches_$WL.csv \
     python scripts/ncu_target.py $WL 2 > $O/ncu_launches.log 2>&1
 echo "rc=$? ncu launch list"
 # representative launches of the 2nd forward (gemm-only indices): 1=blk0.qkv 2=proj 3=fc1 4=fc2

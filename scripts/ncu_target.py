@@ -8,9 +8,10 @@ from bench import WORKLOADS, make_inputs
 from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
 wl = sys.argv[1] if len(sys.argv) > 1 else "B64"
 nfwd = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-kwargs, batch, desc = WORKLOADS[wl]
-m = MCM(**kwargs); m.load_state_dict(make_state_dict(PathConfig(**kwargs), 0)); m.cuda().eval()
-imgs, scores = make_inputs(kwargs, batch, 0, 1)
+kwargs, batch, desc, kind = WORKLOADS[wl]
+import os
+m = MCM(**kwargs, precise=os.environ.get("TMAE_BENCH_PRECISE") or None); m.load_state_dict(make_state_dict(PathConfig(**kwargs), 0)); m.cuda().eval()
+imgs, scores = make_inputs(kwargs, batch, 0, 1, kind)
 imgs = imgs[0].cuda(); scores = scores[0].cuda()
 for _ in range(nfwd):
     out = m(imgs, scores)

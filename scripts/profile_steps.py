@@ -9,12 +9,12 @@ from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "B64"
 batch_override = int(sys.argv[2]) if len(sys.argv) > 2 else None
-kwargs, batch, desc = WORKLOADS[wl]
+kwargs, batch, desc, kind = WORKLOADS[wl]
 batch = batch_override or batch
 cfg = PathConfig(**kwargs)
 share = len(sys.argv) > 3 and sys.argv[3] == "share"      # third argument 'share': the half-smem configs of multi-stream mode
 m = MCM(**kwargs, share_sm=share); m.load_state_dict(make_state_dict(cfg, 0)); m.cuda().eval()
-imgs, scores = make_inputs(kwargs, batch, 0, 2)
+imgs, scores = make_inputs(kwargs, batch, 0, 2, kind)
 imgs = [t.cuda() for t in imgs]; scores = [t.cuda() for t in scores]
 for i in range(3): m(imgs[i % 2], scores[i % 2])
 torch.cuda.synchronize()
