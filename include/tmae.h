@@ -182,7 +182,8 @@ TMAE_API int  tmae_pack_nchw_i32(const int32_t* nhwc, int32_t* nchw, int N, int 
  * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */
 TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K,
                     int block_n, int impl, void* stream);
-/* 3x3 pad-1 stride-1 convolution on the engine: x bf16 [N, s, s, Cin] NHWC, w f32 [Cout, Cin, 3, 3] -> f32 NHWC. */
+/* 3x3 pad-1 stride-1 convolution on the engine: x bf16 [N, s, s, Cin] NHWC, w f32 [Cout, Cin, 3, 3] -> f32 NHWC.
+ * impl 2 = the CTA-pair (cta_group::2) launch of the tcgen05 kernel. */
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,
                        int Cin, int Cout, int gelu, int impl, void* stream);
 

@@ -6,7 +6,7 @@ sys.path.insert(0, str(ROOT))
 import torch
 from bench import WORKLOADS, make_inputs
 from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
-kwargs, batch, desc = WORKLOADS["B64"]
+kwargs, batch, desc, kind = WORKLOADS["B64"]
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 sd = make_state_dict(PathConfig(**kwargs), 0)
 models = []

@@ -110,3 +110,23 @@ def test_gemm_pair_matches_single_cta_and_torch(cuda_dev, M, N, K, bn):
     assert G.rel_err(one, ref) < 2e-5
     assert G.rel_err(two, ref) < 2e-5, f"pair rel err {G.rel_err(two, ref)}"
     assert torch.equal(one, two)
+
+
+@pytest.mark.parametrize("N,s,Cin,Cout,gelu", [(64, 8, 352, 224, True), (64, 8, 384, 224, False), (3, 12, 384, 224, True), (33, 8, 128, 80, True),
+                                                  (9, 16, 64, 96, True), (40, 6, 128, 64, True), (21, 4, 64, 48, False), (1, 16, 576, 224, True)])
+def test_conv3x3_pair_matches_single_cta(cuda_dev, N, s, Cin, Cout, gelu):
+    """CTA-pair launch of the 3x3 conv (two 128-row tiles per MMA, each CTA stages half of the weight tile), with and
+    without the haloed-box A reuse, odd tile counts (an empty second CTA) and ragged image groups: bit-identical to the
+    one-CTA launch."""
+    g = torch.Generator(device="cpu").manual_seed(N * 1000 + s * 100 + Cin + 9)
+    x = torch.randn(N, s, s, Cin, generator=g).to(cuda_dev).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (3 * Cin ** 0.5))).to(cuda_dev)
+    b = torch.randn(Cout, generator=g).to(cuda_dev)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.bfloat16().float(), b, padding=1)
+    if gelu:
+        ref = F.gelu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    one = G.conv3x3(x, w, b, gelu=gelu, impl=0)
+    two = G.conv3x3(x, w, b, gelu=gelu, impl=2)
+    assert G.rel_err(two, ref) < 3e-5, G.rel_err(two, ref)
+    assert torch.equal(one, two)

@@ -396,6 +396,14 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* 
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster, int32_t c0, int32_t c1,
+                                                 int32_t c2, int32_t c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::
+            "r"(smem_dst),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // one warp of EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
 }

@@ -431,7 +431,7 @@ cudaError_t launch_pack_nchw_i32(const int32_t* src, int32_t* dst, int N, int hw
 // ---------------------------------------------------------------------------------------------------------
 __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
                                       int Cin_total, int taps, int nseg, int seg_c0, int seg_c1, int seg_c2,
-                                      int shuffle, int planes) {
+                                      int shuffle, int planes, const float* __restrict__ gamma) {
     const int segc[3] = {seg_c0, seg_c1, seg_c2};
     int segpad[3], kp_tap = 0;
     for (int i = 0; i < 3; ++i) {
@@ -465,6 +465,7 @@ __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16
         }
         float v = 0.f;
         if (ci >= 0) v = w[((size_t)co * Cin_total + ci) * taps + tap];
+        if (ci >= 0 && gamma != nullptr) v *= gamma[ci];          // LayerNorm folded into this linear: W' = W diag(gamma)
         const __nv_bfloat16 hi = __float2bfloat16(v);
         const float r1 = v - __bfloat162float(hi);
         const __nv_bfloat16 mid = __float2bfloat16(r1);
@@ -472,9 +473,30 @@ __global__ void prepack_weight_kernel(const float* __restrict__ w, __nv_bfloat16
     }
 }
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
-                                  const int* segc, int shuffle, int planes, cudaStream_t st) {
+                                  const int* segc, int shuffle, int planes, cudaStream_t st, const float* gamma) {
     prepack_weight_kernel<<<1024, 256, 0, st>>>(w, out, Cout, Cin_total, taps, nseg, segc[0], nseg > 1 ? segc[1] : 0,
-                                                nseg > 2 ? segc[2] : 0, shuffle, planes);
+                                                nseg > 2 ? segc[2] : 0, shuffle, planes, gamma);
+    return cudaGetLastError();
+}
+
+// LayerNorm folded into a linear layer (GemmParams::ln_stats_in): bias' = bias + W beta (fp32 W), and
+// wsum_c = sum_k W'[c, k] taken over the bf16-ROUNDED packed weights, so that mean * wsum cancels exactly what the
+// tensor core accumulated for a constant row.  One warp per output channel.
+__global__ void fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ beta, const float* __restrict__ bias,
+                               const __nv_bfloat16* __restrict__ packed, int Kp, int Cout, int Cin, float* __restrict__ bias_out,
+                               float* __restrict__ wsum) {
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= Cout) return;
+    float b = 0.f, s = 0.f;
+    for (int k = lane; k < Cin; k += 32) b = fmaf(w[(size_t)c * Cin + k], beta[k], b);
+    for (int k = lane; k < Kp; k += 32) s += __bfloat162float(packed[(size_t)c * Kp + k]);
+    b = warp_sum(b);
+    s = warp_sum(s);
+    if (lane == 0) { bias_out[c] = bias[c] + b; wsum[c] = s; }
+}
+cudaError_t launch_fold_ln(const float* w, const float* beta, const float* bias, const __nv_bfloat16* packed, int Kp, int Cout, int Cin,
+                           float* bias_out, float* wsum, cudaStream_t st) {
+    fold_ln_kernel<<<(Cout * 32 + 255) / 256, 256, 0, st>>>(w, beta, bias, packed, Kp, Cout, Cin, bias_out, wsum);
     return cudaGetLastError();
 }
 

@@ -93,6 +93,18 @@ struct alignas(64) GemmParams {
     int resid_map;
     const int64_t* gather_ids;        // MAP_GATHER1
     OutSpec out[2];
+    // LayerNorm folded into the GEMMs around it (bf16 mode, encoder blocks).  Consumer (QKV / fc1): A = bf16(x) of the raw
+    // residual stream, the weights carry gamma (W' = W diag(gamma), bias' = bias + W beta) and the epilogue applies
+    //     out = rstd_r * (acc - mean_r * wsum_c) + bias'_c,   wsum_c = sum_k W'[c, k] (of the bf16-rounded W'),
+    // with (sum x, sum x^2) of row r summed from ln_stats_in.  Producer (proj / fc2, fp32 residual epilogue): writes one
+    // (sum v, sum v^2) partial per output row and 32-column chunk to ln_stats_out (plain stores, a fixed slot per chunk:
+    // deterministic and independent of tiling / batch size) and bf16(v) to xbf_out.
+    const float* ln_stats_in;         // [rows][ln_chunks][2] or nullptr
+    const float* ln_wsum;             // [N]
+    float ln_inv_c, ln_eps;
+    int ln_chunks;                    // C / 32 of the normalised rows
+    float* ln_stats_out;              // [rows][N / 32][2] or nullptr
+    __nv_bfloat16* xbf_out;           // [rows][N] or nullptr
     double flops;                     // flops of this GEMM as the reference would count them for the rows computed (profiling)
     int mma_terms;                    // tensor-core products issued per algorithmic product: 1, or 3 / 6 for precise (split-bf16) layers
     long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)

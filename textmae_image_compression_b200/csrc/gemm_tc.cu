@@ -33,6 +33,12 @@ struct EpiCtx {
     const int64_t* gather_ids;
     OutSpec out[2];
     const void* out_map;
+    const float* ln_stats_in;
+    const float* ln_wsum;
+    float* ln_stats_out;
+    __nv_bfloat16* xbf_out;
+    float ln_inv_c, ln_eps;
+    int ln_chunks;
     int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used, exact_act;
 };
 
@@ -45,6 +51,8 @@ __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
     e.M = p.M; e.N = p.N; e.in_mode = p.in_mode; e.s = p.s; e.K = p.K; e.T = p.T;
     e.n_img = p.n_img; e.box_y = p.box_y; e.box_n = p.box_n; e.y_tiles = p.y_tiles; e.rows_used = p.rows_used;
     e.exact_act = p.mma_terms > 1;
+    e.ln_stats_in = p.ln_stats_in; e.ln_wsum = p.ln_wsum; e.ln_stats_out = p.ln_stats_out; e.xbf_out = p.xbf_out;
+    e.ln_inv_c = p.ln_inv_c; e.ln_eps = p.ln_eps; e.ln_chunks = p.ln_chunks;
     return e;
 }
 
@@ -233,15 +241,15 @@ constexpr uint32_t kStoreBoxBytes = kBlockM * 32 * 2;      // one 128 x 32 bf16 
 // Phase 2 (8 lanes = 32 consecutive channels of one row, 4 rows per instruction): + bias, activation, residual add,
 // coalesced 64 / 128-byte row segments to global memory.
 // ---------------------------------------------------------------------------------------------------------
-template <int ACT, int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n0, int block_n, uint32_t tmem_acc,
-                                              uint32_t stage_base, int warp, int lane, uint64_t* wait_bar,
-                                              uint32_t wait_parity, long long* ticks, int nsub = 2) {
+template <int ACT, int EPI, bool EXACT>
+__device__ __forceinline__ void epilogue_tile_impl(const EpiCtx& e, int m_tile, int n0, int block_n, uint32_t tmem_acc,
+                                                   uint32_t stage_base, int warp, int lane, uint64_t* wait_bar,
+                                                   uint32_t wait_parity, long long* ticks, int nsub) {
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;                  // which of the `nsub` warps of this TMEM lane quarter
-    // precise layers evaluate GELU with erff (the fast form's 1.5e-7 absolute error is visible next to fp32-exact products)
-    const bool exact = e.exact_act != 0;
-    auto act = [exact](float x) { return (ACT == ACT_GELU && exact) ? gelu_erf(x) : act_fast<ACT>(x); };
+    // precise layers evaluate GELU with erff (the fast form's 1.5e-7 absolute error is visible next to fp32-exact products);
+    // a compile-time choice: a per-element runtime select cost the GELU layers 20 % (measured)
+    auto act = [](float x) { return (ACT == ACT_GELU && EXACT) ? gelu_erf(x) : act_fast<ACT>(x); };
     const int cstride = 32 * nsub;
     const int m0 = m_tile * kBlockM;                   // first row of the tile in a linear row space
     if (EPI == EPI_BF16_TMA) {
@@ -257,6 +265,19 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
         int ty0 = 0, tn0 = 0;
         if (conv_t) conv_tile_origin(m_tile, e.y_tiles, e.box_y, e.box_n, ty0, tn0);
         const int nboxes = block_n >> 5;
+        // folded LayerNorm (see GemmParams::ln_stats_in): this thread's row statistics, fetched before the accumulator wait
+        const bool fold = e.ln_stats_in != nullptr;
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (fold && m0 + row < e.M) {
+            // one (sum, sum of squares) partial per 32-column chunk of the row, written by the producing layer: summed in
+            // a fixed order, so the statistics do not depend on tiling, batch size or run (no atomics)
+            const float2* sp = reinterpret_cast<const float2*>(e.ln_stats_in) + (long long)(m0 + row) * e.ln_chunks;
+            float s1 = 0.f, s2 = 0.f;
+            for (int c = 0; c < e.ln_chunks; ++c) { const float2 v = sp[c]; s1 += v.x; s2 += v.y; }
+            ln_mean = s1 * e.ln_inv_c;
+            ln_rstd = rsqrtf(fmaxf(s2 * e.ln_inv_c - ln_mean * ln_mean, 0.f) + e.ln_eps);
+        }
+        const float ln_nm = -ln_mean;
         mbar_wait(wait_bar, wait_parity);
         tc_fence_after();
         if (ticks && warp == 2 && lane == 0) ticks[5] = globaltimer_ns();
@@ -272,8 +293,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
             for (int g4 = 0; g4 < 8; ++g4) {
                 const int col = n0 + c0 + g4 * 4;
                 const float4 bb = col < e.N ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                pk[g4 * 2] = pack_bf16x2(act(__uint_as_float(acc[g4 * 4]) + bb.x), act(__uint_as_float(acc[g4 * 4 + 1]) + bb.y));
-                pk[g4 * 2 + 1] = pack_bf16x2(act(__uint_as_float(acc[g4 * 4 + 2]) + bb.z), act(__uint_as_float(acc[g4 * 4 + 3]) + bb.w));
+                float a0 = __uint_as_float(acc[g4 * 4]), a1 = __uint_as_float(acc[g4 * 4 + 1]);
+                float a2 = __uint_as_float(acc[g4 * 4 + 2]), a3 = __uint_as_float(acc[g4 * 4 + 3]);
+                if (fold) {                                  // rstd * (acc - mean * wsum) + bias'
+                    const float4 ws = col < e.N ? __ldg(reinterpret_cast<const float4*>(e.ln_wsum + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    a0 = fmaf(ln_nm, ws.x, a0) * ln_rstd; a1 = fmaf(ln_nm, ws.y, a1) * ln_rstd;
+                    a2 = fmaf(ln_nm, ws.z, a2) * ln_rstd; a3 = fmaf(ln_nm, ws.w, a3) * ln_rstd;
+                }
+                pk[g4 * 2] = pack_bf16x2(act(a0 + bb.x), act(a1 + bb.y));
+                pk[g4 * 2 + 1] = pack_bf16x2(act(a2 + bb.z), act(a3 + bb.w));
             }
             const uint32_t buf = buf0 + (uint32_t)(it & 1) * kStoreBoxBytes;
             if (it >= 2) {                                 // the store that last read this buffer must be done with it
@@ -384,30 +412,49 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
             continue;
         }
         if (EPI == EPI_F32_SAME_RESID) {
-            if (col_ok) {
-                const long long off0 = (long long)(m0 + quarter * 32 + rsub) * e.out[0].ld + col;
-                const long long step = 4ll * e.out[0].ld;
-                float* dst = reinterpret_cast<float*>(e.out[0].ptr) + off0;
-                const float* src = e.resid + (long long)(m0 + quarter * 32 + rsub) * e.resid_ld + col;
-                const long long rstep = 4ll * e.resid_ld;
+            const int row0 = m0 + quarter * 32 + rsub;
+            const long long step = 4ll * e.out[0].ld;
+            float* dst = reinterpret_cast<float*>(e.out[0].ptr) + (long long)row0 * e.out[0].ld + col;
+            const float* src = e.resid + (long long)row0 * e.resid_ld + col;
+            const long long rstep = 4ll * e.resid_ld;
+            const bool ln_out = e.ln_stats_out != nullptr;           // uniform: this layer feeds a folded LayerNorm
 #pragma unroll
-                for (int hb = 0; hb < 2; ++hb) {
-                    float4 rs[4];
+            for (int hb = 0; hb < 2; ++hb) {
+                float4 rs[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int rr = (hb * 4 + j) * 4 + rsub;
-                        rs[j] = ((valid_mask >> rr) & 1u) ? *reinterpret_cast<const float4*>(src + (hb * 4 + j) * rstep)
-                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = (hb * 4 + j) * 4 + rsub;
+                    rs[j] = (col_ok && ((valid_mask >> rr) & 1u)) ? *reinterpret_cast<const float4*>(src + (hb * 4 + j) * rstep)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int rr = (hb * 4 + j) * 4 + rsub;
-                        if ((valid_mask >> rr) & 1u) {
-                            const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
-                            *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) =
-                                make_float4(act(t4.x + b4.x) + rs[j].x, act(t4.y + b4.y) + rs[j].y,
-                                            act(t4.z + b4.z) + rs[j].z, act(t4.w + b4.w) + rs[j].w);
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = (hb * 4 + j) * 4 + rsub;
+                    const bool ok = col_ok && ((valid_mask >> rr) & 1u);
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok) {
+                        const float4 t4 = lds128(stage_a + (uint32_t)(rr * kEpiPitch + c4) * 4u);
+                        o = make_float4(act(t4.x + b4.x) + rs[j].x, act(t4.y + b4.y) + rs[j].y,
+                                        act(t4.z + b4.z) + rs[j].z, act(t4.w + b4.w) + rs[j].w);
+                        *reinterpret_cast<float4*>(dst + (hb * 4 + j) * step) = o;
+                        if (e.xbf_out != nullptr) {                  // bf16 copy of the residual stream: A operand of the next GEMM
+                            uint2 pk;
+                            pk.x = pack_bf16x2(o.x, o.y);
+                            pk.y = pack_bf16x2(o.z, o.w);
+                            *reinterpret_cast<uint2*>(e.xbf_out + (long long)(row0 + (hb * 4 + j) * 4) * e.N + col) = pk;
                         }
+                    }
+                    if (ln_out) {                                    // (sum v, sum v^2) of this 32-column segment of the row
+                        float s1 = (o.x + o.y) + (o.z + o.w);
+                        float s2 = fmaf(o.x, o.x, o.y * o.y) + fmaf(o.z, o.z, o.w * o.w);
+#pragma unroll
+                        for (int sh = 1; sh < 8; sh <<= 1) {
+                            s1 += __shfl_xor_sync(0xffffffffu, s1, sh);
+                            s2 += __shfl_xor_sync(0xffffffffu, s2, sh);
+                        }
+                        if ((lane & 7) == 0 && ((valid_mask >> rr) & 1u) && col < e.N)       // this chunk's slot of the row
+                            reinterpret_cast<float2*>(e.ln_stats_out)[(long long)(row0 + (hb * 4 + j) * 4) * (e.N >> 5) + (col >> 5)] =
+                                make_float2(s1, s2);
                     }
                 }
             }
@@ -450,6 +497,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
     }
 }
 
+template <int ACT, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n0, int block_n, uint32_t tmem_acc,
+                                              uint32_t stage_base, int warp, int lane, uint64_t* wait_bar,
+                                              uint32_t wait_parity, long long* ticks, int nsub = 2) {
+    if (ACT == ACT_GELU && e.exact_act != 0)
+        epilogue_tile_impl<ACT, EPI, true>(e, m_tile, n0, block_n, tmem_acc, stage_base, warp, lane, wait_bar, wait_parity, ticks, nsub);
+    else
+        epilogue_tile_impl<ACT, EPI, false>(e, m_tile, n0, block_n, tmem_acc, stage_base, warp, lane, wait_bar, wait_parity, ticks, nsub);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Pipeline stage = `kgroup` consecutive k-blocks (1, 2 or 4) behind ONE full / empty barrier pair:
 //   [A atom 0 .. A atom G-1][B atom 0 .. B atom G-1],  A atom = 128 rows x 128 B, B atom = block_n rows x 128 B.
@@ -467,20 +524,35 @@ __device__ __forceinline__ void epilogue_tile(const EpiCtx& e, int m_tile, int n
 __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, int n0, int total_kb, int stages, int kgroup,
                                              int stage_bytes, uint32_t pipe_base, uint32_t full_a, uint32_t empty_a,
                                              int& stage, uint32_t& phase, uint32_t& stage_off, long long* ticks,
-                                             int prod_id = 0, int num_prod = 1) {
+                                             int prod_id = 0, int num_prod = 1, int pair = 0, uint32_t pair_rank = 0,
+                                             uint32_t full_sig = 0) {
+    // pair != 0 (CTA-pair launches, gemm_tc_pair_kernel): this CTA stages its own A tile and HALF of the weight tile (rows
+    // [n0 + rank * block_n / 2, ...)); every load signals the LEADER's full barrier (`full_sig`, a shared::cluster
+    // address) and only the leader arms it - with the bytes of both CTAs.
     // num_prod producer warps share the stage sequence round-robin (prod_id = which one this is): every producer walks
     // all stages (same coordinate / parity bookkeeping) but waits, arms and loads only its own.  One warp needs
     // ~300 cycles of barrier handshake PLUS ~140 cycles per 16 KB load it issues for every stage (the two add up: the
     // loop was producer bound at ~210 ns per k-block on the narrow conv tiles); two warps overlap each other's handshake.
     const int nseg = p.num_segs;
-    const void* mapb = &p.b_map;
+    const void* mapb = pair ? &p.b_map_pair : &p.b_map;
+    const int b_rows = pair ? (p.block_n >> 1) : p.block_n;
+    const int b_row0 = n0 + (pair ? (int)pair_rank * b_rows : 0);
+    if (!pair) full_sig = full_a;
+    const uint32_t tx_mult = pair ? 2u : 1u;
+    const bool arm = !pair || pair_rank == 0;
     const int b_kb_per_tap = p.b_kb_per_tap;               // k-blocks per tap of the packed weights
     const bool conv = p.in_mode == IN_CONV;
     int y0 = 0, img0 = 0;
     if (conv) conv_tile_origin(m_tile, p.y_tiles, p.box_y, p.box_n, y0, img0);
     const int row = m_tile * kBlockM;
-    const uint32_t b_atom = (uint32_t)(p.block_n * kBlockK * 2);
+    const uint32_t b_atom = (uint32_t)(b_rows * kBlockK * 2);
     const uint32_t kb_bytes = (uint32_t)((conv ? p.rows_used : kBlockM) * kBlockK * 2) + b_atom;
+    auto ld2d = [pair](uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
+        if (pair) tma_load_2d_pair(dst, map, bar, c0, c1); else tma_load_2d_a(dst, map, bar, c0, c1);
+    };
+    auto ld4d = [pair](uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+        if (pair) tma_load_4d_pair(dst, map, bar, c0, c1, c2, c3); else tma_load_4d_a(dst, map, bar, c0, c1, c2, c3);
+    };
     const uint32_t b_base = (uint32_t)(kgroup * kAStageBytes);
     int sg = 0, k = 0, skb_cur = p.seg_kblocks[0];
     int koff = p.seg_b_kb0[0];                             // k-block of (sg, k) inside one tap of the packed weights
@@ -498,13 +570,13 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
             if (mine) {
                 mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
                 if (elect_one()) {
-                    const uint32_t fb = full_a + 8u * stage;
-                    mbar_arrive_expect_tx_a(fb, a_bytes + 3u * b_atom);
-                    tma_load_4d_a(pipe_base + stage_off, map_cur, fb, k * kBlockK, dx, img0, y0 - 1);
+                    const uint32_t fb = full_sig + 8u * stage;
+                    if (arm) mbar_arrive_expect_tx_a(full_a + 8u * stage, tx_mult * (a_bytes + 3u * b_atom));
+                    ld4d(pipe_base + stage_off, map_cur, fb, k * kBlockK, dx, img0, y0 - 1);
 #pragma unroll
                     for (int t3 = 0; t3 < 3; ++t3)         // tap (dy = t3 - 1, dx): index t3 * 3 + (dx + 1) in (kh, kw) order
-                        tma_load_2d_a(pipe_base + stage_off + a_bytes + (uint32_t)t3 * b_atom, mapb, fb,
-                                      ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, n0);
+                        ld2d(pipe_base + stage_off + a_bytes + (uint32_t)t3 * b_atom, mapb, fb,
+                             ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, b_row0);
                     if (ticks && it == 0) ticks[2] = globaltimer_ns();
                 }
                 __syncwarp();
@@ -529,10 +601,10 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
         const int nk = min(kgroup, total_kb - kb);
         const bool mine = turn == prod_id;
         if (++turn == num_prod) turn = 0;
-        const uint32_t fb = full_a + 8u * stage;
+        const uint32_t fb = full_sig + 8u * stage;
         if (mine) {
             mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
-            if (elect_one()) mbar_arrive_expect_tx_a(fb, kb_bytes * (uint32_t)nk);
+            if (arm && elect_one()) mbar_arrive_expect_tx_a(full_a + 8u * stage, tx_mult * kb_bytes * (uint32_t)nk);
             __syncwarp();
         }
         for (int j = 0; j < nk; ++j, ++kb) {
@@ -540,11 +612,11 @@ __device__ __forceinline__ void produce_tile(const GemmParams& p, int m_tile, in
                 const uint32_t a_dst = pipe_base + stage_off + (uint32_t)(j * kAStageBytes);
                 const uint32_t b_dst = pipe_base + stage_off + b_base + (uint32_t)j * b_atom;
                 if (conv) {
-                    tma_load_4d_a(a_dst, map_cur, fb, k * kBlockK, dx, img0, y0 + t3 - 1);
-                    tma_load_2d_a(b_dst, mapb, fb, ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, n0);
+                    ld4d(a_dst, map_cur, fb, k * kBlockK, dx, img0, y0 + t3 - 1);
+                    ld2d(b_dst, mapb, fb, ((t3 * 3 + dx + 1) * b_kb_per_tap + koff) * kBlockK, b_row0);
                 } else {
-                    tma_load_2d_a(a_dst, map_cur, fb, k * kBlockK, row);
-                    tma_load_2d_a(b_dst, mapb, fb, koff * kBlockK, n0);
+                    ld2d(a_dst, map_cur, fb, k * kBlockK, row);
+                    ld2d(b_dst, mapb, fb, koff * kBlockK, b_row0);
                 }
                 if (ticks && kb == 0) ticks[2] = globaltimer_ns();
             }
@@ -571,10 +643,16 @@ __device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, 
                                          uint32_t pipe_base, uint32_t full_a, uint32_t empty_a, uint32_t tmem_acc,
                                          uint32_t done_bar, int& stage, uint32_t& phase, uint32_t& stage_off,
                                          long long* ticks, int tick_issue, int tick_done,
-                                         uint32_t reuse_a_bytes = 0, uint32_t reuse_dy_bytes = 0) {
-    const uint32_t idesc = umma_idesc_bf16_f32(kBlockM, block_n);
+                                         uint32_t reuse_a_bytes = 0, uint32_t reuse_dy_bytes = 0, int pair = 0) {
+    // pair != 0: cta_group::2 MMAs of M = 256 over this CTA's and the peer's shared memory (each holds half of the B rows);
+    // commits are multicast to the barriers at the same offsets in both CTAs
+    const uint32_t idesc = umma_idesc_bf16_f32(pair ? 2 * kBlockM : kBlockM, block_n);
     const uint64_t desc0 = umma_smem_desc_sw128(pipe_base);       // + (byte offset >> 4) selects stage / atom / k-slice
-    const uint32_t b_atom = (uint32_t)(block_n * kBlockK * 2);
+    const uint32_t b_atom = (uint32_t)((pair ? (block_n >> 1) : block_n) * kBlockK * 2);
+    auto mma = [pair](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (pair) umma_bf16_pair(d, a, b, id, acc); else umma_bf16(d, a, b, id, acc);
+    };
+    auto commit = [pair](uint32_t bar) { if (pair) umma_commit_pair(bar, (uint16_t)3); else umma_commit_a(bar); };
     if (reuse_a_bytes != 0) {
         // conv_reuse: total_kb counts k-blocks (9 taps); a stage holds the three dy taps of one (channel block, dx):
         // tap dy reads the haloed A box from row offset (dy + 1) * box_n * s (a whole number of 8-row swizzle atoms)
@@ -590,11 +668,11 @@ __device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, 
                     const uint64_t b_desc = desc0 + (uint64_t)((stage_off + reuse_a_bytes + (uint32_t)t3 * b_atom) >> 4);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | t3 | k) != 0 ? 1u : 0u);
+                        mma(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (it | t3 | k) != 0 ? 1u : 0u);
                 }
-                umma_commit_a(empty_a + 8u * stage);
+                commit(empty_a + 8u * stage);
                 if (it == n_stage - 1) {
-                    umma_commit_a(done_bar);
+                    commit(done_bar);
                     if (ticks && tick_done >= 0) ticks[tick_done] = globaltimer_ns();
                 }
             }
@@ -617,12 +695,12 @@ __device__ __forceinline__ void mma_tile(int block_n, int total_kb, int stages, 
 #pragma unroll
                 for (int k = 0; k < kBlockK / 16; ++k) {
                     // advance 16 bf16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb + j) | k) != 0 ? 1u : 0u);
+                    mma(tmem_acc, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, ((kb + j) | k) != 0 ? 1u : 0u);
                 }
             }
-            umma_commit_a(empty_a + 8u * stage);          // smem stage reusable once these MMAs retire
+            commit(empty_a + 8u * stage);                 // smem stage reusable once these MMAs retire
             if (kb + nk == total_kb) {
-                umma_commit_a(done_bar);                  // accumulator complete
+                commit(done_bar);                         // accumulator complete
                 if (ticks && tick_done >= 0) ticks[tick_done] = globaltimer_ns();
             }
         }
@@ -862,16 +940,18 @@ gemm_tc_pair_kernel(const GemmParams* __restrict__ params, int stages, const Gem
         prefetch_next_weights(next, next_groups, (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, gridDim.x * gridDim.y * gridDim.z);
     const GemmParams& p = params[blockIdx.z];
     const uint32_t rank = cluster_ctarank();             // cluster = 2 consecutive CTAs along x
-    const int m_tile = blockIdx.x;                       // this CTA's 128 rows: pair tile blockIdx.x / 2, half `rank`
+    const int m_tile = blockIdx.x;                       // this CTA's 128 rows (conv: its box of images / rows): pair blockIdx.x / 2, half `rank`
     const int n0 = blockIdx.y * p.block_n;
-    if ((m_tile >> 1) * 2 * kBlockM >= p.M || n0 >= p.N) return;      // uniform over the pair
+    if ((m_tile >> 1) * 2 * kBlockM >= p.M || n0 >= p.N) return;      // uniform over the pair (grouped launches: smaller members)
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
     if ((smem_u32(smem) & 1023u) != 0u) { if (threadIdx.x == 0) printf("tmae: dynamic shared memory not 1024-byte aligned\n"); __trap(); }
     const int block_n = p.block_n;
     const int half_n = block_n >> 1;
-    const int stage_bytes = kAStageBytes + half_n * kBlockK * 2;
+    const bool reuse = p.in_mode == IN_CONV && p.conv_reuse != 0;
+    const uint32_t reuse_a_bytes = reuse ? (uint32_t)(p.a_halo_rows * kBlockK * 2) : 0u;
+    const int stage_bytes = reuse ? (int)reuse_a_bytes + 3 * half_n * kBlockK * 2 : kAStageBytes + half_n * kBlockK * 2;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* accum_bar = empty_bar + stages;
@@ -883,6 +963,7 @@ gemm_tc_pair_kernel(const GemmParams* __restrict__ params, int stages, const Gem
     while (tmem_cols < (uint32_t)block_n) tmem_cols <<= 1;
     int total_kb = 0;
     for (int sg = 0; sg < p.num_segs; ++sg) total_kb += p.seg_kblocks[sg];
+    total_kb *= p.num_taps;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -901,57 +982,18 @@ gemm_tc_pair_kernel(const GemmParams* __restrict__ params, int stages, const Gem
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
     if (warp == 0) {
-        // ===== TMA producer (both CTAs; warp-uniform) =====
-        const uint32_t full_leader = mapa_shared(full_a, 0);
-        const uint32_t tx = 2u * (uint32_t)stage_bytes;
-        const int row = m_tile * kBlockM;
-        const int brow = n0 + (int)rank * half_n;
-        int stage = 0, sg = 0, k = 0, skb_cur = p.seg_kblocks[0], koff = p.seg_b_kb0[0];
+        // ===== TMA producer (both CTAs) =====
+        int stage = 0;
         uint32_t phase = 0, stage_off = 0;
-        const void* map_cur = &p.a_map[0];
-        for (int kb = 0; kb < total_kb; ++kb) {
-            mbar_wait_a(empty_a + 8u * stage, phase ^ 1u);
-            if (elect_one()) {
-                if (rank == 0) mbar_arrive_expect_tx_a(full_a + 8u * stage, tx);
-                tma_load_2d_pair(smem_base + stage_off, map_cur, full_leader + 8u * stage, k * kBlockK, row);
-                tma_load_2d_pair(smem_base + stage_off + kAStageBytes, &p.b_map_pair, full_leader + 8u * stage, koff * kBlockK, brow);
-            }
-            __syncwarp();
-            ++koff;
-            if (++k == skb_cur) {
-                k = 0;
-                if (++sg == p.num_segs) sg = 0;
-                skb_cur = p.seg_kblocks[sg];
-                koff = p.seg_b_kb0[sg];
-                map_cur = &p.a_map[sg];
-            }
-            stage_off += (uint32_t)stage_bytes;
-            if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-        }
+        produce_tile(p, m_tile, n0, total_kb, stages, 1, stage_bytes, smem_base, full_a, empty_a, stage, phase, stage_off, nullptr,
+                     0, 1, 1, rank, mapa_shared(full_a, 0));
     } else if (warp == 1) {
         if (rank == 0) {
-            // ===== MMA issuer (leader only; warp-uniform) =====
-            const uint32_t idesc = umma_idesc_bf16_f32(2 * kBlockM, block_n);
-            const uint64_t desc0 = umma_smem_desc_sw128(smem_base);
-            const uint32_t accum_a = smem_u32(accum_bar);
+            // ===== MMA issuer (leader only) =====
             int stage = 0;
             uint32_t phase = 0, stage_off = 0;
-            for (int kb = 0; kb < total_kb; ++kb) {
-                mbar_wait_a(full_a + 8u * stage, phase);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t a_desc = desc0 + (uint64_t)(stage_off >> 4);
-                    const uint64_t b_desc = desc0 + (uint64_t)((stage_off + (uint32_t)kAStageBytes) >> 4);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)
-                        umma_bf16_pair(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_pair(empty_a + 8u * stage, (uint16_t)3);
-                    if (kb + 1 == total_kb) umma_commit_pair(accum_a, (uint16_t)3);
-                }
-                __syncwarp();
-                stage_off += (uint32_t)stage_bytes;
-                if (++stage == stages) { stage = 0; phase ^= 1u; stage_off = 0; }
-            }
+            mma_tile(block_n, total_kb, stages, 1, stage_bytes, smem_base, full_a, empty_a, tmem_base, smem_u32(accum_bar),
+                     stage, phase, stage_off, nullptr, -1, -1, reuse_a_bytes, (uint32_t)(p.box_n * p.s * kBlockK * 2), 1);
         }
     } else {
         // ===== epilogue (both CTAs, own TMEM lanes = own 128 rows); staging reuses the idle pipeline buffers =====
@@ -1067,6 +1109,9 @@ cudaError_t gemm_tc_configure() {
         if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_SAME>)) != cudaSuccess) return e;
         if ((e = cfgp(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_SAME>)) != cudaSuccess) return e;
         if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_F32_SAME_RESID>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_NONE, EPI_GENERIC>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_GELU, EPI_GENERIC>)) != cudaSuccess) return e;
+        if ((e = cfgp(gemm_tc_pair_kernel<ACT_HALF_TANH, EPI_GENERIC>)) != cudaSuccess) return e;
     }
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>);
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>);
@@ -1097,16 +1142,26 @@ int gemm_epi_kind(const GemmParams& p) {
     return EPI_GENERIC;
 }
 
-// params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
-// CTA-pair launches: linear layers with one bf16 / fp32+residual same-row output, block_n % 32 == 0, enough rows to fill
-// the machine with pairs.  TMAE_NO_PAIR=1 switches them off (A/B).
-bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok) {
+// CTA-pair policy.  Linear layers: one bf16 / fp32+residual same-row output and >= 8 row tiles (the encoder GEMMs).  3x3 conv
+// layers: >= 8 row tiles and a weight tile of >= 64 columns (below that the B tile is too small for halving it to matter and
+// the launch is latency bound).  block_n % 16 == 0 always holds.  TMAE_NO_PAIR=1 / TMAE_NO_PAIR_CONV=1 switch them off (A/B).
+bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok, bool conv) {
     static const bool off = getenv("TMAE_NO_PAIR") != nullptr;
-    if (off || !pair_ok || groups != 1 || (block_n & 31) != 0 || max_M < 8 * kBlockM) return false;
+    static const bool off_conv = getenv("TMAE_NO_PAIR_CONV") != nullptr;
+    if (off || !pair_ok || max_M < 8 * kBlockM) return false;
+    if (conv) return !off_conv && block_n >= 64;
+    if (groups != 1) return false;
     if (epi == EPI_F32_SAME_RESID) return act == ACT_NONE;
     return (epi == EPI_BF16_SAME || epi == EPI_BF16_TMA) && (act == ACT_NONE || act == ACT_GELU);
 }
 
+template <int ACT, int EPI>
+static cudaError_t launch_pair(dim3 grid, int smem, cudaStream_t stream, const GemmParams* d_params, int stages, const GemmParams* d_next,
+                               int next_groups) {
+    return launch_k_cluster(gemm_tc_pair_kernel<ACT, EPI>, grid, dim3(kGemmThreads), smem, stream, true, 2, d_params, stages, d_next, next_groups);
+}
+
+// params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups,
                         int conv_reuse_stage_bytes, bool pair) {
@@ -1117,24 +1172,26 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     }
     int smem = 0;
     dim3 grid((max_M + kBlockM - 1) / kBlockM, (max_N + block_n - 1) / block_n, groups);
-    if (pair) {                                               // the plan's policy (gemm_use_pair) decided; hard requirements only
-        if (groups != 1 || (block_n & 31) != 0 || !(epi == EPI_BF16_SAME || epi == EPI_BF16_TMA || epi == EPI_F32_SAME_RESID) ||
-            act == ACT_HALF_TANH || (epi == EPI_F32_SAME_RESID && act != ACT_NONE))
-            return cudaErrorInvalidConfiguration;
-        dim3 pgrid((grid.x + 1) / 2 * 2, grid.y, 1);           // whole pairs along x
-        const int stage_bytes = kAStageBytes + (block_n / 2) * kBlockK * 2;
+    if (pair) {                                               // the plan's policy (gemm_use_pair) decided
+        if ((block_n & 15) != 0) return cudaErrorInvalidConfiguration;
+        dim3 pgrid((grid.x + 1) / 2 * 2, grid.y, groups);      // whole pairs along x
+        // conv_reuse_stage_bytes is the PAIR stage here (haloed A box + three half B atoms), computed by the plan
+        const int stage_bytes = conv_reuse_stage_bytes > 0 ? conv_reuse_stage_bytes : kAStageBytes + (block_n / 2) * kBlockK * 2;
         const int overhead = 256;
-        const bool whole_sm = (int)(pgrid.x * pgrid.y) <= 148 && !share_sm;
+        const bool whole_sm = (int)(pgrid.x * pgrid.y * pgrid.z) <= 148 && !share_sm;
         const int budget = (whole_sm ? 226 : 113) * 1024 - overhead;
         int pst = budget / stage_bytes;
-        if (pst > 8) pst = 8;
+        if (pst > (conv_reuse_stage_bytes > 0 ? 4 : 8)) pst = conv_reuse_stage_bytes > 0 ? 4 : 8;
         if (pst < 2) return cudaErrorInvalidConfiguration;
         const int psmem = overhead + pst * stage_bytes;
-        if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_TMA>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
-        if (epi == EPI_BF16_TMA) return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_TMA>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
-        if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_kernel<ACT_GELU, EPI_BF16_SAME>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
-        if (epi == EPI_BF16_SAME) return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_BF16_SAME>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
-        return launch_k_cluster(gemm_tc_pair_kernel<ACT_NONE, EPI_F32_SAME_RESID>, pgrid, dim3(kGemmThreads), psmem, stream, true, 2, d_params, pst, d_next, next_groups);
+        if (epi == EPI_BF16_TMA) return act == ACT_GELU ? launch_pair<ACT_GELU, EPI_BF16_TMA>(pgrid, psmem, stream, d_params, pst, d_next, next_groups)
+                                                        : launch_pair<ACT_NONE, EPI_BF16_TMA>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
+        if (epi == EPI_BF16_SAME) return act == ACT_GELU ? launch_pair<ACT_GELU, EPI_BF16_SAME>(pgrid, psmem, stream, d_params, pst, d_next, next_groups)
+                                                         : launch_pair<ACT_NONE, EPI_BF16_SAME>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
+        if (epi == EPI_F32_SAME_RESID) return launch_pair<ACT_NONE, EPI_F32_SAME_RESID>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
+        if (act == ACT_GELU) return launch_pair<ACT_GELU, EPI_GENERIC>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
+        if (act == ACT_HALF_TANH) return launch_pair<ACT_HALF_TANH, EPI_GENERIC>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
+        return launch_pair<ACT_NONE, EPI_GENERIC>(pgrid, psmem, stream, d_params, pst, d_next, next_groups);
     }
     if (conv_reuse_stage_bytes == 0 && gemm_use_persistent(groups, epi, act, (int)(grid.x * grid.y), share_sm)) {
         const int stage_bytes = kAStageBytes + block_n * kBlockK * 2;

@@ -24,7 +24,7 @@ int gemm_epi_kind(const GemmParams& p);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream,
                         const GemmParams* d_next = nullptr, int next_groups = 0, int conv_reuse_stage_bytes = 0, bool pair = false);
-bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok);
+bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok, bool conv);
 int gemm_reuse_stages(int stage_bytes, int total_ctas, bool share_sm, int* smem_bytes);
 
 // mask.cu
@@ -65,7 +65,9 @@ cudaError_t launch_copy_outputs(const IoBlock* io, const float* y, const float* 
                                 const float* yhat, const int64_t* ids_keep, long long n_y, long long n_z, long long n_ids,
                                 cudaStream_t st);
 cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, int Cin_total, int taps, int nseg,
-                                  const int* segc, int shuffle, int planes, cudaStream_t st);
+                                  const int* segc, int shuffle, int planes, cudaStream_t st, const float* gamma = nullptr);
+cudaError_t launch_fold_ln(const float* w, const float* beta, const float* bias, const __nv_bfloat16* packed, int Kp, int Cout, int Cin,
+                           float* bias_out, float* wsum, cudaStream_t st);
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st);
 cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st);

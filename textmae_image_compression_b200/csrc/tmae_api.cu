@@ -39,6 +39,7 @@ struct Layer {                      // one prepacked linear / conv
     __nv_bfloat16* w = nullptr;     // [Cout, Kp]
     float* bias = nullptr;          // [Cout] (permuted for PixelShuffle layers)
     int Cout = 0, Cin = 0, taps = 1, nseg = 1, segc[3] = {0, 0, 0}, Kp = 0, shuffle = 0;
+    float* wsum = nullptr;          // LayerNorm folded into this linear (W' = W diag(gamma), bias' = bias + W beta): row sums of bf16(W')
     int planes = 1;                 // 2 / 3 = precise layer: every tap holds the hi planes of its segments, then the lo (mid, lo) planes
     int kb_tap = 0;                 // k-blocks of one plane of one tap
 };
@@ -93,6 +94,8 @@ struct Workspace {
     // encoder
     int64_t* ids_keep = nullptr;
     Bf patches, xn, qkv, attn, h1, enc;
+    Bf x_bf;                         // bf16 copy of the residual stream (A operand of the LayerNorm-folded QKV / fc1)
+    float* ln_stats = nullptr;       // [2 * depth][N * T][C / 32][2]: (sum x, sum x^2) partials per LayerNorm, token and 32-column chunk
     float* x = nullptr;
     // g_a
     Bf ga1, ga2, ga3, y_bf;
@@ -135,6 +138,7 @@ struct tmae_handle {
     bool use_graph = true;           // TMAE_NO_GRAPH=1 disables CUDA-graph replay
     bool precise_rate = false;       // TMAE_FLAG_PRECISE_RATE / _ALL: split-bf16 layers after the encoder
     bool precise_enc = false;        // TMAE_FLAG_PRECISE_ALL: the encoder as well
+    bool ln_fold = false;            // bf16 encoder: LayerNorm of the blocks folded into proj / fc2 (statistics) and QKV / fc1 (apply)
     int planes = 2;                  // bf16 planes per operand of a precise layer: 2 (3 terms) or 3 (TMAE_FLAG_PRECISE_X6, 6 terms)
     cudaStream_t cap_stream = nullptr;
     // profiling
@@ -283,7 +287,7 @@ int need_raw(tmae_handle* h, const std::string& name, size_t numel, const RawTen
 
 // Prepack one conv / linear: weight [Cout, Cin, taps] fp32 -> bf16 [Cout, Kp]; bias fp32 (permuted if shuffle).
 int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname, int Cout, int Cin, int taps, int nseg,
-               const int* segc, int shuffle, bool precise) {
+               const int* segc, int shuffle, bool precise, const std::string& fold_ln = std::string()) {
     const RawTensor *w = nullptr, *b = nullptr;
     int rc = need_raw(h, wname + ".weight", (size_t)Cout * Cin * taps, &w);
     if (rc) return rc;
@@ -310,6 +314,16 @@ int pack_layer(tmae_handle* h, const std::string& key, const std::string& wname,
     if (rc) return rc;
     rc = dev_alloc(h, h->weight_allocs, &L.bias, (size_t)Cout);
     if (rc) return rc;
+    if (!fold_ln.empty()) {            // LayerNorm `fold_ln` (.weight / .bias) folded into this linear layer
+        const RawTensor *g = nullptr, *be = nullptr;
+        if (taps != 1 || nseg != 1 || shuffle || precise) return fail(h, TMAE_EINVAL, "layer %s: LayerNorm fold needs a plain bf16 linear", key.c_str());
+        if ((rc = need_raw(h, fold_ln + ".weight", (size_t)Cin, &g)) || (rc = need_raw(h, fold_ln + ".bias", (size_t)Cin, &be))) return rc;
+        if ((rc = dev_alloc(h, h->weight_allocs, &L.wsum, (size_t)Cout))) return rc;
+        CUDA_TRY(h, launch_prepack_weight(w->ptr, L.w, Cout, Cin, taps, nseg, L.segc, shuffle, L.planes, 0, g->ptr));
+        CUDA_TRY(h, launch_fold_ln(w->ptr, be->ptr, b->ptr, L.w, L.Kp, Cout, Cin, L.bias, L.wsum, 0));
+        h->layers[key] = L;
+        return TMAE_OK;
+    }
     CUDA_TRY(h, launch_prepack_weight(w->ptr, L.w, Cout, Cin, taps, nseg, L.segc, shuffle, L.planes, 0));
     if (shuffle) CUDA_TRY(h, launch_permute_bias_shuffle(b->ptr, L.bias, Cout, 0));
     else CUDA_TRY(h, cudaMemcpyAsync(L.bias, b->ptr, (size_t)Cout * sizeof(float), cudaMemcpyDeviceToDevice, 0));
@@ -453,6 +467,9 @@ struct GemmDesc {
     int act = ACT_NONE;
     const float* resid = nullptr; int resid_ld = 0; int resid_map = MAP_SAME;
     const int64_t* gather_ids = nullptr;
+    const float* ln_stats_in = nullptr;     // folded LayerNorm, consumer side (the layer's pack carries gamma / beta / wsum)
+    float* ln_stats_out = nullptr;          // producer side: statistics + bf16 copy of the output rows
+    __nv_bfloat16* xbf_out = nullptr;
     OutSpec out0 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
     OutSpec out1 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
     double flops = 0;
@@ -521,7 +538,7 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     int rc = make_map(h, &p->b_map, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)p->block_n);
     if (rc) return rc;
     p->pair_ok = 0;
-    if (!conv && (p->block_n & 31) == 0) {               // CTA-pair launches stage half of the weight tile per CTA
+    if ((p->block_n & 15) == 0) {                        // CTA-pair launches stage half of the weight tile per CTA
         rc = make_map(h, &p->b_map_pair, L.w, (uint64_t)L.Kp, (uint64_t)L.Cout, (uint64_t)L.Kp, (uint32_t)(p->block_n / 2));
         if (rc) return rc;
         p->pair_ok = 1;
@@ -547,6 +564,11 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->act = d.act;
     p->resid = d.resid; p->resid_ld = d.resid_ld; p->resid_map = d.resid_map;
     p->gather_ids = d.gather_ids;
+    if ((d.ln_stats_in != nullptr) != (L.wsum != nullptr)) return fail(h, TMAE_EINVAL, "LayerNorm fold: layer pack and plan disagree");
+    p->ln_stats_in = d.ln_stats_in; p->ln_wsum = L.wsum; p->ln_inv_c = 1.0f / (float)L.Cin; p->ln_eps = h->cfg.ln_eps;
+    p->ln_chunks = L.Cin / 32;
+    if (d.ln_stats_out != nullptr && L.Cout % 32 != 0) return fail(h, TMAE_EINVAL, "LayerNorm statistics need Cout %% 32 == 0");
+    p->ln_stats_out = d.ln_stats_out; p->xbf_out = d.xbf_out;
     p->out[0] = d.out0;
     p->out[1] = d.out1;
     p->flops = d.flops;
@@ -585,6 +607,8 @@ int ensure_workspace(tmae_handle* h, int N) {
     WS_ALLOC_BF(w.patches, rk * h->patch_dim, pe);
     WS_ALLOC(w.x, rt * C);
     WS_ALLOC_BF(w.xn, rt * C, pe);
+    WS_ALLOC_BF(w.x_bf, rt * C, false);
+    WS_ALLOC(w.ln_stats, (size_t)2 * h->cfg.encoder_depth * rt * (C / 32) * 2);
     WS_ALLOC_BF(w.qkv, rt * 3 * C, pe);
     WS_ALLOC_BF(w.attn, rt * C, pe);
     WS_ALLOC_BF(w.h1, rt * h->mlp, pe);
@@ -658,14 +682,15 @@ double conv_flops(long long out_positions, int cin, int cout, int taps) {
 
 // conv_reuse decision for one launch: the geometry must allow it and at least two stages (one haloed A box + three B
 // atoms each) must fit the launch's shared-memory budget.  Returns the stage size in bytes, 0 = per-tap loads.
-int conv_reuse_stage_bytes(const tmae_handle* h, const GemmDesc& d, int bn, int n_tiles, int groups) {
+int conv_reuse_stage_bytes(const tmae_handle* h, const GemmDesc& d, int bn, int n_tiles, int groups, bool pair = false) {
     if (d.in_mode != IN_CONV) return 0;
     ConvGeom cg;
     if (!conv_geom(d.side, d.n_img, &cg) || !cg.reuse_ok) return 0;
+    const int bn_cta = pair ? bn / 2 : bn;             // B rows this CTA stages (a pair splits the weight tile)
     // a tap's MMA always reads 128 rows from its dy offset: with a partial tile the rows past the A box must still lie
     // inside the stage (they land in the B atoms; the accumulator rows they feed are never stored)
-    if (cg.rows_used + 3 * bn < kBlockM) return 0;
-    const int stage = ((cg.box_y + 2) * cg.box_n * d.side + 3 * bn) * kBlockK * 2;
+    if (cg.rows_used + 3 * bn_cta < kBlockM) return 0;
+    const int stage = ((cg.box_y + 2) * cg.box_n * d.side + 3 * bn_cta) * kBlockK * 2;
     int smem = 0;
     const bool share = (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0;
     return gemm_reuse_stages(stage, cg.m_tiles * n_tiles * groups, share, &smem) >= 2 ? stage : 0;
@@ -706,10 +731,22 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         const bool conv_layer = descs[0].in_mode == IN_CONV;
         if (all_bf16_same && bn % 32 != 0 && bn + 16 <= 256 && (round_mode == 1 || (round_mode == 2 && !conv_layer))) bn += 16;
     }
-    for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant
-        if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF) bn = (bn + 31) / 32 * 32;
+    for (int g = 0; g < groups; ++g)       // PixelShuffle epilogue: a 32-column chunk must not straddle a quadrant;
+        if (descs[g].out0.map == MAP_SHUF || descs[g].out1.map == MAP_SHUF || descs[g].ln_stats_out != nullptr)
+            bn = (bn + 31) / 32 * 32;      // LayerNorm statistics: one slot per 32-column chunk, owned by exactly one tile
+    // CTA-pair launch?  (decided before the stage sizes: a pair stages half of the weight tile per CTA)
+    {
+        const bool conv_l = descs[0].in_mode == IN_CONV;
+        bool one_bf16 = descs[0].out0.dtype == OUT_BF16 && descs[0].out0.map == MAP_SAME && descs[0].out1.dtype == OUT_NONE && descs[0].resid == nullptr;
+        bool f32_resid = descs[0].out0.dtype == OUT_F32 && descs[0].out0.map == MAP_SAME && descs[0].out1.dtype == OUT_NONE &&
+                         descs[0].resid != nullptr && descs[0].resid_map == MAP_SAME && descs[0].act == ACT_NONE;
+        const int epi_hint = one_bf16 ? 1 : (f32_resid ? 2 : 0);
+        st.pair = !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && (bn & 15) == 0 &&
+                  gemm_use_pair(groups, epi_hint, descs[0].act, max_M, bn, true, conv_l);
+        for (int g = 1; g < groups; ++g) if (descs[g].in_mode != descs[0].in_mode) st.pair = false;
+    }
     // 3x3 conv launches: haloed-box A reuse when every member agrees on the geometry and the stages fit
-    st.conv_reuse_stage_bytes = conv_reuse_stage_bytes(h, descs[0], bn, (max_N + bn - 1) / bn, groups);
+    st.conv_reuse_stage_bytes = conv_reuse_stage_bytes(h, descs[0], bn, (max_N + bn - 1) / bn, groups, st.pair);
     for (int g = 1; g < groups; ++g)
         if (descs[g].in_mode != descs[0].in_mode || descs[g].side != descs[0].side || descs[g].n_img != descs[0].n_img) st.conv_reuse_stage_bytes = 0;
     for (int g = 0; g < groups; ++g) {
@@ -725,8 +762,12 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         st.flops += descs[g].flops;
         st.mma_terms = p.mma_terms;
     }
+    if (descs[0].ln_stats_in != nullptr && st.epi != 3 /*EPI_BF16_TMA*/)
+        return fail(h, TMAE_EINVAL, "%s: a LayerNorm-folded layer needs the TMA-store epilogue (epi %d)", tag, st.epi);
+    if (descs[0].ln_stats_out != nullptr && st.epi != 2 /*EPI_F32_SAME_RESID*/)
+        return fail(h, TMAE_EINVAL, "%s: LayerNorm statistics need the fp32 residual epilogue (epi %d)", tag, st.epi);
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
-    st.pair = !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && gemm_use_pair(groups, st.epi, st.act, max_M, bn, pl.host_params[st.param_index].pair_ok != 0);
+    if (st.pair && !pl.host_params[st.param_index].pair_ok) st.pair = false;
     static const bool plan_debug = getenv("TMAE_PLAN_DEBUG") != nullptr;
     if (plan_debug)
         fprintf(stderr, "[plan] %-14s groups %2d M %6d N %4d bn %3d ctas %4d epi %d conv_reuse_stage %6d B pair %d\n", tag, groups, max_M, max_N, bn,
@@ -787,11 +828,20 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
     }
     for (int i = 0; i < h->cfg.encoder_depth; ++i) {
         const std::string pre = "encoder_blocks." + std::to_string(i);
-        Step ln; ln.kind = ST_LN; ln.family = FAM_LN; ln.ln_gamma = h->vecs[pre + ".norm1.weight"]; ln.ln_beta = h->vecs[pre + ".norm1.bias"]; ln.tag = pre + ".norm1";
-        pl.steps.push_back(ln);
+        // LayerNorm fold (bf16 encoder): norm1 of block 0 follows the patch embed + cls rows and stays a kernel; every other
+        // block LayerNorm lives in the GEMMs around it - proj / fc2 emit row statistics + a bf16 copy of x, QKV / fc1 apply them
+        const bool fold1 = h->ln_fold && i > 0, fold2 = h->ln_fold;
+        const size_t stat_stride = (size_t)rt * (C / 32) * 2;
+        float* stats1 = w.ln_stats + (size_t)(2 * i) * stat_stride;          // statistics of x entering norm1 / norm2 of block i
+        float* stats2 = w.ln_stats + (size_t)(2 * i + 1) * stat_stride;
+        if (!fold1) {
+            Step ln; ln.kind = ST_LN; ln.family = FAM_LN; ln.ln_gamma = h->vecs[pre + ".norm1.weight"]; ln.ln_beta = h->vecs[pre + ".norm1.bias"]; ln.tag = pre + ".norm1";
+            pl.steps.push_back(ln);
+        }
         GemmDesc d;
         d.layer = get_layer(h, pre + ".attn.qkv");
-        d.seg[0] = seg(w.xn, C, C); d.a_rows = rt; d.M = (int)rt;
+        d.seg[0] = fold1 ? seg(w.x_bf, C, C) : seg(w.xn, C, C); d.a_rows = rt; d.M = (int)rt;
+        if (fold1) d.ln_stats_in = stats1;
         d.out0 = outspec(w.qkv, 3 * C, MAP_SAME);
         d.flops = 2.0 * rt * C * 3.0 * C;
         snprintf(tag, sizeof(tag), "blk%d.qkv", i);
@@ -803,14 +853,18 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
         p2.seg[0] = seg(w.attn, C, C); p2.a_rows = rt; p2.M = (int)rt;
         p2.resid = w.x; p2.resid_ld = C; p2.resid_map = MAP_SAME;
         p2.out0 = outspec(w.x, C, OUT_F32, MAP_SAME);
+        if (fold2) { p2.ln_stats_out = stats2; p2.xbf_out = w.x_bf.p; }
         p2.flops = 2.0 * rt * C * (double)C;
         snprintf(tag, sizeof(tag), "blk%d.proj", i);
         rc = add_gemm_group(h, pl, &p2, 1, tag); if (rc) return rc;
-        Step ln2; ln2.kind = ST_LN; ln2.family = FAM_LN; ln2.ln_gamma = h->vecs[pre + ".norm2.weight"]; ln2.ln_beta = h->vecs[pre + ".norm2.bias"]; ln2.tag = pre + ".norm2";
-        pl.steps.push_back(ln2);
+        if (!fold2) {
+            Step ln2; ln2.kind = ST_LN; ln2.family = FAM_LN; ln2.ln_gamma = h->vecs[pre + ".norm2.weight"]; ln2.ln_beta = h->vecs[pre + ".norm2.bias"]; ln2.tag = pre + ".norm2";
+            pl.steps.push_back(ln2);
+        }
         GemmDesc f1;
         f1.layer = get_layer(h, pre + ".mlp.fc1");
-        f1.seg[0] = seg(w.xn, C, C); f1.a_rows = rt; f1.M = (int)rt; f1.act = ACT_GELU;
+        f1.seg[0] = fold2 ? seg(w.x_bf, C, C) : seg(w.xn, C, C); f1.a_rows = rt; f1.M = (int)rt; f1.act = ACT_GELU;
+        if (fold2) f1.ln_stats_in = stats2;
         f1.out0 = outspec(w.h1, h->mlp, MAP_SAME);
         f1.flops = 2.0 * rt * C * (double)h->mlp;
         snprintf(tag, sizeof(tag), "blk%d.fc1", i);
@@ -820,6 +874,9 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
         f2.seg[0] = seg(w.h1, h->mlp, h->mlp); f2.a_rows = rt; f2.M = (int)rt;
         f2.resid = w.x; f2.resid_ld = C; f2.resid_map = MAP_SAME;
         f2.out0 = outspec(w.x, C, OUT_F32, MAP_SAME);
+        if (h->ln_fold && i + 1 < h->cfg.encoder_depth) {                    // statistics for norm1 of the next block
+            f2.ln_stats_out = w.ln_stats + (size_t)(2 * i + 2) * stat_stride; f2.xbf_out = w.x_bf.p;
+        }
         f2.flops = 2.0 * rt * C * (double)h->mlp;
         snprintf(tag, sizeof(tag), "blk%d.fc2", i);
         rc = add_gemm_group(h, pl, &f2, 1, tag); if (rc) return rc;
@@ -1208,6 +1265,8 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     h->precise_enc = (h->cfg.flags & TMAE_FLAG_PRECISE_ALL) != 0;
     h->precise_rate = h->precise_enc || (h->cfg.flags & TMAE_FLAG_PRECISE_RATE) != 0;
     h->planes = (h->cfg.flags & TMAE_FLAG_PRECISE_X6) ? 3 : 2;
+    // the fold needs the thread-per-row TMA-store epilogue; the CUDA-core checker keeps the stand-alone LayerNorm path
+    h->ln_fold = !h->precise_enc && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && !getenv("TMAE_NO_LN_FOLD") && !getenv("TMAE_NO_TMA_STORE");
     *out = h.release();
     return TMAE_OK;
 }
@@ -1267,9 +1326,11 @@ int tmae_finalize_weights(tmae_handle* h) {
         for (const char* nm : {".norm1.weight", ".norm1.bias", ".norm2.weight", ".norm2.bias"})
             if ((rc = keep_vec(h, pre + nm, C))) return rc;
         int sgC[1] = {C}, sgM[1] = {h->mlp};
-        if ((rc = pack_layer(h, pre + ".attn.qkv", pre + ".attn.qkv", 3 * C, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
+        if ((rc = pack_layer(h, pre + ".attn.qkv", pre + ".attn.qkv", 3 * C, C, 1, 1, sgC, 0, h->precise_enc,
+                             (h->ln_fold && i > 0) ? pre + ".norm1" : std::string()))) return rc;
         if ((rc = pack_layer(h, pre + ".attn.proj", pre + ".attn.proj", C, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
-        if ((rc = pack_layer(h, pre + ".mlp.fc1", pre + ".mlp.fc1", h->mlp, C, 1, 1, sgC, 0, h->precise_enc))) return rc;
+        if ((rc = pack_layer(h, pre + ".mlp.fc1", pre + ".mlp.fc1", h->mlp, C, 1, 1, sgC, 0, h->precise_enc,
+                             h->ln_fold ? pre + ".norm2" : std::string()))) return rc;
         if ((rc = pack_layer(h, pre + ".mlp.fc2", pre + ".mlp.fc2", C, h->mlp, 1, 1, sgM, 0, h->precise_enc))) return rc;
     }
     if ((rc = keep_vec(h, "encoder_norm.weight", C))) return rc;
@@ -1536,7 +1597,7 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
         const int mt = (d.M + kBlockM - 1) / kBlockM;
         const int bn = block_n > 0 ? block_n : pick_block_n(mt, d.layer->Cout, 1);
         block_n = bn;
-        reuse_bytes = conv_reuse_stage_bytes(tmp, d, bn, (d.layer->Cout + bn - 1) / bn, 1);
+        reuse_bytes = conv_reuse_stage_bytes(tmp, d, bn, (d.layer->Cout + bn - 1) / bn, 1, pair && impl == 0);
         d.conv_reuse = reuse_bytes > 0;
     }
     int rc = fill_params(tmp, d, 1, &p, block_n);
@@ -1699,7 +1760,7 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
     d.a_rows = (long long)N * s * s; d.M = cg.m_tiles * kBlockM; d.in_mode = IN_CONV; d.side = s; d.n_img = N;
     d.act = gelu ? ACT_GELU : ACT_NONE;
     d.out0 = outspec(out, Cout, OUT_F32, MAP_SAME);
-    rc = engine_common(tmp.get(), d, 0, impl, st);
+    rc = engine_common(tmp.get(), d, 0, impl == 2 ? 0 : impl, st, impl == 2);      // impl 2: CTA-pair (cta_group::2) launch
     if (rc) g_create_error = tmp->err;
     free_pool(pool);
     return rc;
