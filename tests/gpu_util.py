@@ -36,6 +36,15 @@ def conv3x3(x_nhwc_bf16, w, bias, gelu=False, impl=0):
     return out
 
 
+def attention(qkv_bf16, N, T, H, impl=0):
+    """softmax(q k^T / 8) v over qkv bf16 [N*T, 3*H*64]; impl 0 = mma.sync kernel, 1 = tcgen05 kernel."""
+    out = torch.zeros(N * T, H * 64, dtype=torch.bfloat16, device=qkv_bf16.device)
+    rc = _native.load().tmae_attention_bf16(ptr(qkv_bf16.contiguous()), ptr(out), N, T, H, impl, stream())
+    _native.check(rc, None, RuntimeError)
+    torch.cuda.synchronize()
+    return out
+
+
 def gemm_resid(A_bf16, B_bf16, bias, resid, block_n=0, pair=0, impl=0):
     """C = resid + A @ B^T + bias (proj / fc2 store phase); pair=1 -> CTA-pair (cta_group::2) kernel."""
     M, K = A_bf16.shape

@@ -130,3 +130,18 @@ def test_conv3x3_pair_matches_single_cta(cuda_dev, N, s, Cin, Cout, gelu):
     two = G.conv3x3(x, w, b, gelu=gelu, impl=2)
     assert G.rel_err(two, ref) < 3e-5, G.rel_err(two, ref)
     assert torch.equal(one, two)
+
+
+@pytest.mark.parametrize("N,T,H", [(1, 17, 2), (3, 65, 2), (64, 65, 12), (2, 145, 12), (5, 129, 3), (1, 192, 1), (4, 128, 4)])
+@pytest.mark.parametrize("impl", [0, 1], ids=["mma_sync", "tcgen05"])
+def test_attention_matches_torch(cuda_dev, N, T, H, impl):
+    """Both attention kernels against fp32 softmax(q k^T / sqrt(64)) v of the same bf16 q, k, v (P is rounded to bf16 before
+    the second product in both kernels)."""
+    g = torch.Generator(device="cpu").manual_seed(N * 100 + T + H)
+    qkv = (torch.randn(N * T, 3 * H * 64, generator=g) * 1.5).to(cuda_dev).bfloat16()
+    q, k, v = qkv.float().reshape(N, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = (((q @ k.transpose(-2, -1)) * 0.125).softmax(-1) @ v).transpose(1, 2).reshape(N * T, H * 64)
+    out = G.attention(qkv, N, T, H, impl=impl).float()
+    err = G.rel_err(out, ref)
+    assert err < 6e-3, f"impl={impl} rel err {err}"
+    assert torch.isfinite(out).all()

@@ -6,6 +6,8 @@
 // warp-level MMA; the GEMM / conv engine (gemm_tc.cu) is where tcgen05 is spent.
 #include <math.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -263,6 +265,171 @@ inline size_t attn_f32_smem(int T) {
     return ((size_t)T * KP32 + (size_t)T * HD + (size_t)kAttnF32Warps * HD + (size_t)kAttnF32Warps * T) * sizeof(float);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 attention (bf16 mode, T <= 192): one CTA per (image, head).  Q, K, V tiles arrive by TMA straight out of the
+// qkv matrix; S = Q K^T and O = P V are tcgen05.mma with the accumulators in tensor memory; softmax runs thread-per-row on
+// the S row read back with tcgen05.ld (no shuffles), P goes to shared memory as the K-major 128B-swizzled A operand of the
+// second MMA, V is transposed in shared memory into the K-major B operand ([64 dims][keys]) while the first MMA runs.
+//   smem: Q [128 x 64] | K [Tp x 64] (both as TMA wrote them: SWIZZLE_128B, K-major) | V raw [Tp x 64] (no swizzle) |
+//         V^T [64 x keys] in 64-key atoms | P [128 x keys] in 64-key atoms.   TMEM: S at column 0 (Tp <= 192), O at 192.
+// Rows >= T of a tile belong to the next image (or are zero-filled at the end of the tensor): as keys they are masked in the
+// softmax, as queries they are computed and not stored.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAttnTcThreads = 128;
+constexpr int kAttnTcMaxTp = 192;
+constexpr uint32_t kAttnOCol = 192;
+
+__global__ void __launch_bounds__(kAttnTcThreads)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
+                    float scale_log2e) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(1024) uint8_t smem_tc[];
+    const int atoms = (Tp + 63) >> 6;
+    const uint32_t kbytes = (uint32_t)Tp * 128u;
+    const uint32_t kreg = (kbytes + 1023u) & ~1023u;
+    uint8_t* sQ = smem_tc;                               // 16 KB
+    uint8_t* sK = sQ + 16384;
+    uint8_t* sVr = sK + kreg;
+    uint8_t* sVt = sVr + kreg;                           // atoms x 8 KB
+    uint8_t* sP = sVt + (size_t)atoms * 8192;            // atoms x 16 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (size_t)atoms * 16384);     // load, s, o
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+    }
+    if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();
+
+    const uint32_t q_a = smem_u32(sQ), k_a = smem_u32(sK), vr_a = smem_u32(sVr), vt_a = smem_u32(sVt), p_a = smem_u32(sP);
+    const uint32_t bar_load = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
+    const int row0 = n * T;
+    const int q_tiles = (T + 127) >> 7;
+    for (int qt = 0; qt < q_tiles; ++qt) {
+        const uint32_t ph = (uint32_t)qt & 1u;
+        const int q0 = qt * 128;
+        if (tid == 0) {
+            mbar_arrive_expect_tx_a(bar_load, 16384u + (qt == 0 ? 2u * kbytes : 0u));
+            tma_load_2d_a(q_a, &map_q, bar_load, h * HD, row0 + q0);
+            if (qt == 0) {
+                tma_load_2d_a(k_a, &map_k, bar_load, C + h * HD, row0);
+                tma_load_2d_a(vr_a, &map_v, bar_load, 2 * C + h * HD, row0);
+            }
+        }
+        mbar_wait_a(bar_load, ph);
+        if (tid == 0) {                                   // S = Q K^T: M = 128, N = Tp, K = 64 in four k-steps
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16_f32(128, Tp);
+            const uint64_t dq = umma_smem_desc_sw128(q_a), dk = umma_smem_desc_sw128(k_a);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+            umma_commit_a(bar_s);
+        }
+        if (qt == 0) {
+            // V^T while the MMA runs: thread -> (dim d, every second 8-key chunk); 8 strided 2-byte reads, one 16-byte store
+            const int d = tid & 63;
+            for (int j0 = (tid >> 6) * 8; j0 < Tp; j0 += 16) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sVr + (size_t)(j0 + 2 * i) * 128 + d * 2);
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sVr + (size_t)(j0 + 2 * i + 1) * 128 + d * 2);
+                    pk[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+                }
+                const uint32_t dst = vt_a + (uint32_t)(j0 >> 6) * 8192u + (uint32_t)d * 128u + ((((uint32_t)(j0 & 63) >> 3) ^ (uint32_t)(d & 7)) << 4);
+                sts128(dst, pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+        // ---- softmax of this thread's query row (TMEM lane = row) ----
+        mbar_wait_a(bar_s, ph);
+        tc_fence_after();
+        const int row = warp * 32 + lane;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < Tp; c0 += 16) {
+            uint32_t sv[16];
+            tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, sv);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c0 + i < T) mx = fmaxf(mx, __uint_as_float(sv[i]));
+        }
+        const float mxs = mx * scale_log2e;
+        float sum = 0.f;
+        const uint32_t prow = p_a + (uint32_t)row * 128u;
+        for (int c0 = 0; c0 < Tp; c0 += 16) {
+            uint32_t sv[16];
+            tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, sv);
+            tmem_ld_wait();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float p0 = (c0 + 2 * i < T) ? exp2f(fmaf(__uint_as_float(sv[2 * i]), scale_log2e, -mxs)) : 0.f;
+                const float p1 = (c0 + 2 * i + 1 < T) ? exp2f(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2e, -mxs)) : 0.f;
+                sum += p0 + p1;
+                pk[i] = pack_bf16x2(p0, p1);
+            }
+            const uint32_t base = prow + (uint32_t)(c0 >> 6) * 16384u;
+            const uint32_t ch = (uint32_t)(c0 & 63) >> 3;
+            sts128(base + (((ch) ^ (uint32_t)(row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
+            sts128(base + (((ch + 1u) ^ (uint32_t)(row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async_smem();                         // P (and V^T) written through the generic proxy -> visible to the MMA
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {                                   // O = P V: M = 128, N = 64, K = Tp in Tp / 16 k-steps
+            tc_fence_after();
+            const uint32_t idesc = umma_idesc_bf16_f32(128, HD);
+            const uint64_t dp = umma_smem_desc_sw128(p_a), dv = umma_smem_desc_sw128(vt_a);
+            const int ksteps = Tp >> 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t a_desc = dp + (uint64_t)((uint32_t)(ks >> 2) * (16384u >> 4)) + (uint64_t)(2 * (ks & 3));
+                const uint64_t b_desc = dv + (uint64_t)((uint32_t)(ks >> 2) * (8192u >> 4)) + (uint64_t)(2 * (ks & 3));
+                umma_bf16(tmem + kAttnOCol, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
+            }
+            umma_commit_a(bar_o);
+        }
+        mbar_wait_a(bar_o, ph);
+        tc_fence_after();
+        const float inv = 1.f / sum;
+        const bool store = q0 + row < T;
+        __nv_bfloat16* dst = out + ((size_t)(row0 + q0 + row)) * C + (size_t)h * HD;
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+            uint32_t ov[32];
+            tmem_ld_32x32b_x32(lane_base + kAttnOCol + (uint32_t)c0, ov);
+            tmem_ld_wait();
+            if (store) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint4 pk;
+                    pk.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
+                    pk.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
+                    pk.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
+                    pk.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
+                    *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                  // S / O / P / Q are reused by the next query tile
+        tc_fence_after();
+    }
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+inline size_t attn_tc_smem(int Tp) {
+    const size_t kreg = ((size_t)Tp * 128 + 1023) & ~(size_t)1023;
+    const size_t atoms = (Tp + 63) / 64;
+    return 16384 + 2 * kreg + atoms * (8192 + 16384) + 64;
+}
+
 }  // namespace
 
 // The dynamic shared-memory limit is a property of the (process-global) kernel, not of a handle: it is raised to the
@@ -271,6 +438,8 @@ cudaError_t attention_configure(int T) {
     if (attn_smem(T) > 227 * 1024) return cudaErrorInvalidValue;
     static cudaError_t once = [] {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }();
@@ -284,6 +453,29 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
     TMAE_CARVEOUT_ONCE(attention_kernel);
     return launch_k(attention_kernel, dim3(N * H), dim3(kAttnThreads), attn_smem(T), st, true, qkv, out, T, Tp, H, C,
                     scale * 1.4426950408889634f);
+}
+
+// tcgen05 path: supported for head_dim 64 and T <= 192 (S row + O fit 256 TMEM columns); the tensor maps (Q: box 64 x 128,
+// K: 64 x Tp, both SWIZZLE_128B; V: 64 x Tp unswizzled) are built by the plan.
+// MEASURED (B200, batch 64): correct (tests/test_gpu_engine.py::test_attention_matches_torch) but SLOWER than the mma.sync
+// kernel - 25 us vs 18 us per launch at T = 65, 106 us vs 43 us at T = 145.  One (image, head) is a strictly serial chain
+// (TMA -> S MMA -> softmax -> P to smem -> PV MMA -> store, every hop a barrier round trip) and its 84-128 KB of shared
+// memory + 256 TMEM columns allow 1-2 CTAs per SM, against 6 CTAs / 30 warps of the mma.sync kernel: at these sizes
+// (0.8-3 % of the path's flops) occupancy beats the faster pipe.  It is therefore opt-in (TMAE_TC_ATTN=1); making it win
+// needs a warp-specialised kernel that pipelines several heads per CTA.
+bool attention_tc_supported(int T) { return attn_tp(T) <= kAttnTcMaxTp; }
+bool attention_tc_eligible(int T) {
+    static const bool on = getenv("TMAE_TC_ATTN") != nullptr;
+    return on && attention_tc_supported(T);
+}
+int attention_tc_tp(int T) { return attn_tp(T); }
+cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_k, const CUtensorMap* map_v, __nv_bfloat16* out,
+                                int N, int T, int H, int C, float scale, cudaStream_t st) {
+    if (C != H * HD) return cudaErrorInvalidValue;
+    const int Tp = attn_tp(T);
+    TMAE_CARVEOUT_ONCE(attention_tc_kernel);
+    return launch_k(attention_tc_kernel, dim3(N * H), dim3(kAttnTcThreads), attn_tc_smem(Tp), st, true, *map_q, *map_k, *map_v, out, T,
+                    Tp, H, C, scale * 1.4426950408889634f);
 }
 
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,

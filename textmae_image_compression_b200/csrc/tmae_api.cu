@@ -83,6 +83,8 @@ struct Plan {
     bool from_latent_ok = true;
     cudaGraphExec_t graph = nullptr; // whole forward (steps + output copies), pointers via the device IoBlock
     int calls = 0;                   // the first call runs plain launches (one-time function attributes), then capture
+    bool attn_tc = false;           // tcgen05 attention: tensor maps of Q / K / V tiles over this plan's qkv matrix
+    CUtensorMap attn_q, attn_k, attn_v;
     int first_rate_step = 0;        // index of the first step of the rate half (h_a)
     int encoder_end_step = 0;       // one past the final LayerNorm
 };
@@ -777,6 +779,25 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     return TMAE_OK;
 }
 
+// Tensor maps of the tcgen05 attention kernel: Q / K / V tiles of one (image, head) are 64-column boxes of qkv [rows, 3C]
+int make_attention_maps(tmae_handle* h, const __nv_bfloat16* qkv, long long rows, int C, int T, CUtensorMap* mq, CUtensorMap* mk, CUtensorMap* mv) {
+    const int Tp = attention_tc_tp(T);
+    cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
+    cuuint32_t estr[2] = {1, 1};
+    cuuint32_t box_q[2] = {64, 128}, box_k[2] = {64, (cuuint32_t)Tp};
+    void* base = const_cast<__nv_bfloat16*>(qkv);
+    CUresult r1 = h->encode(mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = h->encode(mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r3 = h->encode(mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS)
+        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(attention) failed (%d %d %d)", (int)r1, (int)r2, (int)r3);
+    return TMAE_OK;
+}
+
 SegSrc seg(const __nv_bfloat16* p, int cols, int ld, long long lo = 0) { SegSrc s; s.ptr = p; s.cols = cols; s.ld = ld; s.lo = lo; return s; }
 SegSrc seg(const Bf& b, int cols, int ld, int col0 = 0) { return seg(b.p + col0, cols, ld, b.lo); }
 OutSpec outspec(void* p, int ld, int dtype, int map, long long lo = 0) { OutSpec o; o.ptr = p; o.ld = ld; o.dtype = dtype; o.map = map; o.lo_off = lo; return o; }
@@ -812,6 +833,10 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
     };
     auto simple = [&](StepKind k, int fam, const char* t) { Step st; st.kind = k; st.family = fam; st.tag = t; pl.steps.push_back(st); };
 
+    if (!h->precise_enc && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && attention_tc_eligible(T)) {
+        if ((rc = make_attention_maps(h, w.qkv.p, rt, C, T, &pl.attn_q, &pl.attn_k, &pl.attn_v))) return rc;
+        pl.attn_tc = true;
+    }
     simple(ST_ZERO_RATE, FAM_MISC, "zero_rate");
     simple(ST_MASK, FAM_MASK, "mask_select");
     simple(ST_GATHER, FAM_GATHER, "gather_patches");
@@ -1135,6 +1160,8 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
             case ST_ATTN:
                 if (h->precise_enc)
                     CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                else if (pl.attn_tc)
+                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, &pl.attn_v, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else
                     CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 break;
@@ -1764,6 +1791,32 @@ int tmae_conv3x3_bf16(const void* x, const float* wgt, const float* bias, float*
     if (rc) g_create_error = tmp->err;
     free_pool(pool);
     return rc;
+}
+
+// softmax(q k^T / sqrt(64)) v for qkv bf16 [N*T, 3C] (columns [3][H][64]) -> out bf16 [N*T, C]: the attention kernels of the
+// encoder blocks stand-alone.  impl 0 = mma.sync kernel, 1 = tcgen05 / TMEM kernel (T <= 192).
+int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int impl, void* stream) {
+    if (!qkv || !out || N <= 0 || T <= 0 || H <= 0) return fail(nullptr, TMAE_EINVAL, "tmae_attention_bf16: invalid argument");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int C = H * 64;
+    cudaError_t e = attention_configure(T);
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
+    if (impl == 1) {
+        if (!attention_tc_supported(T)) return fail(nullptr, TMAE_EINVAL, "tcgen05 attention needs T <= 192");
+        CUtensorMap mq, mk, mv;
+        if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, &mq, &mk, &mv))) {
+            g_create_error = tmp->err; return rc;
+        }
+        e = launch_attention_tc(&mq, &mk, &mv, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st);
+    } else {
+        e = launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention launch: %s / %s", cudaGetErrorString(e), cudaGetErrorString(e2));
+    return TMAE_OK;
 }
 
 // x_out = resid + A B^T + bias (fp32 in / out, bf16 operands): the encoder's proj / fc2 epilogue.  pair = 1 runs the CTA-pair
