@@ -97,6 +97,19 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Gaussian conditional likelihood + quantisation of one element (compressai GaussianConditional eval forward + quantize_ste,
+// MCM.py:771-776): shared by gaussian_slice_kernel and the fused epilogue of the cc_transform nets' last layer.
+__device__ __forceinline__ void gaussian_elem(float y, float mu, float sigma, float& lik, float& sym, float& yhat) {
+    const float kNegInvSqrt2 = -0.70710678118654752440f;        // float(-(2 ** -0.5))
+    sym = rintf(y - mu);
+    yhat = sym + mu;
+    const float d = fabsf(yhat - mu);
+    const float s = fmaxf(sigma, 0.11f);
+    const float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - d) / s));
+    const float lower = 0.5f * erfcf(kNegInvSqrt2 * ((-0.5f - d) / s));
+    lik = fmaxf(upper - lower, 1e-9f);
+}
+
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
 // while its predecessor is still running; everything before pdl_wait() (barrier init, TMEM allocation, descriptor
 // prefetch) overlaps the predecessor's tail, pdl_wait() blocks until the predecessor has completed and flushed.

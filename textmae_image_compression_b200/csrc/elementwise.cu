@@ -222,17 +222,6 @@ cudaError_t launch_bottleneck(const float* z, const float* eb_tab, long long row
 //   y, mu, sigma, lik, sym, y_hat : fp32 / int32 [rows, ld] with channel offset col0, `cs` channels in the slice.
 //   yhat_bf (optional) : bf16 copy [rows, ld_bf], same channel offset: support for later slices.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void gaussian_elem(float y, float mu, float sigma, float& lik, float& sym, float& yhat) {
-    const float kNegInvSqrt2 = -0.70710678118654752440f;        // float(-(2 ** -0.5))
-    sym = rintf(y - mu);
-    yhat = sym + mu;
-    const float d = fabsf(yhat - mu);
-    const float s = fmaxf(sigma, 0.11f);
-    const float upper = 0.5f * erfcf(kNegInvSqrt2 * ((0.5f - d) / s));
-    const float lower = 0.5f * erfcf(kNegInvSqrt2 * ((-0.5f - d) / s));
-    lik = fmaxf(upper - lower, 1e-9f);
-}
-
 __global__ void __launch_bounds__(256)
 gaussian_slice_kernel(const float* __restrict__ y, const float* __restrict__ mu, const float* __restrict__ sigma,
                       long long rows, int ld, int col0, int cs, float* __restrict__ lik_out,
@@ -507,6 +496,40 @@ __global__ void permute_bias_shuffle_kernel(const float* __restrict__ b, float* 
     const int q = ro / cq, c = ro - q * cq;
     out[ro] = b[c * 4 + q];
 }
+// Block-diagonal pack of TWO conv layers that read different inputs into ONE GEMM (GemmParams::gc_on): output rows
+// [0, half) = layer A over K segment 0, rows [half, 2 half) = layer B over K segment 1, zeros elsewhere.  Same K layout as
+// prepack_weight_kernel with two segments of `Cin` channels each (tap-major, plane-major inside a tap).
+__global__ void prepack_blockdiag2_kernel(const float* __restrict__ wa, const float* __restrict__ wb, __nv_bfloat16* __restrict__ out,
+                                          int half, int Cin, int taps, int planes) {
+    const int segpad = ((Cin + 63) / 64) * 64;
+    const int kp_tap = 2 * segpad;
+    const long long Kp = (long long)kp_tap * taps * planes;
+    const long long total = (long long)(2 * half) * Kp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int ro = (int)(idx / Kp);
+        const long long kidx = idx - (long long)ro * Kp;
+        const int tap = (int)(kidx / (kp_tap * planes));
+        int within = (int)(kidx - (long long)tap * kp_tap * planes);
+        const int plane = within / kp_tap;
+        within -= plane * kp_tap;
+        const int sg = within / segpad, c = within - sg * segpad;
+        float v = 0.f;
+        if (c < Cin) {
+            if (ro < half && sg == 0) v = wa[((size_t)ro * Cin + c) * taps + tap];
+            else if (ro >= half && sg == 1) v = wb[((size_t)(ro - half) * Cin + c) * taps + tap];
+        }
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        const float r1 = v - __bfloat162float(hi);
+        const __nv_bfloat16 mid = __float2bfloat16(r1);
+        out[idx] = plane == 0 ? hi : (plane == 1 ? mid : __float2bfloat16(r1 - __bfloat162float(mid)));
+    }
+}
+cudaError_t launch_prepack_blockdiag2(const float* wa, const float* wb, __nv_bfloat16* out, int half, int Cin, int taps, int planes,
+                                      cudaStream_t st) {
+    prepack_blockdiag2_kernel<<<256, 256, 0, st>>>(wa, wb, out, half, Cin, taps, planes);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st) {
     permute_bias_shuffle_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(b, out, Cout);
     return cudaGetLastError();

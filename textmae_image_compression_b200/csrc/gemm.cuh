@@ -105,6 +105,25 @@ struct alignas(64) GemmParams {
     int ln_chunks;                    // C / 32 of the normalised rows
     float* ln_stats_out;              // [rows][N / 32][2] or nullptr
     __nv_bfloat16* xbf_out;           // [rows][N] or nullptr
+    // Gaussian conditional fused into the LAST layer of cc_transform_mean[i] and cc_transform_scale[i] (MCM.py:761-776): the two
+    // 3x3 convs (80 -> 32 channels, different inputs) run as ONE block-diagonal GEMM with 64 output columns - [0, 32) = mu,
+    // [32, 64) = sigma of slice i - and the epilogue (thread = pixel) quantises y, evaluates the likelihoods, emits symbols /
+    // scale-table indexes / y_hat and adds the pixel's log2-likelihood to its image's rate.  No gaussian_slice_kernel launch, mu
+    // and sigma never travel through HBM to be read back.
+    int gc_on;
+    int gc_col0;                      // first channel of the slice in the [rows, gc_ld] tensors
+    int gc_ld;                        // Cy
+    int gc_pixels;                    // pixels per image (rate accumulator index = row / gc_pixels)
+    const float* gc_y;                // [rows, Cy] latent
+    float* gc_mu;                     // [rows, Cy] workspace copies (parity outputs)
+    float* gc_sigma;
+    float* gc_yhat;                   // [rows, Cy] fp32 y_hat before LRP (the LRP net's last layer adds to it)
+    __nv_bfloat16* gc_yhat_bf;        // [rows, Cy] bf16 copy (+ planes, gc_yhat_lo): support of the later slices
+    long long gc_yhat_lo;
+    double* gc_rate;                  // [images] sum of log2 likelihoods
+    const float* gc_table;            // scale table for y_indexes (may be null)
+    int gc_ntable;
+    const void* gc_io;                // IoBlock*: the caller's y_likelihoods / y_symbols / y_symbols_i16 / y_indexes of this call
     double flops;                     // flops of this GEMM as the reference would count them for the rows computed (profiling)
     int mma_terms;                    // tensor-core products issued per algorithmic product: 1, or 3 / 6 for precise (split-bf16) layers
     long long* dbg_ticks;             // optional [ctas][8] globaltimer stamps of the kernel phases (bring-up)
