@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TMAE_ABI_VERSION 2
+#define TMAE_ABI_VERSION 3
 #if defined(__GNUC__)
 #define TMAE_API __attribute__((visibility("default")))
 #else
@@ -177,6 +177,21 @@ TMAE_API int  tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows,
 /* [N, hw, C] channels-last int32 -> [N, C, hw]: the order the reference feeds its range coder, slice by slice in
  * (c, y, x) order (MCM.py:867-873), for symbols and indexes alike. */
 TMAE_API int  tmae_pack_nchw_i32(const int32_t* nhwc, int32_t* nchw, int N, int hw, int C, void* stream);
+
+/* Patch-score generation (the reference's offline generator, generate_scores_file.py:19-31 = utils/map.py:6-60
+ * Division_Merge_Segmented + laplacian, utils/distribution.py:5-16 cal_patch_score, min-max normalisation): what
+ * `total_scores` of MCM.forward is made of.  gray: uint8 [n, height, width] (cv2.imread(..., IMREAD_GRAYSCALE) of each
+ * image, all of one size); out_side = 224 in the reference (any multiple of 16).  Any output may be NULL.  Bit-exact
+ * with the reference's numpy / OpenCV arithmetic (integer and float64 work; see csrc/scores.cu). */
+typedef struct {
+    float*   scores;          /* [n, (out_side/16)^2]  fp32, NaN where an image's scores are all equal (0/0, like numpy) */
+    uint8_t* s_map;           /* [n, out_side, out_side]  Division_Merge_Segmented(img, (out_side, out_side)) */
+    uint8_t* t_map;           /* [n, out_side, out_side]  laplacian(img, (out_side, out_side)) of the segmented image */
+    uint8_t* segmented;       /* [n, height, width]       the image after Recursion / Merge (utils/map.py:35-42) */
+} tmae_score_outputs;
+TMAE_API size_t tmae_scores_workspace_bytes(int n, int height, int width, int out_side);   /* 0 = invalid geometry */
+TMAE_API int  tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int out_side,
+                          const tmae_score_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tensor-core GEMM/conv engine self-test hook (tests): C[M,N] = A[M,K] * B[N,K]^T (+bias) with bf16 inputs,
  * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */

@@ -25,7 +25,7 @@ def test_header_symbols_are_exported(lib):
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.tmae_abi_version() == 2
+    assert lib.tmae_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

@@ -5,6 +5,7 @@ Public surface:
     PathConfig          geometry derived from the reference constructor arguments
     make_state_dict     seeded synthetic checkpoint with the reference's parameter names
     distributed         image sharding + the scalar rate all-reduce for N GPUs
+    scores              GPU patch-score generation (the reference's generate_scores_file.py)
 """
 from .config import PathConfig, vit_base, vit_large
 from .synthetic import make_state_dict

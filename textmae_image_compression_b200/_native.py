@@ -44,6 +44,10 @@ class TmaeHostOutputs(C.Structure):
     _fields_ = [(name, C.c_void_p) for name in HOST_OUTPUT_FIELDS]
 
 
+class TmaeScoreOutputs(C.Structure):
+    _fields_ = [(name, C.c_void_p) for name in ("scores", "s_map", "t_map", "segmented")]
+
+
 class TmaeProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("ms", C.c_float), ("flops", C.c_double),
                 ("bytes", C.c_double), ("mma_flops", C.c_double)]
@@ -75,6 +79,8 @@ SIGNATURES = {
     "tmae_mask_select": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "tmae_gaussian_rate": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "tmae_bottleneck_rate": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
+    "tmae_scores_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tmae_generate_scores": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(TmaeScoreOutputs), _P, C.c_size_t, _P]),
     "tmae_gemm_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_attention_bf16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

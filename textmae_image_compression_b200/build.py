@@ -22,6 +22,7 @@ SOURCES = {
     "attention.cu": [],
     "elementwise.cu": [],
     "mask.cu": ["-fmad=false"],
+    "scores.cu": ["-fmad=false"],
     "tmae_api.cu": [],
 }
 

@@ -81,4 +81,21 @@ cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaSt
 cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st);
 cudaError_t launch_f32_to_bf16_cols(const float* a, __nv_bfloat16* o, long long rows, int cols, int ld, long long lo_off, cudaStream_t st);
 
+// ---- patch-score generation (scores.cu; generate_scores_file.py:19-31, utils/map.py, utils/distribution.py) ----
+constexpr int kScoreMaxLevels = 16;
+struct ScoreGeom {
+    int H, W, S;                           // grey image, side of the resized maps (224)
+    int levels;                            // quadtree levels whose nodes may split (min(h, w) > 5); deeper nodes are leaves
+    int flag_total;                        // split-decision flags per image = sum of 4^d over those levels
+    int large_levels, large_nodes, large_cta_total, small_nodes;
+    int h[kScoreMaxLevels + 1], w[kScoreMaxLevels + 1];       // node size per level: int(h / 2) of the level above
+    int flag_off[kScoreMaxLevels + 1];
+    int chunks[kScoreMaxLevels], large_node_off[kScoreMaxLevels], large_ctas[kScoreMaxLevels];
+    double scale_x_crop, scale_y_crop, scale_x_full, scale_y_full;   // cv2.resize source/destination ratios
+};
+bool score_geometry(int H, int W, int S, ScoreGeom* out);
+size_t score_workspace_bytes(const ScoreGeom& g, int n);
+cudaError_t launch_generate_scores(const uint8_t* gray, int n, const ScoreGeom& g, float* scores, uint8_t* s_map, uint8_t* t_map,
+                                   uint8_t* seg_out, void* workspace, cudaStream_t st);
+
 }  // namespace tmae

@@ -1615,6 +1615,27 @@ int tmae_bottleneck_rate(tmae_handle* h, const float* z, int64_t rows, float* li
     return TMAE_OK;
 }
 
+// ---- patch-score generation (generate_scores_file.py:19-31) ---------------------------------------------
+size_t tmae_scores_workspace_bytes(int n, int height, int width, int out_side) {
+    ScoreGeom g;
+    if (n < 0 || !score_geometry(height, width, out_side, &g)) return 0;
+    return score_workspace_bytes(g, n);
+}
+int tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int out_side, const tmae_score_outputs* out,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    ScoreGeom g;
+    if (n < 0 || !out || (n > 0 && (!gray || !workspace))) return fail(nullptr, TMAE_EINVAL, "invalid argument");
+    if (!score_geometry(height, width, out_side, &g))
+        return fail(nullptr, TMAE_EINVAL, "score generation needs height, width >= 8 and out_side a positive multiple of 16 (got %d x %d -> %d)",
+                    height, width, out_side);
+    if (workspace_bytes < score_workspace_bytes(g, n))
+        return fail(nullptr, TMAE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes, score_workspace_bytes(g, n));
+    cudaError_t e = launch_generate_scores(gray, n, g, out->scores, out->s_map, out->t_map, out->segmented, workspace,
+                                           reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "generate_scores: %s", cudaGetErrorString(e));
+    return TMAE_OK;
+}
+
 // ---- engine self-tests ---------------------------------------------------------------------------------
 static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st, bool pair = false) {
     GemmParams p;
