@@ -193,6 +193,27 @@ TMAE_API size_t tmae_scores_workspace_bytes(int n, int height, int width, int ou
 TMAE_API int  tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int out_side,
                           const tmae_score_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Side-information coder of the reference's eval CLI: utils/huffman.py HuffmanCoding (testing.py:73-76 codes `ids_restore`
+ * with it and adds len(bit string) / pixels to the bpp, testing.py:89).  HOST-only (h_ pointers are host memory, nothing
+ * touches the device): produces the reference's exact '0'/'1' string, tie-breaking included (CPython heapq on nodes compared
+ * by frequency, first-appearance order of the values). */
+typedef struct tmae_huffman tmae_huffman;
+TMAE_API int  tmae_huffman_create(tmae_huffman** out);
+TMAE_API void tmae_huffman_destroy(tmae_huffman* h);
+TMAE_API const char* tmae_huffman_last_error(const tmae_huffman* h);
+/* HuffmanCoding.compress (utils/huffman.py:141-157): build the code of h_values [n] and encode them; *n_bits = len(encoded_text). */
+TMAE_API int  tmae_huffman_compress(tmae_huffman* h, const int64_t* h_values, int64_t n, int64_t* n_bits);
+/* The encoded text of the last compress: as_chars = 1 -> one '0' / '1' byte per bit (the reference's Python str, capacity >=
+ * n_bits); 0 -> packed, MSB first (capacity >= (n_bits + 7) / 8). */
+TMAE_API int  tmae_huffman_bits(const tmae_huffman* h, uint8_t* h_out, int64_t capacity, int as_chars);
+/* codes[value] as a NUL-terminated '0'/'1' string. */
+TMAE_API int  tmae_huffman_code(const tmae_huffman* h, int64_t value, char* out, int capacity);
+/* Distinct values in the key order of the reference's `codes` dict (pre-order walk of the tree); returns their count. */
+TMAE_API int  tmae_huffman_num_symbols(const tmae_huffman* h, int64_t* h_values, int64_t capacity);
+/* HuffmanCoding.decode (:120-139) with the code of the last compress: *n_values = values decoded. */
+TMAE_API int  tmae_huffman_decompress(const tmae_huffman* h, const uint8_t* h_bits, int64_t n_bits, int as_chars,
+                             int64_t* h_values, int64_t capacity, int64_t* n_values);
+
 /* Tensor-core GEMM/conv engine self-test hook (tests): C[M,N] = A[M,K] * B[N,K]^T (+bias) with bf16 inputs,
  * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */
 TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K,

@@ -6,6 +6,7 @@ Public surface:
     make_state_dict     seeded synthetic checkpoint with the reference's parameter names
     distributed         image sharding + the scalar rate all-reduce for N GPUs
     scores              GPU patch-score generation (the reference's generate_scores_file.py)
+    huffman             HuffmanCoding: the reference's ids_restore side-information coder (utils/huffman.py), host side
 """
 from .config import PathConfig, vit_base, vit_large
 from .synthetic import make_state_dict

@@ -81,6 +81,14 @@ SIGNATURES = {
     "tmae_bottleneck_rate": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P]),
     "tmae_scores_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "tmae_generate_scores": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(TmaeScoreOutputs), _P, C.c_size_t, _P]),
+    "tmae_huffman_create": (C.c_int, [C.POINTER(_P)]),
+    "tmae_huffman_destroy": (None, [_P]),
+    "tmae_huffman_last_error": (C.c_char_p, [_P]),
+    "tmae_huffman_compress": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "tmae_huffman_bits": (C.c_int, [_P, _P, C.c_int64, C.c_int]),
+    "tmae_huffman_code": (C.c_int, [_P, C.c_int64, C.c_char_p, C.c_int]),
+    "tmae_huffman_num_symbols": (C.c_int, [_P, _P, C.c_int64]),
+    "tmae_huffman_decompress": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "tmae_gemm_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_conv3x3_bf16": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "tmae_attention_bf16": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
