@@ -1,9 +1,11 @@
 // Fused softmax attention over the visible tokens of one image and one head (timm 0.4.5 Attention.forward as
-// used by the encoder blocks, MCM.py:313-322, 629-630):  softmax((q k^T) * hd^-0.5) v, head_dim = 64, T <= ~300.
-// One CTA per (image, head); K and V of all T keys stay in shared memory, each warp owns 16-query tiles and runs
-// an online-softmax loop over 16-key chunks; S and P never leave registers.  bf16 tensor-core math
-// (mma.sync m16n8k16, fp32 accumulate): this op is 1.7-3 % of the path's FLOPs, so it uses the legacy
-// warp-level MMA; the GEMM / conv engine (gemm_tc.cu) is where tcgen05 is spent.
+// used by the encoder blocks, MCM.py:313-322, 629-630):  softmax((q k^T) * hd^-0.5) v, head_dim = 64.
+// Three kernels:
+//   attention_tc_kernel   (default, Tp <= 384) tcgen05 / TMEM / TMA: persistent, warp-specialised, see its header below.
+//   attention_kernel      mma.sync m16n8k16 + ldmatrix, one CTA per (image, head), K and V of all keys in shared memory,
+//                         online softmax in registers: the fallback for longer sequences and the A/B partner
+//                         (TMAE_NO_TC_ATTN=1).
+//   attention_f32_kernel  fp32 CUDA-core attention of the precise (conformance) modes.
 #include <math.h>
 
 #include <cuda.h>
@@ -266,168 +268,357 @@ inline size_t attn_f32_smem(int T) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// tcgen05 attention (bf16 mode, T <= 192): one CTA per (image, head).  Q, K, V tiles arrive by TMA straight out of the
-// qkv matrix; S = Q K^T and O = P V are tcgen05.mma with the accumulators in tensor memory; softmax runs thread-per-row on
-// the S row read back with tcgen05.ld (no shuffles), P goes to shared memory as the K-major 128B-swizzled A operand of the
-// second MMA, V is transposed in shared memory into the K-major B operand ([64 dims][keys]) while the first MMA runs.
-//   smem: Q [128 x 64] | K [Tp x 64] (both as TMA wrote them: SWIZZLE_128B, K-major) | V raw [Tp x 64] (no swizzle) |
-//         V^T [64 x keys] in 64-key atoms | P [128 x keys] in 64-key atoms.   TMEM: S at column 0 (Tp <= 192), O at 192.
+// tcgen05 attention (bf16 mode, Tp <= 384): a PERSISTENT, warp-specialised kernel - one CTA per SM walks a list of
+// (image, head, query tile) items; the pieces of consecutive items overlap:
+//   warp 0    TMA producer: Q [<=128 x 64], K [Tp x 64], V [Tp x 64] boxes of the qkv matrix into an nst-stage ring
+//             (all three SWIZZLE_128B; V is consumed as the MN-major B operand exactly as TMA wrote it - no transpose)
+//   warp 1    MMA issuer: S = Q K^T (M 128, N Tp, K 64) into TMEM buffer b, O = P V (M 128, N 64, K Tp) into O buffer b;
+//             S of item i+1 is issued BEFORE waiting for the softmax of item i (two S / O / P buffers when Tp <= 192)
+//   warps 2-5 / 6-9   two softmax groups (128 threads = 128 TMEM lanes = 128 query rows) taking alternate items: read the S
+//             row with tcgen05.ld, max / exp2 / sum in registers (no shuffles), write P as the K-major 128B-swizzled A operand
+//             of the second MMA, then read O, scale by 1 / sum and store the bf16 row.
+// Barriers per item: full/empty (stage), s_ready, p_ready (128 arrivals), o_ready, o_free (128 arrivals).  WAR hazards on
+// S (next S MMA vs. this softmax's loads) and P (next softmax's stores vs. this PV MMA) are covered by program order of
+// the issuing warp / the owning group, see the loop comments.
 // Rows >= T of a tile belong to the next image (or are zero-filled at the end of the tensor): as keys they are masked in the
-// softmax, as queries they are computed and not stored.
+// softmax, as queries they are computed on whatever the tile holds and never stored.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kAttnTcThreads = 128;
-constexpr int kAttnTcMaxTp = 192;
-constexpr uint32_t kAttnOCol = 192;
+constexpr int kAttnTcThreads = 320;
+constexpr int kAttnTcMaxTp = 384;
+constexpr int kAttnTcMaxStages = 3;
 
-__global__ void __launch_bounds__(kAttnTcThreads)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
-                    const __grid_constant__ CUtensorMap map_v, __nv_bfloat16* __restrict__ out, int T, int Tp, int H, int C,
-                    float scale_log2e) {
+struct AttnTcParams {
+    int T, Tp, H, C;
+    int n_items, q_tiles;
+    int nbuf;                 // 2: double-buffered S / O / P and both softmax groups; 1: single (Tp > 192)
+    int nst;                  // Q/K/V stages
+    int qrows, krows, kloads; // TMA boxes: Q rows, K/V rows per load, loads per K/V tile
+    int atoms;                // 64-key atoms of the P tile
+    uint32_t qreg, kreg;      // bytes reserved per Q / K / V tile (multiples of 1024)
+    uint32_t s_stride, o_col0, tmem_cols;
+    float scale_log2e;
+    long long* dbg;           // bring-up: [item][16] clock64 stamps of CTA 0 (TMAE_ATTN_TIMING=1), else nullptr
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// MN-major (transposed) B operand, 128-byte swizzle: rows of the K dimension are 128 B apart, 8-row groups 1024 B apart
+// (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units; one 64-element MN block, so LBO is unused).
+__device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <int NCH>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
+__global__ void __launch_bounds__(kAttnTcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                    __nv_bfloat16* __restrict__ out, const AttnTcParams p) {
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_tc[];
-    const int atoms = (Tp + 63) >> 6;
-    const uint32_t kbytes = (uint32_t)Tp * 128u;
-    const uint32_t kreg = (kbytes + 1023u) & ~1023u;
-    uint8_t* sQ = smem_tc;                               // 16 KB
-    uint8_t* sK = sQ + 16384;
-    uint8_t* sVr = sK + kreg;
-    uint8_t* sVt = sVr + kreg;                           // atoms x 8 KB
-    uint8_t* sP = sVt + (size_t)atoms * 8192;            // atoms x 16 KB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (size_t)atoms * 16384);     // load, s, o
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-    const int n = blockIdx.x / H, h = blockIdx.x - n * H;
+    const uint32_t stage_bytes = p.qreg + 2u * p.kreg;
+    const uint32_t smem0 = smem_u32(smem_tc);
+    const uint32_t p_base = smem0 + (uint32_t)p.nst * stage_bytes;
+    const uint32_t p_bytes = (uint32_t)p.atoms * 16384u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_tc + (size_t)p.nst * stage_bytes + (size_t)p.nbuf * p_bytes);
+    // full[3] empty[3] s_ready[2] p_ready[2] o_ready[2] o_free[2]
+    const uint32_t bar0 = smem_u32(bars);
+    auto bar_full = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+    auto bar_empty = [&](int s) { return bar0 + 8u * (uint32_t)(3 + s); };
+    auto bar_sready = [&](int b) { return bar0 + 8u * (uint32_t)(6 + b); };
+    auto bar_pready = [&](int b) { return bar0 + 8u * (uint32_t)(8 + b); };
+    auto bar_oready = [&](int b) { return bar0 + 8u * (uint32_t)(10 + b); };
+    auto bar_ofree = [&](int b) { return bar0 + 8u * (uint32_t)(12 + b); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+        for (int s = 0; s < 3; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[3 + s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars[6 + b], 1); mbar_init(&bars[8 + b], 128); mbar_init(&bars[10 + b], 1); mbar_init(&bars[12 + b], 128); }
         fence_barrier_init();
-        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+        tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv);
     }
-    if (warp == 0) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(tmem_slot, p.tmem_cols); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     pdl_wait();
 
-    const uint32_t q_a = smem_u32(sQ), k_a = smem_u32(sK), vr_a = smem_u32(sVr), vt_a = smem_u32(sVt), p_a = smem_u32(sP);
-    const uint32_t bar_load = smem_u32(&bars[0]), bar_s = smem_u32(&bars[1]), bar_o = smem_u32(&bars[2]);
-    const int row0 = n * T;
-    const int q_tiles = (T + 127) >> 7;
-    for (int qt = 0; qt < q_tiles; ++qt) {
-        const uint32_t ph = (uint32_t)qt & 1u;
-        const int q0 = qt * 128;
-        if (tid == 0) {
-            mbar_arrive_expect_tx_a(bar_load, 16384u + (qt == 0 ? 2u * kbytes : 0u));
-            tma_load_2d_a(q_a, &map_q, bar_load, h * HD, row0 + q0);
-            if (qt == 0) {
-                tma_load_2d_a(k_a, &map_k, bar_load, C + h * HD, row0);
-                tma_load_2d_a(vr_a, &map_v, bar_load, 2 * C + h * HD, row0);
-            }
-        }
-        mbar_wait_a(bar_load, ph);
-        if (tid == 0) {                                   // S = Q K^T: M = 128, N = Tp, K = 64 in four k-steps
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16_f32(128, Tp);
-            const uint64_t dq = umma_smem_desc_sw128(q_a), dk = umma_smem_desc_sw128(k_a);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
-            umma_commit_a(bar_s);
-        }
-        if (qt == 0) {
-            // V^T while the MMA runs: thread -> (dim d, every second 8-key chunk); 8 strided 2-byte reads, one 16-byte store
-            const int d = tid & 63;
-            for (int j0 = (tid >> 6) * 8; j0 < Tp; j0 += 16) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sVr + (size_t)(j0 + 2 * i) * 128 + d * 2);
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sVr + (size_t)(j0 + 2 * i + 1) * 128 + d * 2);
-                    pk[i] = (uint32_t)lo | ((uint32_t)hi << 16);
-                }
-                const uint32_t dst = vt_a + (uint32_t)(j0 >> 6) * 8192u + (uint32_t)d * 128u + ((((uint32_t)(j0 & 63) >> 3) ^ (uint32_t)(d & 7)) << 4);
-                sts128(dst, pk[0], pk[1], pk[2], pk[3]);
-            }
-        }
-        // ---- softmax of this thread's query row (TMEM lane = row) ----
-        mbar_wait_a(bar_s, ph);
-        tc_fence_after();
-        const int row = warp * 32 + lane;
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < Tp; c0 += 16) {
-            uint32_t sv[16];
-            tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, sv);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (c0 + i < T) mx = fmaxf(mx, __uint_as_float(sv[i]));
-        }
-        const float mxs = mx * scale_log2e;
-        float sum = 0.f;
-        const uint32_t prow = p_a + (uint32_t)row * 128u;
-        for (int c0 = 0; c0 < Tp; c0 += 16) {
-            uint32_t sv[16];
-            tmem_ld_32x32b_x16(lane_base + (uint32_t)c0, sv);
-            tmem_ld_wait();
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float p0 = (c0 + 2 * i < T) ? exp2f(fmaf(__uint_as_float(sv[2 * i]), scale_log2e, -mxs)) : 0.f;
-                const float p1 = (c0 + 2 * i + 1 < T) ? exp2f(fmaf(__uint_as_float(sv[2 * i + 1]), scale_log2e, -mxs)) : 0.f;
-                sum += p0 + p1;
-                pk[i] = pack_bf16x2(p0, p1);
-            }
-            const uint32_t base = prow + (uint32_t)(c0 >> 6) * 16384u;
-            const uint32_t ch = (uint32_t)(c0 & 63) >> 3;
-            sts128(base + (((ch) ^ (uint32_t)(row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
-            sts128(base + (((ch + 1u) ^ (uint32_t)(row & 7)) << 4), pk[4], pk[5], pk[6], pk[7]);
-        }
-        fence_proxy_async_smem();                         // P (and V^T) written through the generic proxy -> visible to the MMA
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {                                   // O = P V: M = 128, N = 64, K = Tp in Tp / 16 k-steps
-            tc_fence_after();
-            const uint32_t idesc = umma_idesc_bf16_f32(128, HD);
-            const uint64_t dp = umma_smem_desc_sw128(p_a), dv = umma_smem_desc_sw128(vt_a);
-            const int ksteps = Tp >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
-                const uint64_t a_desc = dp + (uint64_t)((uint32_t)(ks >> 2) * (16384u >> 4)) + (uint64_t)(2 * (ks & 3));
-                const uint64_t b_desc = dv + (uint64_t)((uint32_t)(ks >> 2) * (8192u >> 4)) + (uint64_t)(2 * (ks & 3));
-                umma_bf16(tmem + kAttnOCol, a_desc, b_desc, idesc, ks != 0 ? 1u : 0u);
-            }
-            umma_commit_a(bar_o);
-        }
-        mbar_wait_a(bar_o, ph);
-        tc_fence_after();
-        const float inv = 1.f / sum;
-        const bool store = q0 + row < T;
-        __nv_bfloat16* dst = out + ((size_t)(row0 + q0 + row)) * C + (size_t)h * HD;
-#pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 32) {
-            uint32_t ov[32];
-            tmem_ld_32x32b_x32(lane_base + kAttnOCol + (uint32_t)c0, ov);
-            tmem_ld_wait();
-            if (store) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint4 pk;
-                    pk.x = pack_bf16x2(__uint_as_float(ov[i]) * inv, __uint_as_float(ov[i + 1]) * inv);
-                    pk.y = pack_bf16x2(__uint_as_float(ov[i + 2]) * inv, __uint_as_float(ov[i + 3]) * inv);
-                    pk.z = pack_bf16x2(__uint_as_float(ov[i + 4]) * inv, __uint_as_float(ov[i + 5]) * inv);
-                    pk.w = pack_bf16x2(__uint_as_float(ov[i + 6]) * inv, __uint_as_float(ov[i + 7]) * inv);
-                    *reinterpret_cast<uint4*>(dst + c0 + i) = pk;
+    const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t kbytes = (uint32_t)p.Tp * 128u;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int k = 0; k < n_my; ++k) {
+                const int item = (int)blockIdx.x + k * (int)gridDim.x;
+                const int qt = item % p.q_tiles, nh = item / p.q_tiles;
+                const int h = nh % p.H, n = nh / p.H;
+                const int st = k % p.nst;
+                mbar_wait_a(bar_empty(st), (((uint32_t)(k / p.nst)) & 1u) ^ 1u);
+                const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
+                mbar_arrive_expect_tx_a(bar_full(st), (uint32_t)p.qrows * 128u + 2u * kbytes);
+                const int row0 = n * p.T;
+                tma_load_2d_a(base, &map_q, bar_full(st), h * HD, row0 + qt * 128);
+                for (int l = 0; l < p.kloads; ++l) {
+                    tma_load_2d_a(base + p.qreg + (uint32_t)(l * p.krows) * 128u, &map_kv, bar_full(st), p.C + h * HD, row0 + l * p.krows);
+                    tma_load_2d_a(base + p.qreg + p.kreg + (uint32_t)(l * p.krows) * 128u, &map_kv, bar_full(st), 2 * p.C + h * HD,
+                                  row0 + l * p.krows);
                 }
             }
         }
-        tc_fence_before();
-        __syncthreads();                                  // S / O / P / Q are reused by the next query tile
-        tc_fence_after();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_pv = umma_idesc_bf16_f32(128, HD) | (1u << 16);            // B (= V) is MN-major
+            auto issue_s = [&](int k) {
+                const int st = k % p.nst, b = k % p.nbuf;
+                mbar_wait_a(bar_full(st), ((uint32_t)(k / p.nst)) & 1u);
+                tc_fence_after();
+                if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 0] = clock64();
+                const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
+                const uint64_t dq = umma_smem_desc_sw128(base);
+                for (int n0 = 0; n0 < p.Tp; n0 += 256) {
+                    const int nn = min(256, p.Tp - n0);
+                    const uint32_t idesc = umma_idesc_bf16_f32(128, nn);
+                    const uint64_t dk = umma_smem_desc_sw128(base + p.qreg + (uint32_t)n0 * 128u);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16(tmem + (uint32_t)b * p.s_stride + (uint32_t)n0, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc, kk != 0 ? 1u : 0u);
+                }
+                umma_commit_a(bar_sready(b));
+                if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 1] = clock64();
+            };
+            if (n_my > 0 && p.nbuf == 2) issue_s(0);
+            for (int k = 0; k < n_my; ++k) {
+                const int st = k % p.nst, b = k % p.nbuf;
+                const uint32_t use = (uint32_t)(k / p.nbuf);
+                // S buffer of the item issued here was last read by the softmax of item k-1 (dual) / k-1 (single): its
+                // p_ready was waited for below in the previous iteration, so the loads of that S row are complete.
+                if (p.nbuf == 2) { if (k + 1 < n_my) issue_s(k + 1); }
+                else issue_s(k);
+                mbar_wait_a(bar_pready(b), use & 1u);                 // P of item k is in shared memory
+                if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 2] = clock64();
+                mbar_wait_a(bar_ofree(b), (use & 1u) ^ 1u);           // O buffer b drained by the epilogue of item k - nbuf
+                tc_fence_after();
+                const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
+                const uint64_t dp = umma_smem_desc_sw128(p_base + (uint32_t)b * p_bytes);
+                const uint64_t dv = umma_smem_desc_mn_sw128(base + p.qreg + p.kreg);
+                const int ksteps = p.Tp >> 4;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint64_t a_desc = dp + (uint64_t)((uint32_t)(ks >> 2) * (16384u >> 4)) + (uint64_t)(2 * (ks & 3));
+                    const uint64_t b_desc = dv + (uint64_t)((uint32_t)ks * (2048u >> 4));
+                    umma_bf16(tmem + p.o_col0 + (uint32_t)b * 64u, a_desc, b_desc, idesc_pv, ks != 0 ? 1u : 0u);
+                }
+                umma_commit_a(bar_oready(b));
+                umma_commit_a(bar_empty(st));                         // Q / K / V of this stage are no longer read
+                if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 3] = clock64();
+            }
+        }
+    } else {
+        const int g = (warp - 2) >> 2;                                // softmax group
+        const int quad = warp & 3;                                    // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+        if (g < p.nbuf) {
+            for (int k = g; k < n_my; k += p.nbuf) {
+                const int item = (int)blockIdx.x + k * (int)gridDim.x;
+                const int qt = item % p.q_tiles, nh = item / p.q_tiles;
+                const int h = nh % p.H, n = nh / p.H;
+                const int b = k % p.nbuf;
+                const uint32_t use = (uint32_t)(k / p.nbuf);
+                const int q0 = qt * 128;
+                const bool valid = q0 + row < p.T;
+                const uint32_t s_addr = tmem + lane_off + (uint32_t)b * p.s_stride;
+                const bool stamp = p.dbg && blockIdx.x == 0 && row == 0;
+                if (stamp) p.dbg[k * 16 + 4] = clock64();
+                mbar_wait_a(bar_sready(b), use & 1u);
+                tc_fence_after();
+                if (stamp) p.dbg[k * 16 + 5] = clock64();
+                const uint32_t prow = p_base + (uint32_t)b * p_bytes + (uint32_t)row * 128u;
+                const uint32_t rsw = (uint32_t)(row & 7);
+                float mx = -INFINITY, sum = 0.f;
+                // 32 S values at key columns [c0, c0 + 32): running maximum / exp2, row sum, bf16 P into the swizzled A tile.
+                // Columns are masked only in the 8-column group that straddles T; groups past T are written as zeros.
+                auto chunk_max = [&](const uint32_t (&sv)[32], int c0) {
+                    if (c0 + 32 <= p.T) {
+                        float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
+#pragma unroll
+                        for (int i = 4; i < 32; i += 4) {
+                            m0 = fmaxf(m0, __uint_as_float(sv[i])); m1 = fmaxf(m1, __uint_as_float(sv[i + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(sv[i + 2])); m3 = fmaxf(m3, __uint_as_float(sv[i + 3]));
+                        }
+                        mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (c0 + q * 8 < p.T) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) if (c0 + q * 8 + i < p.T) mx = fmaxf(mx, __uint_as_float(sv[q * 8 + i]));
+                            }
+                        }
+                    }
+                };
+                auto chunk_exp = [&](const uint32_t (&sv)[32], int c0, float mxs) {
+                    const uint32_t abase = prow + (uint32_t)(c0 >> 6) * 16384u;
+                    const uint32_t ch = (uint32_t)(c0 & 63) >> 3;
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t pk[4] = {0u, 0u, 0u, 0u};
+                        const int cq = c0 + q * 8;
+                        if (cq + 8 <= p.T) {
+                            float e[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2e, -mxs));
+                            s0 += e[0] + e[4]; s1 += e[1] + e[5]; s2 += e[2] + e[6]; s3 += e[3] + e[7];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+                        } else if (cq < p.T) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = cq + 2 * i;
+                                const float p0 = (c < p.T) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i]), p.scale_log2e, -mxs)) : 0.f;
+                                const float p1 = (c + 1 < p.T) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i + 1]), p.scale_log2e, -mxs)) : 0.f;
+                                s0 += p0 + p1;
+                                pk[i] = pack_bf16x2(p0, p1);
+                            }
+                        }
+                        if (cq < p.Tp) sts128(abase + (((ch + (uint32_t)q) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                    sum += (s0 + s1) + (s2 + s3);
+                };
+                if constexpr (NCH > 0) {
+                    // the whole S row in registers: one round of TMEM loads, one wait
+                    uint32_t sv[NCH][32];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(s_addr + (uint32_t)(32 * c), sv[c]);
+                    tmem_ld_wait();
+                    if (stamp) p.dbg[k * 16 + 6] = clock64();
+                    if (valid) {
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_max(sv[c], 32 * c);
+                        const float mxs = mx * p.scale_log2e;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_exp(sv[c], 32 * c, mxs);
+                    }
+                } else {
+                    // long rows: two passes over tensor memory, the load of the next 32 columns in flight while this one is used
+                    uint32_t sa[32], sb[32];
+                    float mxs = 0.f;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        tmem_ld_32x32b_x32(s_addr, sa);
+                        tmem_ld_wait();
+                        for (int c0 = 0; c0 < p.Tp; c0 += 64) {
+                            const bool has_b = c0 + 32 < p.Tp, has_a2 = c0 + 64 < p.Tp;
+                            if (has_b) tmem_ld_32x32b_x32(s_addr + (uint32_t)(c0 + 32), sb);
+                            if (valid) { if (pass == 0) chunk_max(sa, c0); else chunk_exp(sa, c0, mxs); }
+                            tmem_ld_wait();
+                            if (has_b) {
+                                if (has_a2) tmem_ld_32x32b_x32(s_addr + (uint32_t)(c0 + 64), sa);
+                                if (valid) { if (pass == 0) chunk_max(sb, c0 + 32); else chunk_exp(sb, c0 + 32, mxs); }
+                                tmem_ld_wait();
+                            }
+                        }
+                        mxs = mx * p.scale_log2e;
+                    }
+                }
+                if (stamp) p.dbg[k * 16 + 7] = clock64();
+                fence_proxy_async_smem();                             // P written through the generic proxy -> visible to the MMA
+                tc_fence_before();                                    // this thread's S loads are ordered before the next S MMA
+                mbar_arrive(&bars[8 + b]);
+                if (stamp) p.dbg[k * 16 + 8] = clock64();
+                // ---- epilogue: O row / sum -> bf16 ----
+                mbar_wait_a(bar_oready(b), use & 1u);
+                tc_fence_after();
+                if (stamp) p.dbg[k * 16 + 9] = clock64();
+                uint32_t o0[32], o1[32];
+                tmem_ld_32x32b_x32(tmem + lane_off + p.o_col0 + (uint32_t)b * 64u, o0);
+                tmem_ld_32x32b_x32(tmem + lane_off + p.o_col0 + (uint32_t)b * 64u + 32u, o1);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&bars[12 + b]);                           // O buffer b may be overwritten
+                if (stamp) p.dbg[k * 16 + 10] = clock64();
+                // O row * (1 / sum) -> bf16 into this group's (now idle) P tile, 128B-swizzled, then each warp copies its 32 rows
+                // out with full 128-byte lines: lane -> (row l / 8 + 4 i, 16-byte chunk l % 8).
+                const uint32_t stg = p_base + (uint32_t)b * p_bytes;
+                if (valid) {
+                    const float inv = 1.f / sum;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        sts128(stg + (uint32_t)row * 128u + ((((uint32_t)c) ^ rsw) << 4),
+                               pack_bf16x2(__uint_as_float(o0[8 * c]) * inv, __uint_as_float(o0[8 * c + 1]) * inv),
+                               pack_bf16x2(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv),
+                               pack_bf16x2(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv),
+                               pack_bf16x2(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv));
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        sts128(stg + (uint32_t)row * 128u + ((((uint32_t)(c + 4)) ^ rsw) << 4),
+                               pack_bf16x2(__uint_as_float(o1[8 * c]) * inv, __uint_as_float(o1[8 * c + 1]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv),
+                               pack_bf16x2(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv));
+                }
+                __syncwarp();
+                {
+                    const int rows_left = p.T - q0 - quad * 32;                    // valid rows of this warp's 32
+                    __nv_bfloat16* wdst = out + ((size_t)(n * p.T + q0 + quad * 32)) * p.C + (size_t)h * HD;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3);
+                        if (r < rows_left) {
+                            const uint32_t rr = (uint32_t)(quad * 32 + r);
+                            const float4 v = lds128(stg + rr * 128u + ((((uint32_t)lane & 7u) ^ (rr & 7u)) << 4));
+                            *reinterpret_cast<float4*>(wdst + (size_t)r * p.C + (lane & 7) * 8) = v;
+                        }
+                    }
+                }
+                __syncwarp();                                         // the tile is rewritten by this group's next softmax
+                if (stamp) p.dbg[k * 16 + 11] = clock64();
+            }
+        }
     }
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem, p.tmem_cols);
 }
-inline size_t attn_tc_smem(int Tp) {
-    const size_t kreg = ((size_t)Tp * 128 + 1023) & ~(size_t)1023;
-    const size_t atoms = (Tp + 63) / 64;
-    return 16384 + 2 * kreg + atoms * (8192 + 16384) + 64;
+
+// shared-memory / tensor-memory plan of the tcgen05 kernel for T tokens; returns false when it does not fit
+inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* out, size_t* smem) {
+    AttnTcParams p = {};
+    const int Tp = attn_tp(T);
+    if (Tp > kAttnTcMaxTp) return false;
+    p.T = T; p.Tp = Tp; p.H = H; p.C = C;
+    p.q_tiles = (T + 127) / 128;
+    p.n_items = N * H * p.q_tiles;
+    p.qrows = Tp < 128 ? Tp : 128;
+    p.kloads = Tp <= 256 ? 1 : 2;
+    p.krows = Tp / p.kloads;
+    p.atoms = (Tp + 63) / 64;
+    p.qreg = ((uint32_t)p.qrows * 128u + 1023u) & ~1023u;
+    p.kreg = ((uint32_t)Tp * 128u + 1023u) & ~1023u;
+    const uint32_t sp = ((uint32_t)Tp + 31u) & ~31u;
+    const size_t limit = 227 * 1024 - 256;
+    const size_t stage = p.qreg + 2 * (size_t)p.kreg, pb = (size_t)p.atoms * 16384;
+    p.nbuf = (2 * sp + 128 <= 512 && 2 * stage + 2 * pb <= limit) ? 2 : 1;
+    if (stage + (size_t)p.nbuf * pb > limit) return false;
+    int nst = (int)((limit - (size_t)p.nbuf * pb) / stage);
+    p.nst = nst > kAttnTcMaxStages ? kAttnTcMaxStages : nst;
+    p.s_stride = sp;
+    p.o_col0 = (uint32_t)p.nbuf * sp;
+    const uint32_t need = p.o_col0 + (uint32_t)p.nbuf * 64u;
+    p.tmem_cols = need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    if (need > 512) return false;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    *out = p;
+    *smem = (size_t)p.nst * stage + (size_t)p.nbuf * pb + 256;
+    return true;
 }
 
 }  // namespace
@@ -439,7 +630,11 @@ cudaError_t attention_configure(int T) {
     static cudaError_t once = [] {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }();
@@ -455,27 +650,41 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
                     scale * 1.4426950408889634f);
 }
 
-// tcgen05 path: supported for head_dim 64 and T <= 192 (S row + O fit 256 TMEM columns); the tensor maps (Q: box 64 x 128,
-// K: 64 x Tp, both SWIZZLE_128B; V: 64 x Tp unswizzled) are built by the plan.
-// MEASURED (B200, batch 64): correct (tests/test_gpu_engine.py::test_attention_matches_torch) but SLOWER than the mma.sync
-// kernel - 25 us vs 18 us per launch at T = 65, 106 us vs 43 us at T = 145.  One (image, head) is a strictly serial chain
-// (TMA -> S MMA -> softmax -> P to smem -> PV MMA -> store, every hop a barrier round trip) and its 84-128 KB of shared
-// memory + 256 TMEM columns allow 1-2 CTAs per SM, against 6 CTAs / 30 warps of the mma.sync kernel: at these sizes
-// (0.8-3 % of the path's flops) occupancy beats the faster pipe.  It is therefore opt-in (TMAE_TC_ATTN=1); making it win
-// needs a warp-specialised kernel that pipelines several heads per CTA.
-bool attention_tc_supported(int T) { return attn_tp(T) <= kAttnTcMaxTp; }
+// tcgen05 path: head_dim 64, Tp <= 384 (S row + O fit the 512 TMEM columns and the tiles fit shared memory); the tensor maps
+// (Q: box 64 x min(128, Tp), K / V: box 64 x Tp or Tp / 2, all SWIZZLE_128B) are built by the plan with attention_tc_boxes().
+bool attention_tc_supported(int T) {
+    AttnTcParams p; size_t smem;
+    return attn_tc_plan(T, 1, HD, 1, 0.125f, &p, &smem);
+}
 bool attention_tc_eligible(int T) {
-    static const bool on = getenv("TMAE_TC_ATTN") != nullptr;
-    return on && attention_tc_supported(T);
+    static const bool off = getenv("TMAE_NO_TC_ATTN") != nullptr;
+    return !off && attention_tc_supported(T);
 }
 int attention_tc_tp(int T) { return attn_tp(T); }
-cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_k, const CUtensorMap* map_v, __nv_bfloat16* out,
-                                int N, int T, int H, int C, float scale, cudaStream_t st) {
+void attention_tc_boxes(int T, int* q_rows, int* kv_rows) {
+    AttnTcParams p = {}; size_t smem = 0;
+    attn_tc_plan(T, 1, HD, 1, 0.125f, &p, &smem);
+    *q_rows = p.qrows; *kv_rows = p.krows;
+}
+cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int N, int T, int H, int C,
+                                float scale, cudaStream_t st, long long* dbg) {
     if (C != H * HD) return cudaErrorInvalidValue;
-    const int Tp = attn_tp(T);
-    TMAE_CARVEOUT_ONCE(attention_tc_kernel);
-    return launch_k(attention_tc_kernel, dim3(N * H), dim3(kAttnTcThreads), attn_tc_smem(Tp), st, true, *map_q, *map_k, *map_v, out, T,
-                    Tp, H, C, scale * 1.4426950408889634f);
+    AttnTcParams p; size_t smem;
+    if (!attn_tc_plan(T, H, C, N, scale, &p, &smem)) return cudaErrorInvalidValue;
+    p.dbg = dbg;
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    TMAE_CARVEOUT_ONCE(attention_tc_kernel<3>);
+    TMAE_CARVEOUT_ONCE(attention_tc_kernel<4>);
+    TMAE_CARVEOUT_ONCE(attention_tc_kernel<0>);
+    const int grid = p.n_items < sms ? p.n_items : sms;
+    if (p.Tp <= 96) return launch_k(attention_tc_kernel<3>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    if (p.Tp <= 128) return launch_k(attention_tc_kernel<4>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    return launch_k(attention_tc_kernel<0>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
 }
 
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,

@@ -36,11 +36,12 @@ cudaError_t attention_configure(int T);
 cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N, int T, int H, int C, float scale,
                              cudaStream_t st);
 // tcgen05 / TMEM attention (T <= 192): Q / K / V by TMA out of the qkv matrix, S and O in tensor memory
-bool attention_tc_supported(int T);   // kernel limits
-bool attention_tc_eligible(int T);    // policy: opt-in (TMAE_TC_ATTN=1), measured slower than the mma.sync kernel at T = 65 / 145
+bool attention_tc_supported(int T);   // kernel limits (Tp <= 384: shared memory and the 512 TMEM columns)
+bool attention_tc_eligible(int T);    // policy: the tcgen05 kernel whenever it is supported (TMAE_NO_TC_ATTN=1 -> mma.sync kernel)
 int attention_tc_tp(int T);
-cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_k, const CUtensorMap* map_v, __nv_bfloat16* out,
-                                int N, int T, int H, int C, float scale, cudaStream_t st);
+void attention_tc_boxes(int T, int* q_rows, int* kv_rows);   // TMA box rows of the Q map and of the K / V map
+cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int N, int T, int H, int C,
+                                float scale, cudaStream_t st, long long* dbg = nullptr);
 // precise mode: fp32 softmax attention on CUDA cores over split-bf16 (hi + lo plane) q, k, v; writes both planes
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,
                                  int T, int H, int C, float scale, cudaStream_t st);

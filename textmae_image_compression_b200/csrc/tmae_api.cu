@@ -779,22 +779,21 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     return TMAE_OK;
 }
 
-// Tensor maps of the tcgen05 attention kernel: Q / K / V tiles of one (image, head) are 64-column boxes of qkv [rows, 3C]
-int make_attention_maps(tmae_handle* h, const __nv_bfloat16* qkv, long long rows, int C, int T, CUtensorMap* mq, CUtensorMap* mk, CUtensorMap* mv) {
-    const int Tp = attention_tc_tp(T);
+// Tensor maps of the tcgen05 attention kernel: Q and K / V tiles of one (image, head) are 64-column boxes of qkv [rows, 3C]
+int make_attention_maps(tmae_handle* h, const __nv_bfloat16* qkv, long long rows, int C, int T, CUtensorMap* mq, CUtensorMap* mkv) {
+    int q_rows = 0, kv_rows = 0;
+    attention_tc_boxes(T, &q_rows, &kv_rows);
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
     cuuint32_t estr[2] = {1, 1};
-    cuuint32_t box_q[2] = {64, 128}, box_k[2] = {64, (cuuint32_t)Tp};
+    cuuint32_t box_q[2] = {64, (cuuint32_t)q_rows}, box_k[2] = {64, (cuuint32_t)kv_rows};
     void* base = const_cast<__nv_bfloat16*>(qkv);
     CUresult r1 = h->encode(mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = h->encode(mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r2 = h->encode(mkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r3 = h->encode(mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box_k, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS || r3 != CUDA_SUCCESS)
-        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(attention) failed (%d %d %d)", (int)r1, (int)r2, (int)r3);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+        return fail(h, TMAE_ECUDA, "cuTensorMapEncodeTiled(attention) failed (%d %d)", (int)r1, (int)r2);
     return TMAE_OK;
 }
 
@@ -834,7 +833,7 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
     auto simple = [&](StepKind k, int fam, const char* t) { Step st; st.kind = k; st.family = fam; st.tag = t; pl.steps.push_back(st); };
 
     if (!h->precise_enc && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && attention_tc_eligible(T)) {
-        if ((rc = make_attention_maps(h, w.qkv.p, rt, C, T, &pl.attn_q, &pl.attn_k, &pl.attn_v))) return rc;
+        if ((rc = make_attention_maps(h, w.qkv.p, rt, C, T, &pl.attn_q, &pl.attn_k))) return rc;
         pl.attn_tc = true;
     }
     simple(ST_ZERO_RATE, FAM_MISC, "zero_rate");
@@ -1161,7 +1160,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 if (h->precise_enc)
                     CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else if (pl.attn_tc)
-                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, &pl.attn_v, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else
                     CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 break;
@@ -1826,12 +1825,28 @@ int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int imp
     cudaError_t e = attention_configure(T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
     if (impl == 1) {
-        if (!attention_tc_supported(T)) return fail(nullptr, TMAE_EINVAL, "tcgen05 attention needs T <= 192");
-        CUtensorMap mq, mk, mv;
-        if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, &mq, &mk, &mv))) {
+        if (!attention_tc_supported(T)) return fail(nullptr, TMAE_EINVAL, "tcgen05 attention needs T <= 384");
+        CUtensorMap mq, mk;
+        if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, &mq, &mk))) {
             g_create_error = tmp->err; return rc;
         }
-        e = launch_attention_tc(&mq, &mk, &mv, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st);
+        long long* dbg = nullptr;
+        const bool timing = getenv("TMAE_ATTN_TIMING") != nullptr;      // bring-up aid: per-phase clock64 stamps of CTA 0
+        if (timing) { cudaMalloc(reinterpret_cast<void**>(&dbg), 64 * 16 * 8); cudaMemset(dbg, 0, 64 * 16 * 8); }
+        e = launch_attention_tc(&mq, &mk, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st, dbg);
+        if (timing) {
+            cudaStreamSynchronize(st);
+            std::vector<long long> hd(64 * 16);
+            cudaMemcpy(hd.data(), dbg, hd.size() * 8, cudaMemcpyDeviceToHost);
+            cudaFree(dbg);
+            long long t0 = 0;
+            for (int k = 0; k < 64 && hd[k * 16 + 5]; ++k) {
+                if (k == 0) t0 = hd[0];
+                fprintf(stderr, "[attn item %2d] mma: full %6lld S_issued %6lld p_ready %6lld PV_issued %6lld | wg: enter %6lld s_ready %6lld ld %6lld exp_done %6lld arrived %6lld o_ready %6lld o_ld %6lld stored %6lld\n",
+                        k, hd[k * 16 + 0] - t0, hd[k * 16 + 1] - t0, hd[k * 16 + 2] - t0, hd[k * 16 + 3] - t0, hd[k * 16 + 4] - t0, hd[k * 16 + 5] - t0,
+                        hd[k * 16 + 6] - t0, hd[k * 16 + 7] - t0, hd[k * 16 + 8] - t0, hd[k * 16 + 9] - t0, hd[k * 16 + 10] - t0, hd[k * 16 + 11] - t0);
+            }
+        }
     } else {
         e = launch_attention(reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st);
     }
