@@ -496,37 +496,32 @@ __global__ void permute_bias_shuffle_kernel(const float* __restrict__ b, float* 
     const int q = ro / cq, c = ro - q * cq;
     out[ro] = b[c * 4 + q];
 }
-// Block-diagonal pack of TWO conv layers that read different inputs into ONE GEMM (GemmParams::gc_on): output rows
-// [0, half) = layer A over K segment 0, rows [half, 2 half) = layer B over K segment 1, zeros elsewhere.  Same K layout as
-// prepack_weight_kernel with two segments of `Cin` channels each (tap-major, plane-major inside a tap).
-__global__ void prepack_blockdiag2_kernel(const float* __restrict__ wa, const float* __restrict__ wb, __nv_bfloat16* __restrict__ out,
-                                          int half, int Cin, int taps, int planes) {
-    const int segpad = ((Cin + 63) / 64) * 64;
-    const int kp_tap = 2 * segpad;
-    const long long Kp = (long long)kp_tap * taps * planes;
-    const long long total = (long long)(2 * half) * Kp;
+// Block-diagonal weight of TWO 3x3 conv layers that read different inputs, as ONE layer over the concatenated input
+// (GemmParams::gc_on): out [2 half, 2 Cin, 3, 3] fp32 (+ bias [2 half]); output rows are interleaved in 32-row chunks -
+// chunk b = [layer A rows 16 b .. 16 b + 15 | layer B rows 16 b .. 16 b + 15] - so one 32-column accumulator chunk holds both
+// layers' outputs of the same 16 channels.  Layer A sees input channels [0, Cin), layer B [Cin, 2 Cin); the rest is zero, and
+// a zero product adds exactly 0 to the fp32 accumulator: the fused GEMM is bit-identical to the two separate ones.
+__global__ void build_blockdiag2_kernel(const float* __restrict__ wa, const float* __restrict__ wb, const float* __restrict__ ba,
+                                        const float* __restrict__ bb, float* __restrict__ w_out, float* __restrict__ b_out, int half,
+                                        int Cin, int taps) {
+    const long long per_row = (long long)2 * Cin * taps;
+    const long long total = (long long)2 * half * per_row;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const int ro = (int)(idx / Kp);
-        const long long kidx = idx - (long long)ro * Kp;
-        const int tap = (int)(kidx / (kp_tap * planes));
-        int within = (int)(kidx - (long long)tap * kp_tap * planes);
-        const int plane = within / kp_tap;
-        within -= plane * kp_tap;
-        const int sg = within / segpad, c = within - sg * segpad;
+        const int ro = (int)(idx / per_row);
+        const long long rem = idx - (long long)ro * per_row;
+        const int c = (int)(rem / taps), tap = (int)(rem - (long long)c * taps);
+        const int blk = ro >> 5, within = ro & 31, net = within >> 4, ch = blk * 16 + (within & 15);
         float v = 0.f;
-        if (c < Cin) {
-            if (ro < half && sg == 0) v = wa[((size_t)ro * Cin + c) * taps + tap];
-            else if (ro >= half && sg == 1) v = wb[((size_t)(ro - half) * Cin + c) * taps + tap];
-        }
-        const __nv_bfloat16 hi = __float2bfloat16(v);
-        const float r1 = v - __bfloat162float(hi);
-        const __nv_bfloat16 mid = __float2bfloat16(r1);
-        out[idx] = plane == 0 ? hi : (plane == 1 ? mid : __float2bfloat16(r1 - __bfloat162float(mid)));
+        if (net == 0 && c < Cin) v = wa[((size_t)ch * Cin + c) * taps + tap];
+        else if (net == 1 && c >= Cin) v = wb[((size_t)ch * Cin + (c - Cin)) * taps + tap];
+        w_out[idx] = v;
+        if (rem == 0) b_out[ro] = net == 0 ? ba[ch] : bb[ch];
     }
 }
-cudaError_t launch_prepack_blockdiag2(const float* wa, const float* wb, __nv_bfloat16* out, int half, int Cin, int taps, int planes,
-                                      cudaStream_t st) {
-    prepack_blockdiag2_kernel<<<256, 256, 0, st>>>(wa, wb, out, half, Cin, taps, planes);
+cudaError_t launch_build_blockdiag2(const float* wa, const float* wb, const float* ba, const float* bb, float* w_out, float* b_out,
+                                    int half, int Cin, int taps, cudaStream_t st) {
+    if (half % 16 != 0) return cudaErrorInvalidValue;
+    build_blockdiag2_kernel<<<256, 256, 0, st>>>(wa, wb, ba, bb, w_out, b_out, half, Cin, taps);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "kernels.h"
 
 namespace tmae {
 
@@ -40,6 +41,7 @@ struct EpiCtx {
     float ln_inv_c, ln_eps;
     int ln_chunks;
     int act, resid_ld, resid_map, M, N, in_mode, s, K, T, n_img, box_y, box_n, y_tiles, rows_used, exact_act;
+    const GemmParams* gp;                  // the parameter block itself (EPI_GAUSS reads its gc_* fields)
 };
 
 __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
@@ -53,6 +55,7 @@ __device__ __forceinline__ EpiCtx load_epi(const GemmParams& p) {
     e.exact_act = p.mma_terms > 1;
     e.ln_stats_in = p.ln_stats_in; e.ln_wsum = p.ln_wsum; e.ln_stats_out = p.ln_stats_out; e.xbf_out = p.xbf_out;
     e.ln_inv_c = p.ln_inv_c; e.ln_eps = p.ln_eps; e.ln_chunks = p.ln_chunks;
+    e.gp = &p;
     return e;
 }
 
@@ -231,7 +234,9 @@ constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KB
 //   EPI_F32_SAME_RESID one fp32 output at the accumulator's own row with an fp32 residual at the same row (proj, fc2)
 //   EPI_BF16_TMA       EPI_BF16_SAME when the tile is 128 consecutive output rows and block_n % 32 == 0: bias/activation in
 //                      registers, bf16 boxes of 32 columns staged in smem (64B swizzle) and written by TMA stores
-enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2, EPI_BF16_TMA = 3 };
+//   EPI_GAUSS          last layer of cc_transform_mean[i] + cc_transform_scale[i] as one block-diagonal 64-column GEMM: the
+//                      Gaussian conditional (quantise, likelihood, symbols, indexes, y_hat, rate) runs here, thread = pixel
+enum EpiKind : int { EPI_GENERIC = 0, EPI_BF16_SAME = 1, EPI_F32_SAME_RESID = 2, EPI_BF16_TMA = 3, EPI_GAUSS = 4 };
 constexpr uint32_t kStoreBoxBytes = kBlockM * 32 * 2;      // one 128 x 32 bf16 box
 
 // ---------------------------------------------------------------------------------------------------------
@@ -320,6 +325,81 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiCtx& e, int m_tile, 
             }
         }
         if (issuer) bulk_wait_group_read<0>();             // smem may be reused / released once the TMA has read it
+        return;
+    }
+    if (EPI == EPI_GAUSS) {
+        // Columns are interleaved by the weight pack: 32-column chunk b = [mu of channels 16 b .. 16 b + 15 | sigma of the same
+        // channels], so the warp that drains chunk b holds both statistics of its 16 channels of this pixel (MCM.py:762-776).
+        const GemmParams& g = *e.gp;
+        const IoBlock* io = reinterpret_cast<const IoBlock*>(g.gc_io);
+        float* lik_out = io->out.y_likelihoods;
+        int32_t* sym_out = io->out.y_symbols;
+        int16_t* sym16_out = io->out.y_symbols_i16;
+        int32_t* idx_out = io->out.y_indexes;
+        const RowCtx r = decode_row(e, m_tile, quarter * 32 + lane);
+        mbar_wait(wait_bar, wait_parity);
+        tc_fence_after();
+        const uint32_t lane_base = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+        float lg = 0.f;
+        for (int b = half; b < (block_n >> 5); b += nsub) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(lane_base + (uint32_t)(b * 32), acc);
+            tmem_ld_wait();
+            if (!r.valid) continue;
+            const int c0 = g.gc_col0 + b * 16;
+            const size_t off = (size_t)r.lin * g.gc_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 yv = *reinterpret_cast<const float4*>(g.gc_y + off + 4 * j);
+                const float4 bm = __ldg(reinterpret_cast<const float4*>(e.bias + b * 32 + 4 * j));
+                const float4 bs = __ldg(reinterpret_cast<const float4*>(e.bias + b * 32 + 16 + 4 * j));
+                const float4 mv = make_float4(__uint_as_float(acc[4 * j]) + bm.x, __uint_as_float(acc[4 * j + 1]) + bm.y,
+                                              __uint_as_float(acc[4 * j + 2]) + bm.z, __uint_as_float(acc[4 * j + 3]) + bm.w);
+                const float4 sv = make_float4(__uint_as_float(acc[16 + 4 * j]) + bs.x, __uint_as_float(acc[16 + 4 * j + 1]) + bs.y,
+                                              __uint_as_float(acc[16 + 4 * j + 2]) + bs.z, __uint_as_float(acc[16 + 4 * j + 3]) + bs.w);
+                float4 lk, sy, yh;
+                gaussian_elem(yv.x, mv.x, sv.x, lk.x, sy.x, yh.x);
+                gaussian_elem(yv.y, mv.y, sv.y, lk.y, sy.y, yh.y);
+                gaussian_elem(yv.z, mv.z, sv.z, lk.z, sy.z, yh.z);
+                gaussian_elem(yv.w, mv.w, sv.w, lk.w, sy.w, yh.w);
+                const size_t o4 = off + 4 * j;
+                *reinterpret_cast<float4*>(g.gc_mu + o4) = mv;
+                *reinterpret_cast<float4*>(g.gc_sigma + o4) = sv;
+                *reinterpret_cast<float4*>(g.gc_yhat + o4) = yh;
+                store_bf16x4_planes(g.gc_yhat_bf + o4, g.gc_yhat_lo, yh.x, yh.y, yh.z, yh.w);
+                if (lik_out) *reinterpret_cast<float4*>(lik_out + o4) = lk;
+                if (sym_out) *reinterpret_cast<int4*>(sym_out + o4) = make_int4((int)sy.x, (int)sy.y, (int)sy.z, (int)sy.w);
+                if (sym16_out) {
+                    auto sat = [](float v) { return (int16_t)fminf(fmaxf(v, -32768.f), 32767.f); };
+                    short4 s4v;
+                    s4v.x = sat(sy.x); s4v.y = sat(sy.y); s4v.z = sat(sy.z); s4v.w = sat(sy.w);
+                    *reinterpret_cast<short4*>(sym16_out + o4) = s4v;
+                }
+                if (idx_out && g.gc_table) {            // GaussianConditional.build_indexes (MCM.py:839), as in gaussian_slice_kernel
+                    const float sc[4] = {fmaxf(sv.x, 0.11f), fmaxf(sv.y, 0.11f), fmaxf(sv.z, 0.11f), fmaxf(sv.w, 0.11f)};
+                    int id[4] = {0, 0, 0, 0};
+                    for (int t = 0; t < g.gc_ntable - 1; ++t) {
+                        const float tv = __ldg(g.gc_table + t);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) id[q] += (tv < sc[q]) ? 1 : 0;
+                    }
+                    *reinterpret_cast<int4*>(idx_out + o4) = make_int4(id[0], id[1], id[2], id[3]);
+                }
+                lg += (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
+            }
+        }
+        // rate: sum of log2 likelihoods per image (fp32 per warp when its 32 pixels belong to one image, fp64 atomics per image)
+        const unsigned vm = __ballot_sync(0xffffffffu, r.valid != 0);
+        if (vm != 0u) {
+            const int n_first = __shfl_sync(0xffffffffu, r.n, __ffs(vm) - 1);
+            const bool same = __all_sync(0xffffffffu, !r.valid || r.n == n_first);
+            if (same) {
+                const float sm = warp_sum(r.valid ? lg : 0.f);
+                if (lane == 0 && sm != 0.f) atomicAdd(g.gc_rate + n_first, (double)sm);
+            } else if (r.valid) {
+                atomicAdd(g.gc_rate + r.n, (double)lg);
+            }
+        }
         return;
     }
     const RowCtx r = decode_row(e, m_tile, quarter * 32 + lane);
@@ -1097,6 +1177,7 @@ cudaError_t gemm_tc_configure() {
     if ((e = configure_one<ACT_NONE, EPI_BF16_SAME>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_GELU, EPI_BF16_SAME>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_NONE, EPI_F32_SAME_RESID>()) != cudaSuccess) return e;
+    if ((e = configure_one<ACT_NONE, EPI_GAUSS>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_NONE, EPI_BF16_TMA>()) != cudaSuccess) return e;
     if ((e = configure_one<ACT_GELU, EPI_BF16_TMA>()) != cudaSuccess) return e;
     {
@@ -1133,6 +1214,7 @@ bool gemm_use_persistent(int groups, int epi, int act, int tiles, bool share_sm)
 
 // Store-phase specialisation a parameter block qualifies for (every member of a grouped launch must agree).
 int gemm_epi_kind(const GemmParams& p) {
+    if (p.gc_on) return EPI_GAUSS;
     const bool one_out = p.out[1].dtype == OUT_NONE && p.out[0].map == MAP_SAME;
     static const bool no_tma_store = getenv("TMAE_NO_TMA_STORE") != nullptr;
     if (one_out && p.out[0].dtype == OUT_BF16 && p.resid == nullptr && p.act != ACT_HALF_TANH)
@@ -1220,6 +1302,7 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     // 4 % FASTER without it (25.6k vs 24.4k images/s, one batch in flight; equal with four) - off by default.
     const int two_prod = two_prod_env >= 0 ? two_prod_env : 0;
     // every member of a grouped launch shares the activation and the store-phase specialisation
+    if (epi == EPI_GAUSS) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_GAUSS>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     else if (epi == EPI_BF16_TMA && act == ACT_NONE) return launch_k(gemm_tc_kernel<ACT_NONE, EPI_BF16_TMA>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);
     else if (epi == EPI_BF16_SAME && act == ACT_GELU) return launch_k(gemm_tc_kernel<ACT_GELU, EPI_BF16_SAME>, grid, dim3(kGemmThreads), smem, stream, true, d_params, stages, kgroup, d_next, next_groups, two_prod);

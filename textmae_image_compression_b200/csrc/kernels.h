@@ -75,8 +75,8 @@ cudaError_t launch_prepack_weight(const float* w, __nv_bfloat16* out, int Cout, 
                                   const int* segc, int shuffle, int planes, cudaStream_t st, const float* gamma = nullptr);
 cudaError_t launch_fold_ln(const float* w, const float* beta, const float* bias, const __nv_bfloat16* packed, int Kp, int Cout, int Cin,
                            float* bias_out, float* wsum, cudaStream_t st);
-cudaError_t launch_prepack_blockdiag2(const float* wa, const float* wb, __nv_bfloat16* out, int half, int Cin, int taps, int planes,
-                                      cudaStream_t st);
+cudaError_t launch_build_blockdiag2(const float* wa, const float* wb, const float* ba, const float* bb, float* w_out, float* b_out,
+                                    int half, int Cin, int taps, cudaStream_t st);
 cudaError_t launch_permute_bias_shuffle(const float* b, float* out, int Cout, cudaStream_t st);
 cudaError_t launch_eb_table(const float* const* ptrs, float* tab, int Cz, cudaStream_t st);
 cudaError_t launch_f32_to_bf16(const float* a, __nv_bfloat16* o, long long n, long long lo_off, cudaStream_t st);

@@ -132,6 +132,7 @@ struct tmae_handle {
     float* eb_tab = nullptr;
     float* scale_table = nullptr;    // GaussianConditional scale table (tmae_set_scale_table) for y_indexes
     int n_scale_table = 0;
+    bool gc_fuse = false;            // bf16 rate half: cc_transform_mean/scale[i].8 as one GEMM with the Gaussian conditional in its epilogue
     bool finalized = false;
     Workspace ws;
     std::map<int, std::unique_ptr<Plan>> plans;
@@ -475,6 +476,7 @@ struct GemmDesc {
     OutSpec out0 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
     OutSpec out1 = {nullptr, 0, OUT_NONE, MAP_SAME, 0};
     double flops = 0;
+    int gc_slice = -1;          // >= 0: fused mean + scale last layer of this slice, Gaussian conditional in the epilogue
 };
 
 int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmParams* p, int force_block_n) {
@@ -574,6 +576,20 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->out[0] = d.out0;
     p->out[1] = d.out1;
     p->flops = d.flops;
+    if (d.gc_slice >= 0) {
+        const Workspace& w = h->ws;
+        if (L.Cout != 2 * h->sc || p->block_n != L.Cout || (L.Cout & 31) != 0 || L.planes != 1)
+            return fail(h, TMAE_EINVAL, "fused Gaussian layer: needs one %d-column tile (block_n %d)", L.Cout, p->block_n);
+        p->gc_on = 1;
+        p->gc_col0 = d.gc_slice * h->sc;
+        p->gc_ld = h->Cy;
+        p->gc_pixels = h->K;
+        p->gc_y = w.y; p->gc_mu = w.mu; p->gc_sigma = w.sigma; p->gc_yhat = w.yhat;
+        p->gc_yhat_bf = w.yhat_bf.p; p->gc_yhat_lo = w.yhat_bf.lo;
+        p->gc_rate = w.rate_acc;
+        p->gc_table = h->scale_table; p->gc_ntable = h->n_scale_table;
+        p->gc_io = w.io;
+    }
     return TMAE_OK;
 }
 
@@ -746,6 +762,7 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         st.pair = !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && (bn & 15) == 0 &&
                   gemm_use_pair(groups, epi_hint, descs[0].act, max_M, bn, true, conv_l);
         for (int g = 1; g < groups; ++g) if (descs[g].in_mode != descs[0].in_mode) st.pair = false;
+        if (descs[0].gc_slice >= 0) st.pair = false;          // the Gaussian epilogue lives in the one-CTA kernel
     }
     // 3x3 conv launches: haloed-box A reuse when every member agrees on the geometry and the stages fit
     st.conv_reuse_stage_bytes = conv_reuse_stage_bytes(h, descs[0], bn, (max_N + bn - 1) / bn, groups, st.pair);
@@ -977,6 +994,25 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
         int ch[6];
         cc_channels(h, ch, i0, false);
         for (int l = 0; l < 5; ++l) {    // cc_transform_mean[i] and cc_transform_scale[i] of every member, grouped
+            if (l == 4 && h->gc_fuse) {
+                // last layers of both nets as ONE block-diagonal GEMM per member (K segments = the two nets' activations);
+                // its epilogue is the Gaussian conditional of the slice (MCM.py:762-776): no mu / sigma round trip, no extra launch
+                std::vector<GemmDesc> d((size_t)cnt);
+                for (int j = 0; j < cnt; ++j) {
+                    GemmDesc& g = d[(size_t)j];
+                    const int i = i0 + j;
+                    g.layer = get_layer(h, "gc." + std::to_string(i));
+                    g.seg[0] = seg(w.t[j * 3 + 0][3], ch[4], ch[4]);
+                    g.seg[1] = seg(w.t[j * 3 + 1][3], ch[4], ch[4]);
+                    g.nseg = 2;
+                    conv_in(g, s);
+                    g.gc_slice = i;
+                    g.flops = 2.0 * conv_flops(rk, ch[4], ch[5], 9);      // the two layers as the reference counts them (the zero blocks are not work)
+                }
+                snprintf(tag, sizeof(tag), "cc.%d.8+gauss", i0);
+                rc = add_gemm_group(h, pl, d.data(), cnt, tag); if (rc) return rc;
+                continue;
+            }
             std::vector<GemmDesc> d((size_t)cnt * 2);
             for (int j = 0; j < cnt; ++j)
                 for (int net = 0; net < 2; ++net) {
@@ -999,7 +1035,7 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
             snprintf(tag, sizeof(tag), "cc.%d.%d", i0, 2 * l);
             rc = add_gemm_group(h, pl, d.data(), cnt * 2, tag); if (rc) return rc;
         }
-        { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i0; g.gc_slices = cnt; g.tag = "gaussian." + std::to_string(i0); pl.steps.push_back(g); }
+        if (!h->gc_fuse) { Step g; g.kind = ST_GC; g.family = FAM_ENTROPY; g.slice = i0; g.gc_slices = cnt; g.tag = "gaussian." + std::to_string(i0); pl.steps.push_back(g); }
         if (!(skip_dead && i0 >= half_sl)) {
             int lch[6];
             cc_channels(h, lch, i0, true);
@@ -1111,6 +1147,13 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
     static const tmae_outputs kNoOut = {};
     const tmae_outputs& o = a.out ? *a.out : kNoOut;
     const bool simt = (h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) != 0;
+    if (a.io == nullptr && h->gc_fuse) {
+        // plain launches: the fused Gaussian epilogue always reads the caller's output pointers from the device IoBlock
+        IoBlock hio;
+        memset(&hio, 0, sizeof(hio));
+        hio.out = o;
+        CUDA_TRY(h, cudaMemcpyAsync(w.io, &hio, sizeof(hio), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    }
     for (int si = a.begin; si < a.end; ++si) {
         const Step& sp = pl.steps[si];
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1293,6 +1336,7 @@ int tmae_create(const tmae_config* cfg, tmae_handle** out) {
     h->planes = (h->cfg.flags & TMAE_FLAG_PRECISE_X6) ? 3 : 2;
     // the fold needs the thread-per-row TMA-store epilogue; the CUDA-core checker keeps the stand-alone LayerNorm path
     h->ln_fold = !h->precise_enc && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && !getenv("TMAE_NO_LN_FOLD") && !getenv("TMAE_NO_TMA_STORE");
+    h->gc_fuse = !h->precise_rate && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && !getenv("TMAE_NO_GC_FUSE") && h->sc % 16 == 0;
     *out = h.release();
     return TMAE_OK;
 }
@@ -1395,6 +1439,23 @@ int tmae_finalize_weights(tmae_handle* h) {
                 if (l == 0 && sup > 0) { sg[0] = h->Cy; sg[1] = h->sc * sup; nseg = 2; }
                 if ((rc = pack_layer(h, nm, nm, ch[l + 1], ch[l], 9, nseg, sg, 0, h->precise_rate))) return rc;
             }
+        if (h->gc_fuse) {      // cc_transform_mean[i].8 and cc_transform_scale[i].8 as one block-diagonal layer "gc.<i>"
+            const RawTensor *wa = nullptr, *wb = nullptr, *ba = nullptr, *bb = nullptr;
+            const std::string ma = "cc_transform_mean." + std::to_string(i) + ".8", mb = "cc_transform_scale." + std::to_string(i) + ".8";
+            if ((rc = need_raw(h, ma + ".weight", (size_t)h->sc * ch[4] * 9, &wa)) || (rc = need_raw(h, mb + ".weight", (size_t)h->sc * ch[4] * 9, &wb)) ||
+                (rc = need_raw(h, ma + ".bias", (size_t)h->sc, &ba)) || (rc = need_raw(h, mb + ".bias", (size_t)h->sc, &bb))) return rc;
+            RawTensor wt, bt;
+            wt.numel = (size_t)2 * h->sc * 2 * ch[4] * 9; wt.shape = {2 * h->sc, 2 * ch[4], 3, 3};
+            bt.numel = (size_t)2 * h->sc; bt.shape = {2 * h->sc};
+            CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&wt.ptr), wt.numel * sizeof(float)));
+            CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&bt.ptr), bt.numel * sizeof(float)));
+            CUDA_TRY(h, launch_build_blockdiag2(wa->ptr, wb->ptr, ba->ptr, bb->ptr, wt.ptr, bt.ptr, h->sc, ch[4], 9, 0));
+            const std::string key = "gc." + std::to_string(i);
+            h->raw[key + ".weight"] = wt;          // freed with the other raw tensors at the end of finalize
+            h->raw[key + ".bias"] = bt;
+            int sg[3] = {ch[4], ch[4], 0};
+            if ((rc = pack_layer(h, key, key, 2 * h->sc, 2 * ch[4], 9, 2, sg, 0, false))) return rc;
+        }
         int lch[6];
         cc_channels(h, lch, i, true);
         for (int l = 0; l < 5; ++l) {
@@ -1574,8 +1635,12 @@ int tmae_forward_host(tmae_handle* h, const float* h_imgs, const float* h_scores
 int tmae_set_scale_table(tmae_handle* h, const float* table, int n) {
     if (!h || !table || n < 2 || n > 256) return fail(h, TMAE_EINVAL, "scale table: need 2..256 ascending entries");
     if (!h->scale_table) CUDA_TRY(h, cudaMalloc(reinterpret_cast<void**>(&h->scale_table), 256 * sizeof(float)));
+    CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpy(h->scale_table, table, (size_t)n * sizeof(float), cudaMemcpyDefault));
     h->n_scale_table = n;
+    // plans (and their captured graphs) carry the table pointer / length: rebuild them on the next call
+    for (auto& kv : h->plans) { if (kv.second->d_params) cudaFree(kv.second->d_params); if (kv.second->graph) cudaGraphExecDestroy(kv.second->graph); }
+    h->plans.clear();
     return TMAE_OK;
 }
 
