@@ -472,6 +472,31 @@ def run_b200(args, kwargs, batch_named, desc, wl, kind):
                    for f in fams_launch if f["bytes"] > 0 and f["ms"] > 0}
     launches = model.launch_count(max(batch, 1))
 
+    # ---- score generation: what produces `total_scores` upstream of the path; Kodak-sized grey images ----
+    score_gen = None
+    if rank == 0 and world == 1:
+        from textmae_image_compression_b200.scores import generate_scores
+        gh, gw, gn = 512, 768, 64
+        gg = torch.Generator(device="cpu").manual_seed(4)
+        base = torch.nn.functional.interpolate(torch.rand(gn, 1, gh // 16, gw // 16, generator=gg), size=(gh, gw), mode="bilinear")
+        gray = (base[:, 0] * 255 + torch.randn(gn, gh, gw, generator=gg) * 6).clamp(0, 255).to(torch.uint8).to(dev)
+        for _ in range(3):
+            generate_scores(gray)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(20):
+            generate_scores(gray)
+        ev1.record()
+        torch.cuda.synchronize()
+        g_ms = ev0.elapsed_time(ev1) / 20
+        g_bytes = gn * (3 * gh * gw + 4 * 196)            # grey read by the split decisions and the segment pass, segmented image written
+        score_gen = {"images_per_s": gn / (g_ms * 1e-3), "ms_per_batch": g_ms, "batch": gn, "image": [gh, gw], "kernels_per_batch": 4,
+                     "algorithmic_MB_per_batch": g_bytes / 1e6, "GB/s": g_bytes / (g_ms * 1e-3) / 1e9,
+                     "frac_of_hbm_peak": g_bytes / (g_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "note": "tmae_generate_scores (generate_scores_file.py:19-31 on the GPU): latency-bound byte work, 0.4 MB per image; "
+                             "the reference's Python loops take 0.3-1.0 s per image"}
+
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle on a bounded sample ---------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -519,7 +544,7 @@ def run_b200(args, kwargs, batch_named, desc, wl, kind):
                     "ms_per_step": ms_e2e / args.steps, "check": e2e_check},
             "gpu_launches": launches * args.steps,
             "roofline": roofline, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "latency": latency,
+            "latency": latency, "score_generation": score_gen,
             "model_tflops": value * gfl / 1e3,
             "model_tflops_frac_of_peak": value / world * gfl / 1e3 / peak,
             "bpp_mean_last_step": out["bpp"].mean().item(),

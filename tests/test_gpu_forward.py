@@ -563,7 +563,7 @@ print(json.dumps(dict(ids=bool(torch.equal(out["ids_restore"].cpu(), ref["ids_re
 
 @pytest.mark.parametrize("switch", ["TMAE_NO_GRAPH", "TMAE_NO_PDL", "TMAE_NO_TMA_STORE", "TMAE_NO_CONV_REUSE",
                                     "TMAE_NO_WEIGHT_PREFETCH", "TMAE_TWO_PRODUCERS", "TMAE_KGROUP", "TMAE_NO_PAIR", "TMAE_NO_PAIR_CONV",
-                                    "TMAE_NO_LN_FOLD", "TMAE_TC_ATTN"])
+                                    "TMAE_NO_LN_FOLD", "TMAE_NO_TC_ATTN", "TMAE_NO_GC_FUSE"])
 def test_ab_switches_keep_parity(cuda_dev, switch):
     """Every A/B switch named in INTEGRATION.md selects a path that still meets the parity bar (the switches are read
     once per process, hence one subprocess each)."""
@@ -574,3 +574,44 @@ def test_ab_switches_keep_parity(cuda_dev, switch):
     assert p.returncode == 0, p.stderr[-2000:]
     st = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
     assert st["ids"] and st["flips"] < 0.08 and st["bpp_rel"] < 0.02, (switch, st)
+
+
+_GC_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r})
+from textmae_image_compression_b200 import MCM, PathConfig, make_state_dict
+kw = dict(img_size={img}, encoder_embed_dim=128, encoder_depth=2, encoder_num_heads=2, num_keep_patches={K})
+cfg = PathConfig(**kw); sd = make_state_dict(cfg, seed=5)
+g = torch.Generator().manual_seed(7)
+imgs = torch.rand({N}, 3, {img}, {img}, generator=g); scores = torch.rand({N}, cfg.num_patches, generator=g)
+m = MCM(**kw, softmax_isa=16, extra_outputs=True); m.load_state_dict(sd); m.cuda().eval()
+m.update()
+for _ in range(3):                       # plain launches, graph capture, graph replay
+    out = m(imgs.cuda(), scores.cuda())
+sym = m.compress_symbols(imgs.cuda(), scores.cuda())
+torch.cuda.synchronize()
+blob = dict(y_sym=out["latents"]["y_sym"], y_hat=out["latents"]["y_hat"], lik=out["likelihoods"]["y"], mu=out["mu"], sigma=out["sigma"],
+            bpp=out["bpp"], idx=sym["y_indexes"], csym=sym["y_symbols"], launches=m.launch_count({N}))
+torch.save({{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in blob.items()}}, {dst!r})
+"""
+
+
+@pytest.mark.parametrize("img,K,N", [(128, 64, 5), (192, 144, 3), (64, 16, 7)])
+def test_fused_gaussian_epilogue_is_bit_identical(cuda_dev, tmp_path, img, K, N):
+    """The Gaussian conditional in the epilogue of the block-diagonal cc.8 GEMM (default) against the separate
+    gaussian_slice_kernel launches (TMAE_NO_GC_FUSE=1): the zero blocks add exactly 0, so mu / sigma and everything derived
+    from them - symbols, indexes, y_hat, likelihoods - must agree bit for bit; only the fp64 rate atomics may reorder."""
+    import subprocess, sys
+    root = str(Path(__file__).resolve().parent.parent)
+    res = {}
+    for tag, env in (("fused", {}), ("plain", {"TMAE_NO_GC_FUSE": "1"})):
+        dst = str(tmp_path / f"{tag}.pt")
+        p = subprocess.run([sys.executable, "-c", _GC_SCRIPT.format(root=root, img=img, K=K, N=N, dst=dst)], capture_output=True, text=True,
+                           timeout=300, env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[tag] = torch.load(dst)
+    a, b = res["fused"], res["plain"]
+    for k in ("y_sym", "y_hat", "lik", "mu", "sigma", "idx", "csym"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.allclose(a["bpp"], b["bpp"], rtol=1e-6)
+    assert a["launches"] == b["launches"] - 7          # seven gaussian_slice launches (slices 0-5 + the grouped 6-11) are gone
