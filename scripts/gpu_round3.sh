@@ -24,3 +24,9 @@ if [[ $STAGES == *workloads* ]]; then
   TMO=300 TAILN=60 run steps_B64 python scripts/profile_steps.py B64
 fi
 if [[ $STAGES == *ncu* ]]; then bash scripts/gpu_profile.sh B64; fi
+if [[ $STAGES == *scores* ]]; then
+  TMO=600 TAILN=4 run scores_test python -m pytest -p no:cacheprovider -q -m gpu tests/test_gpu_scores.py
+  TMO=300 TAILN=2 run scores_bench python scripts/bench_scores.py
+  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -k regex:score_ -c 40 --csv --log-file $O/scores_launches.csv python scripts/bench_scores.py > $O/scores_ncu.log 2>&1
+  echo "rc=$? scores ncu"
+fi

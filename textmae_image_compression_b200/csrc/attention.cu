@@ -317,8 +317,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr) 
     return d;
 }
 
-template <int NCH>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
-__global__ void __launch_bounds__(kAttnTcThreads, 1)
+// WGS = softmax groups per CTA.  2: one 320-thread CTA per SM with double-buffered S / O / P (or 1 buffer for long rows).
+// 1 ("lite", Tp <= 96): 192 threads, one buffer, two pipeline stages, 256 TMEM columns, <= 93 KB shared memory - two such CTAs
+// share an SM, or one of them shares it with a GEMM CTA of another stream (multi-stream mode, TMAE_FLAG_SHARE_SM).
+template <int NCH, int WGS>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
+__global__ void __launch_bounds__(64 + 128 * WGS, WGS == 1 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                     __nv_bfloat16* __restrict__ out, const AttnTcParams p) {
     pdl_launch_dependents();
@@ -590,7 +593,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 // shared-memory / tensor-memory plan of the tcgen05 kernel for T tokens; returns false when it does not fit
-inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* out, size_t* smem) {
+inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* out, size_t* smem, bool lite = false) {
     AttnTcParams p = {};
     const int Tp = attn_tp(T);
     if (Tp > kAttnTcMaxTp) return false;
@@ -607,9 +610,11 @@ inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* 
     const size_t limit = 227 * 1024 - 256;
     const size_t stage = p.qreg + 2 * (size_t)p.kreg, pb = (size_t)p.atoms * 16384;
     p.nbuf = (2 * sp + 128 <= 512 && 2 * stage + 2 * pb <= limit) ? 2 : 1;
+    if (lite) p.nbuf = 1;
     if (stage + (size_t)p.nbuf * pb > limit) return false;
     int nst = (int)((limit - (size_t)p.nbuf * pb) / stage);
     p.nst = nst > kAttnTcMaxStages ? kAttnTcMaxStages : nst;
+    if (lite && p.nst > 2) p.nst = 2;
     p.s_stride = sp;
     p.o_col0 = (uint32_t)p.nbuf * sp;
     const uint32_t need = p.o_col0 + (uint32_t)p.nbuf * 64u;
@@ -630,11 +635,13 @@ cudaError_t attention_configure(int T) {
     static cudaError_t once = [] {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(attention_tc_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(attention_tc_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        e = cudaFuncSetAttribute(attention_tc_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(attention_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }();
@@ -667,10 +674,13 @@ void attention_tc_boxes(int T, int* q_rows, int* kv_rows) {
     *q_rows = p.qrows; *kv_rows = p.krows;
 }
 cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int N, int T, int H, int C,
-                                float scale, cudaStream_t st, long long* dbg) {
+                                float scale, cudaStream_t st, long long* dbg, bool share_sm) {
     if (C != H * HD) return cudaErrorInvalidValue;
     AttnTcParams p; size_t smem;
-    if (!attn_tc_plan(T, H, C, N, scale, &p, &smem)) return cudaErrorInvalidValue;
+    // lite form: short rows while several streams share the GPU (TMAE_ATTN_LITE=0 / 1 forces it off / on for A/B runs)
+    static const char* lite_env = getenv("TMAE_ATTN_LITE");
+    const bool lite = attn_tp(T) <= 96 && (lite_env ? lite_env[0] == '1' : share_sm);
+    if (!attn_tc_plan(T, H, C, N, scale, &p, &smem, lite)) return cudaErrorInvalidValue;
     p.dbg = dbg;
     static int sms = 0;
     if (sms == 0) {
@@ -678,13 +688,18 @@ cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    TMAE_CARVEOUT_ONCE(attention_tc_kernel<3>);
-    TMAE_CARVEOUT_ONCE(attention_tc_kernel<4>);
-    TMAE_CARVEOUT_ONCE(attention_tc_kernel<0>);
+    TMAE_CARVEOUT_ONCE((attention_tc_kernel<3, 2>));
+    TMAE_CARVEOUT_ONCE((attention_tc_kernel<3, 1>));
+    TMAE_CARVEOUT_ONCE((attention_tc_kernel<4, 2>));
+    TMAE_CARVEOUT_ONCE((attention_tc_kernel<0, 2>));
+    if (lite) {
+        const int grid = p.n_items < 2 * sms ? p.n_items : 2 * sms;
+        return launch_k(attention_tc_kernel<3, 1>, dim3(grid), dim3(192), smem, st, true, *map_q, *map_kv, out, p);
+    }
     const int grid = p.n_items < sms ? p.n_items : sms;
-    if (p.Tp <= 96) return launch_k(attention_tc_kernel<3>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
-    if (p.Tp <= 128) return launch_k(attention_tc_kernel<4>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
-    return launch_k(attention_tc_kernel<0>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    if (p.Tp <= 96) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    if (p.Tp <= 128) return launch_k(attention_tc_kernel<4, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    return launch_k(attention_tc_kernel<0, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
 }
 
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,

@@ -329,7 +329,8 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiCtx& e, int m_tile, 
     }
     if (EPI == EPI_GAUSS) {
         // Columns are interleaved by the weight pack: 32-column chunk b = [mu of channels 16 b .. 16 b + 15 | sigma of the same
-        // channels], so the warp that drains chunk b holds both statistics of its 16 channels of this pixel (MCM.py:762-776).
+        // channels], so the CTA that owns chunk b (block_n = 32) holds both statistics of its 16 channels of every pixel of
+        // the tile (MCM.py:762-776).
         const GemmParams& g = *e.gp;
         const IoBlock* io = reinterpret_cast<const IoBlock*>(g.gc_io);
         float* lik_out = io->out.y_likelihoods;
@@ -341,51 +342,60 @@ __device__ __forceinline__ void epilogue_tile_impl(const EpiCtx& e, int m_tile, 
         tc_fence_after();
         const uint32_t lane_base = tmem_acc + ((uint32_t)(quarter * 32) << 16);
         float lg = 0.f;
-        for (int b = half; b < (block_n >> 5); b += nsub) {
+        {
+            // block_n == 32: this CTA owns chunk b = n0 / 32, i.e. channels [16 b, 16 b + 16); the two warps of a TMEM lane
+            // quarter take 8 channels each (2 x 32 CTAs x 8 warps share the erfc / log2 work of a slice)
+            const int b = n0 >> 5;
             uint32_t acc[32];
-            tmem_ld_32x32b_x32(lane_base + (uint32_t)(b * 32), acc);
+            tmem_ld_32x32b_x32(lane_base, acc);
             tmem_ld_wait();
-            if (!r.valid) continue;
-            const int c0 = g.gc_col0 + b * 16;
-            const size_t off = (size_t)r.lin * g.gc_ld + c0;
+            if (r.valid) {
+                const int c0 = g.gc_col0 + b * 16;
+                const size_t off = (size_t)r.lin * g.gc_ld + c0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 yv = *reinterpret_cast<const float4*>(g.gc_y + off + 4 * j);
-                const float4 bm = __ldg(reinterpret_cast<const float4*>(e.bias + b * 32 + 4 * j));
-                const float4 bs = __ldg(reinterpret_cast<const float4*>(e.bias + b * 32 + 16 + 4 * j));
-                const float4 mv = make_float4(__uint_as_float(acc[4 * j]) + bm.x, __uint_as_float(acc[4 * j + 1]) + bm.y,
-                                              __uint_as_float(acc[4 * j + 2]) + bm.z, __uint_as_float(acc[4 * j + 3]) + bm.w);
-                const float4 sv = make_float4(__uint_as_float(acc[16 + 4 * j]) + bs.x, __uint_as_float(acc[16 + 4 * j + 1]) + bs.y,
-                                              __uint_as_float(acc[16 + 4 * j + 2]) + bs.z, __uint_as_float(acc[16 + 4 * j + 3]) + bs.w);
-                float4 lk, sy, yh;
-                gaussian_elem(yv.x, mv.x, sv.x, lk.x, sy.x, yh.x);
-                gaussian_elem(yv.y, mv.y, sv.y, lk.y, sy.y, yh.y);
-                gaussian_elem(yv.z, mv.z, sv.z, lk.z, sy.z, yh.z);
-                gaussian_elem(yv.w, mv.w, sv.w, lk.w, sy.w, yh.w);
-                const size_t o4 = off + 4 * j;
-                *reinterpret_cast<float4*>(g.gc_mu + o4) = mv;
-                *reinterpret_cast<float4*>(g.gc_sigma + o4) = sv;
-                *reinterpret_cast<float4*>(g.gc_yhat + o4) = yh;
-                store_bf16x4_planes(g.gc_yhat_bf + o4, g.gc_yhat_lo, yh.x, yh.y, yh.z, yh.w);
-                if (lik_out) *reinterpret_cast<float4*>(lik_out + o4) = lk;
-                if (sym_out) *reinterpret_cast<int4*>(sym_out + o4) = make_int4((int)sy.x, (int)sy.y, (int)sy.z, (int)sy.w);
-                if (sym16_out) {
-                    auto sat = [](float v) { return (int16_t)fminf(fmaxf(v, -32768.f), 32767.f); };
-                    short4 s4v;
-                    s4v.x = sat(sy.x); s4v.y = sat(sy.y); s4v.z = sat(sy.z); s4v.w = sat(sy.w);
-                    *reinterpret_cast<short4*>(sym16_out + o4) = s4v;
-                }
-                if (idx_out && g.gc_table) {            // GaussianConditional.build_indexes (MCM.py:839), as in gaussian_slice_kernel
-                    const float sc[4] = {fmaxf(sv.x, 0.11f), fmaxf(sv.y, 0.11f), fmaxf(sv.z, 0.11f), fmaxf(sv.w, 0.11f)};
-                    int id[4] = {0, 0, 0, 0};
-                    for (int t = 0; t < g.gc_ntable - 1; ++t) {
-                        const float tv = __ldg(g.gc_table + t);
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = half * 2 + jj;                     // 4-channel group of the chunk
+                    const float4 yv = *reinterpret_cast<const float4*>(g.gc_y + off + 4 * j);
+                    const float4 bm = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + 4 * j));
+                    const float4 bs = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + 16 + 4 * j));
+                    float a[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) id[q] += (tv < sc[q]) ? 1 : 0;
+                    for (int q = 0; q < 4; ++q) {                    // dynamic j: select the registers without local memory
+                        a[q] = __uint_as_float(half == 0 ? acc[4 * jj + q] : acc[8 + 4 * jj + q]);
+                        a[4 + q] = __uint_as_float(half == 0 ? acc[16 + 4 * jj + q] : acc[24 + 4 * jj + q]);
                     }
-                    *reinterpret_cast<int4*>(idx_out + o4) = make_int4(id[0], id[1], id[2], id[3]);
+                    const float4 mv = make_float4(a[0] + bm.x, a[1] + bm.y, a[2] + bm.z, a[3] + bm.w);
+                    const float4 sv = make_float4(a[4] + bs.x, a[5] + bs.y, a[6] + bs.z, a[7] + bs.w);
+                    float4 lk, sy, yh;
+                    gaussian_elem(yv.x, mv.x, sv.x, lk.x, sy.x, yh.x);
+                    gaussian_elem(yv.y, mv.y, sv.y, lk.y, sy.y, yh.y);
+                    gaussian_elem(yv.z, mv.z, sv.z, lk.z, sy.z, yh.z);
+                    gaussian_elem(yv.w, mv.w, sv.w, lk.w, sy.w, yh.w);
+                    const size_t o4 = off + 4 * j;
+                    *reinterpret_cast<float4*>(g.gc_mu + o4) = mv;
+                    *reinterpret_cast<float4*>(g.gc_sigma + o4) = sv;
+                    *reinterpret_cast<float4*>(g.gc_yhat + o4) = yh;
+                    store_bf16x4_planes(g.gc_yhat_bf + o4, g.gc_yhat_lo, yh.x, yh.y, yh.z, yh.w);
+                    if (lik_out) *reinterpret_cast<float4*>(lik_out + o4) = lk;
+                    if (sym_out) *reinterpret_cast<int4*>(sym_out + o4) = make_int4((int)sy.x, (int)sy.y, (int)sy.z, (int)sy.w);
+                    if (sym16_out) {
+                        auto sat = [](float v) { return (int16_t)fminf(fmaxf(v, -32768.f), 32767.f); };
+                        short4 s4v;
+                        s4v.x = sat(sy.x); s4v.y = sat(sy.y); s4v.z = sat(sy.z); s4v.w = sat(sy.w);
+                        *reinterpret_cast<short4*>(sym16_out + o4) = s4v;
+                    }
+                    if (idx_out && g.gc_table) {            // GaussianConditional.build_indexes (MCM.py:839), as in gaussian_slice_kernel
+                        const float sc[4] = {fmaxf(sv.x, 0.11f), fmaxf(sv.y, 0.11f), fmaxf(sv.z, 0.11f), fmaxf(sv.w, 0.11f)};
+                        int id[4] = {0, 0, 0, 0};
+                        for (int t = 0; t < g.gc_ntable - 1; ++t) {
+                            const float tv = __ldg(g.gc_table + t);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) id[q] += (tv < sc[q]) ? 1 : 0;
+                        }
+                        *reinterpret_cast<int4*>(idx_out + o4) = make_int4(id[0], id[1], id[2], id[3]);
+                    }
+                    lg += (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
                 }
-                lg += (log2f(lk.x) + log2f(lk.y)) + (log2f(lk.z) + log2f(lk.w));
             }
         }
         // rate: sum of log2 likelihoods per image (fp32 per warp when its 32 pixels belong to one image, fp64 atomics per image)

@@ -103,10 +103,10 @@ score_judge_large_kernel(const uint8_t* __restrict__ gray, const __grid_constant
     const int rows_per = (h + chunks - 1) / chunks;
     const int r0 = chunk * rows_per, r1 = min(h, r0 + rows_per);
     const uint8_t* base = gray + (size_t)img * g.H * g.W + (size_t)oy * g.W + ox;
-    const int npx = (r1 - r0) * w;
-    for (int e = tid; e < npx; e += kJudgeThreads) {
-        const int r = e / w, c = e - r * w;
-        atomicAdd(&hist[warp][base[(size_t)(r0 + r) * g.W + c]], 1u);
+    // one warp per row (coalesced byte loads along the row), rows dealt round-robin to the warps: no per-pixel division
+    for (int r = r0 + warp; r < r1; r += kJudgeWarps) {
+        const uint8_t* rowp = base + (size_t)r * g.W;
+        for (int c = tid & 31; c < w; c += 32) atomicAdd(&hist[warp][rowp[c]], 1u);
     }
     __syncthreads();
     unsigned cnt = 0;
@@ -149,9 +149,14 @@ score_judge_small_kernel(const uint8_t* __restrict__ gray, const __grid_constant
     for (int k = 0; k < 8; ++k) hist[warp][lane * 8 + k] = 0;
     __syncwarp();
     const uint8_t* base = gray + (size_t)img * g.H * g.W + (size_t)oy * g.W + ox;
-    for (int e = lane; e < h * w; e += 32) {
-        const int r = e / w, c = e - r * w;
-        atomicAdd(&hist[warp][base[(size_t)r * g.W + c]], 1u);
+    {   // lane -> pixel e = lane, lane + 32, ...: (r, c) advanced incrementally instead of divided per pixel
+        int r = lane / w, c = lane - r * w;
+        const int dr = 32 / w, dc = 32 - dr * w;
+        for (int e = lane; e < h * w; e += 32) {
+            atomicAdd(&hist[warp][base[(size_t)r * g.W + c]], 1u);
+            r += dr; c += dc;
+            if (c >= w) { c -= w; ++r; }
+        }
     }
     __syncwarp();
     const bool uniform = judge_from_hist_warp(hist[warp], h * w, lane);
@@ -160,25 +165,37 @@ score_judge_small_kernel(const uint8_t* __restrict__ gray, const __grid_constant
 
 // Recursion + Merge (utils/map.py:27-42) for one pixel: descend while the node was split; a pixel on the odd last row /
 // column of a split node belongs to no child and keeps its value.
-__global__ void __launch_bounds__(256)
-score_segment_kernel(const uint8_t* __restrict__ gray, const __grid_constant__ ScoreGeom g, const uint8_t* __restrict__ flags, uint8_t* __restrict__ seg) {
-    const int img = blockIdx.y;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= g.H * g.W) return;
-    const int y = p / g.W, x = p - y * g.W;
-    const uint8_t v = gray[(size_t)img * g.H * g.W + p];
-    const uint8_t* fl = flags + (size_t)img * g.flag_total;
+__device__ __forceinline__ uint8_t segment_pixel(const ScoreGeom& g, const uint8_t* __restrict__ fl, int y, int x, uint8_t v) {
     int d = 0, node_i = 0, node_j = 0, oy = 0, ox = 0;
-    bool covered = true;
     while (d < g.levels && !fl[g.flag_off[d] + (node_i << d) + node_j]) {
         const int nh = g.h[d + 1], nw = g.w[d + 1];
         const int cy = (y - oy) >= nh ? 1 : 0, cx = (x - ox) >= nw ? 1 : 0;
         oy += cy * nh; ox += cx * nw;
-        if (y - oy >= nh || x - ox >= nw) { covered = false; break; }
+        if (y - oy >= nh || x - ox >= nw) return v;              // odd last row / column of a split node: never visited
         node_i = node_i * 2 + cy; node_j = node_j * 2 + cx;
         ++d;
     }
-    seg[(size_t)img * g.H * g.W + p] = covered ? ((v > 60 && v < 150) ? 0 : 255) : v;
+    return (v > 60 && v < 150) ? 0 : 255;                         // Merge (utils/map.py:27-31)
+}
+// VEC = 4: W % 4 == 0, a thread handles four consecutive pixels of one row with 32-bit loads / stores
+template <int VEC>
+__global__ void __launch_bounds__(256)
+score_segment_kernel(const uint8_t* __restrict__ gray, const __grid_constant__ ScoreGeom g, const uint8_t* __restrict__ flags, uint8_t* __restrict__ seg) {
+    const int img = blockIdx.y;
+    const int p = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (p >= g.H * g.W) return;
+    const int y = p / g.W, x = p - y * g.W;
+    const uint8_t* fl = flags + (size_t)img * g.flag_total;
+    const size_t off = (size_t)img * g.H * g.W + p;
+    if (VEC == 4) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(gray + off);
+        uchar4 o;
+        o.x = segment_pixel(g, fl, y, x, v.x); o.y = segment_pixel(g, fl, y, x + 1, v.y);
+        o.z = segment_pixel(g, fl, y, x + 2, v.z); o.w = segment_pixel(g, fl, y, x + 3, v.w);
+        *reinterpret_cast<uchar4*>(seg + off) = o;
+    } else {
+        seg[off] = segment_pixel(g, fl, y, x, gray[off]);
+    }
 }
 
 // cv2.resize (INTER_LINEAR, 8-bit) tap of one output coordinate: source indices and 11-bit coefficients.
@@ -343,7 +360,9 @@ cudaError_t launch_generate_scores(const uint8_t* gray, int n, const ScoreGeom& 
         score_judge_small_kernel<<<dim3((g.small_nodes + kJudgeWarps - 1) / kJudgeWarps, n), kJudgeThreads, 0, st>>>(gray, g, flags);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    score_segment_kernel<<<dim3((g.H * g.W + 255) / 256, n), 256, 0, st>>>(gray, g, flags, seg);
+    const bool vec4 = g.W % 4 == 0 && (reinterpret_cast<uintptr_t>(gray) & 3) == 0;          // seg is 256-byte aligned in the workspace
+    if (vec4) score_segment_kernel<4><<<dim3((g.H * g.W / 4 + 255) / 256, n), 256, 0, st>>>(gray, g, flags, seg);
+    else score_segment_kernel<1><<<dim3((g.H * g.W + 255) / 256, n), 256, 0, st>>>(gray, g, flags, seg);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     score_patch_kernel<<<dim3((unsigned)L, n), 256, 0, st>>>(seg, g, prod, img_tickets, scores, s_map, t_map);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

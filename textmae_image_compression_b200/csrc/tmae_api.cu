@@ -578,8 +578,8 @@ int fill_params(tmae_handle* h, const GemmDesc& d, int groups_for_tiling, GemmPa
     p->flops = d.flops;
     if (d.gc_slice >= 0) {
         const Workspace& w = h->ws;
-        if (L.Cout != 2 * h->sc || p->block_n != L.Cout || (L.Cout & 31) != 0 || L.planes != 1)
-            return fail(h, TMAE_EINVAL, "fused Gaussian layer: needs one %d-column tile (block_n %d)", L.Cout, p->block_n);
+        if (L.Cout != 2 * h->sc || p->block_n != 32 || (L.Cout & 31) != 0 || L.planes != 1)
+            return fail(h, TMAE_EINVAL, "fused Gaussian layer: needs 32-column tiles of a %d-column layer (block_n %d)", L.Cout, p->block_n);
         p->gc_on = 1;
         p->gc_col0 = d.gc_slice * h->sc;
         p->gc_ld = h->Cy;
@@ -728,6 +728,7 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
     }
     const int m_tiles = (max_M + kBlockM - 1) / kBlockM;
     int bn = pick_block_n(m_tiles, max_N, groups);
+    if (descs[0].gc_slice >= 0) bn = 32;        // fused Gaussian epilogue: one 32-column chunk (16 channels: mu | sigma) per CTA
     if (!(h->cfg.flags & TMAE_FLAG_SHARE_SM) && groups == 1 && m_tiles * ((max_N + 255) / 256) > 2 * 148 - 1 && descs[0].out0.dtype == OUT_BF16 && descs[0].out0.map == MAP_SAME &&
         descs[0].out1.dtype == OUT_NONE && descs[0].resid == nullptr) {
         // persistent-kernel candidate: tiles are dealt round-robin to 148 CTAs -> minimise rounds x (tile width + fixed cost)
@@ -1203,7 +1204,8 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 if (h->precise_enc)
                     CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else if (pl.attn_tc)
-                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
+                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st, nullptr,
+                                                    (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0));
                 else
                     CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 break;
@@ -1889,7 +1891,7 @@ int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int imp
     const int C = H * 64;
     cudaError_t e = attention_configure(T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
-    if (impl == 1) {
+    if (impl == 1 || impl == 2) {          // 2 = the multi-stream ("lite") form of the tcgen05 kernel for short rows
         if (!attention_tc_supported(T)) return fail(nullptr, TMAE_EINVAL, "tcgen05 attention needs T <= 384");
         CUtensorMap mq, mk;
         if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, &mq, &mk))) {
@@ -1898,7 +1900,7 @@ int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int imp
         long long* dbg = nullptr;
         const bool timing = getenv("TMAE_ATTN_TIMING") != nullptr;      // bring-up aid: per-phase clock64 stamps of CTA 0
         if (timing) { cudaMalloc(reinterpret_cast<void**>(&dbg), 64 * 16 * 8); cudaMemset(dbg, 0, 64 * 16 * 8); }
-        e = launch_attention_tc(&mq, &mk, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st, dbg);
+        e = launch_attention_tc(&mq, &mk, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st, dbg, impl == 2);
         if (timing) {
             cudaStreamSynchronize(st);
             std::vector<long long> hd(64 * 16);
