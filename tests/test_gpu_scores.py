@@ -78,3 +78,41 @@ def test_rejects_bad_geometry_and_cpu_tensors(cuda_dev):
         generate_scores(torch.zeros(1, 64, 64, dtype=torch.uint8))
     with pytest.raises(TypeError):
         generate_scores(torch.zeros(1, 64, 64, device="cuda"))
+
+
+def test_preprocess_image_scores_keeps_the_reference_file_contract(cuda_dev, tmp_path):
+    """generate_scores_file.py:13-36: sorted rglob over the dataset folder, one row per image, torch.save of the stack; images
+    of different sizes in one folder (batched per size on the GPU)."""
+    cv2 = pytest.importorskip("cv2")
+    from textmae_image_compression_b200.scores import preprocess_image_scores
+    imgs = {"b.png": ref_scores.synthetic_gray(0, 300, 411, 1), "a.png": ref_scores.synthetic_gray(4, 256, 384, 2),
+            "sub/c.png": ref_scores.synthetic_gray(2, 300, 411, 3)}
+    (tmp_path / "data" / "sub").mkdir(parents=True)
+    for name, im in imgs.items():
+        assert cv2.imwrite(str(tmp_path / "data" / name), im)
+    out_file = tmp_path / "scores.pt"
+    got = preprocess_image_scores(tmp_path / "data", out_file)
+    saved = torch.load(out_file)
+    assert torch.equal(saved.nan_to_num(-1), got.nan_to_num(-1)) and saved.shape == (3, 196) and saved.dtype == torch.float32
+    order = sorted(imgs)                                       # sorted(Path.rglob) == lexicographic full paths: a.png, b.png, sub/c.png
+    for row, name in zip(saved, order):
+        assert np.array_equal(row.numpy(), ref_scores.generate_scores(imgs[name]), equal_nan=True), name
+
+
+def test_generated_scores_drive_the_model_like_reference_scores(cuda_dev, kodak):
+    """grey Kodak image -> GPU scores -> mask kernel + forward: identical to the run on the reference-generated scores."""
+    from textmae_image_compression_b200 import MCM, make_state_dict, vit_base
+    from textmae_image_compression_b200.scores import generate_scores
+    gray = np.load(GOLDEN / "kodak_gray6.npz")
+    names = sorted(gray.files)
+    sel = [i for i, n in enumerate(names) if gray[n].shape == (512, 768)][:4]
+    sc = generate_scores(torch.from_numpy(np.stack([gray[names[i]] for i in sel])).cuda())
+    imgs, gold_scores = kodak
+    assert torch.equal(sc.cpu(), gold_scores[sel])
+    cfg = vit_base(64)
+    m = MCM(num_keep_patches=64, softmax_isa=16)
+    m.load_state_dict(make_state_dict(cfg, seed=0))
+    m.cuda().eval()
+    a = m(imgs[sel].cuda(), sc, need_recon=False)
+    b = m(imgs[sel].cuda(), gold_scores[sel].cuda(), need_recon=False)
+    assert torch.equal(a["ids_restore"], b["ids_restore"]) and torch.equal(a["latents"]["y_sym"], b["latents"]["y_sym"])

@@ -290,6 +290,7 @@ constexpr int kAttnTcMaxStages = 3;
 struct AttnTcParams {
     int T, Tp, H, C;
     int n_items, q_tiles;
+    int tail_rows;            // query rows past the last full 128-row tile (T = 257: the 257th) computed by the tail warp on CUDA cores
     int nbuf;                 // 2: double-buffered S / O / P and both softmax groups; 1: single (Tp > 192)
     int nst;                  // Q/K/V stages
     int qrows, krows, kloads; // TMA boxes: Q rows, K/V rows per load, loads per K/V tile
@@ -321,9 +322,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr) 
 // 1 ("lite", Tp <= 96): 192 threads, one buffer, two pipeline stages, 256 TMEM columns, <= 93 KB shared memory - two such CTAs
 // share an SM, or one of them shares it with a GEMM CTA of another stream (multi-stream mode, TMAE_FLAG_SHARE_SM).
 template <int NCH, int WGS>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
-__global__ void __launch_bounds__(64 + 128 * WGS, WGS == 1 ? 2 : 1)
+__global__ void __launch_bounds__(64 + 128 * WGS + (WGS == 2 ? 32 : 0), WGS == 1 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                    __nv_bfloat16* __restrict__ out, const AttnTcParams p) {
+                    const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const AttnTcParams p) {
+    constexpr bool kTailWarp = WGS == 2;          // one more warp: the few query rows past the last full tile, on CUDA cores
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem_tc[];
     const uint32_t stage_bytes = p.qreg + 2u * p.kreg;
@@ -342,7 +344,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < 3; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[3 + s], 1); }
+        for (int s = 0; s < 3; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[3 + s], kTailWarp ? 2 : 1); }   // empty: MMA commit (+ tail warp)
         for (int b = 0; b < 2; ++b) { mbar_init(&bars[6 + b], 1); mbar_init(&bars[8 + b], 128); mbar_init(&bars[10 + b], 1); mbar_init(&bars[12 + b], 128); }
         fence_barrier_init();
         tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_kv);
@@ -422,6 +424,88 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 umma_commit_a(bar_empty(st));                         // Q / K / V of this stage are no longer read
                 if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 3] = clock64();
             }
+        }
+    } else if (kTailWarp && warp == 2 + 4 * WGS) {
+        // ===== tail warp: T = 128 q + r with r <= 8 (ViT-L: 257 = 2 x 128 + 1).  A third query tile for r rows would repeat
+        // the whole K / V load and both MMAs; instead the item of the LAST full tile also computes those r rows here, on CUDA
+        // cores, from the K / V tiles already in shared memory (swizzled as TMA wrote them): lanes = keys for q k^T, lanes =
+        // dim pairs for p v.  Every item is waited for and released (empty has two arrivals), so the warp cannot run ahead.
+        for (int k = 0; k < n_my; ++k) {
+            const int item = (int)blockIdx.x + k * (int)gridDim.x;
+            const int qt = item % p.q_tiles, nh = item / p.q_tiles;
+            const int h = nh % p.H, n = nh / p.H;
+            const int st = k % p.nst;
+            mbar_wait_a(bar_full(st), ((uint32_t)(k / p.nst)) & 1u);
+            if (p.tail_rows > 0 && qt == p.q_tiles - 1) {
+                const uint32_t kb = smem0 + (uint32_t)st * stage_bytes + p.qreg, vb = kb + p.kreg;
+                for (int tr = 0; tr < p.tail_rows; ++tr) {
+                    const int t = p.q_tiles * 128 + tr;
+                    const uint4* qg = reinterpret_cast<const uint4*>(qkv + (size_t)(n * p.T + t) * 3 * p.C + (size_t)h * HD);
+                    float q[HD];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 v = __ldg(qg + c);
+                        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            q[c * 8 + 2 * e] = __uint_as_float(w4[e] << 16);
+                            q[c * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
+                        }
+                    }
+                    float sc[12];                                   // Tp <= 384: at most 12 rounds of 32 keys
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        sc[i] = -INFINITY;
+                        const int j = i * 32 + lane;
+                        if (i * 32 < p.T && j < p.T) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const float4 kv = lds128(kb + (uint32_t)j * 128u + ((((uint32_t)c) ^ ((uint32_t)j & 7u)) << 4));
+                                const uint32_t w4[4] = {__float_as_uint(kv.x), __float_as_uint(kv.y), __float_as_uint(kv.z), __float_as_uint(kv.w)};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    acc = fmaf(q[c * 8 + 2 * e], __uint_as_float(w4[e] << 16), acc);
+                                    acc = fmaf(q[c * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), acc);
+                                }
+                            }
+                            sc[i] = acc * p.scale_log2e;
+                            mx = fmaxf(mx, sc[i]);
+                        }
+                    }
+                    mx = warp_max(mx);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        // P is rounded to bf16 before the second product, like the tensor-core path does
+                        const float pe = (sc[i] == -INFINITY) ? 0.f : ex2_approx(sc[i] - mx);
+                        sum += pe;
+                        sc[i] = __bfloat162float(__float2bfloat16(pe));
+                    }
+                    sum = warp_sum(sum);
+                    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) {
+                        if (i * 32 < p.T) {
+                            const int jn = min(32, p.T - i * 32);
+                            for (int jj = 0; jj < jn; ++jj) {
+                                const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
+                                const int j = i * 32 + jj;
+                                uint32_t vw;
+                                asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(vw)
+                                             : "r"(vb + (uint32_t)j * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)j & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u));
+                                o0 = fmaf(pj, __uint_as_float(vw << 16), o0);
+                                o1 = fmaf(pj, __uint_as_float(vw & 0xffff0000u), o1);
+                            }
+                        }
+                    }
+                    const float inv = 1.f / sum;
+                    *reinterpret_cast<uint32_t*>(out + (size_t)(n * p.T + t) * p.C + (size_t)h * HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[3 + st]);
         }
     } else {
         const int g = (warp - 2) >> 2;                                // softmax group
@@ -599,6 +683,9 @@ inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* 
     if (Tp > kAttnTcMaxTp) return false;
     p.T = T; p.Tp = Tp; p.H = H; p.C = C;
     p.q_tiles = (T + 127) / 128;
+    p.tail_rows = 0;
+    static const bool no_tail = getenv("TMAE_NO_ATTN_TAIL") != nullptr;
+    if (!lite && !no_tail && T / 128 >= 1 && T % 128 != 0 && T % 128 <= 8) { p.q_tiles = T / 128; p.tail_rows = T % 128; }
     p.n_items = N * H * p.q_tiles;
     p.qrows = Tp < 128 ? Tp : 128;
     p.kloads = Tp <= 256 ? 1 : 2;
@@ -673,8 +760,8 @@ void attention_tc_boxes(int T, int* q_rows, int* kv_rows) {
     attn_tc_plan(T, 1, HD, 1, 0.125f, &p, &smem);
     *q_rows = p.qrows; *kv_rows = p.krows;
 }
-cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, __nv_bfloat16* out, int N, int T, int H, int C,
-                                float scale, cudaStream_t st, long long* dbg, bool share_sm) {
+cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int N,
+                                int T, int H, int C, float scale, cudaStream_t st, long long* dbg, bool share_sm) {
     if (C != H * HD) return cudaErrorInvalidValue;
     AttnTcParams p; size_t smem;
     // lite form: short rows while several streams share the GPU (TMAE_ATTN_LITE=0 / 1 forces it off / on for A/B runs)
@@ -694,12 +781,13 @@ cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map
     TMAE_CARVEOUT_ONCE((attention_tc_kernel<0, 2>));
     if (lite) {
         const int grid = p.n_items < 2 * sms ? p.n_items : 2 * sms;
-        return launch_k(attention_tc_kernel<3, 1>, dim3(grid), dim3(192), smem, st, true, *map_q, *map_kv, out, p);
+        return launch_k(attention_tc_kernel<3, 1>, dim3(grid), dim3(192), smem, st, true, *map_q, *map_kv, qkv, out, p);
     }
     const int grid = p.n_items < sms ? p.n_items : sms;
-    if (p.Tp <= 96) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
-    if (p.Tp <= 128) return launch_k(attention_tc_kernel<4, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
-    return launch_k(attention_tc_kernel<0, 2>, dim3(grid), dim3(kAttnTcThreads), smem, st, true, *map_q, *map_kv, out, p);
+    const dim3 blk(kAttnTcThreads + 32);          // + the tail warp
+    if (p.Tp <= 96) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
+    if (p.Tp <= 128) return launch_k(attention_tc_kernel<4, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
+    return launch_k(attention_tc_kernel<0, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
 }
 
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,

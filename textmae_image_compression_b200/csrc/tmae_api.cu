@@ -83,8 +83,8 @@ struct Plan {
     bool from_latent_ok = true;
     cudaGraphExec_t graph = nullptr; // whole forward (steps + output copies), pointers via the device IoBlock
     int calls = 0;                   // the first call runs plain launches (one-time function attributes), then capture
-    bool attn_tc = false;           // tcgen05 attention: tensor maps of Q / K / V tiles over this plan's qkv matrix
-    CUtensorMap attn_q, attn_k, attn_v;
+    bool attn_tc = false;           // tcgen05 attention: tensor maps of the Q and K / V tiles over this plan's qkv matrix
+    CUtensorMap attn_q, attn_k;
     int first_rate_step = 0;        // index of the first step of the rate half (h_a)
     int encoder_end_step = 0;       // one past the final LayerNorm
 };
@@ -1204,7 +1204,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 if (h->precise_enc)
                     CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else if (pl.attn_tc)
-                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st, nullptr,
+                    CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st, nullptr,
                                                     (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0));
                 else
                     CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
@@ -1900,7 +1900,8 @@ int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int imp
         long long* dbg = nullptr;
         const bool timing = getenv("TMAE_ATTN_TIMING") != nullptr;      // bring-up aid: per-phase clock64 stamps of CTA 0
         if (timing) { cudaMalloc(reinterpret_cast<void**>(&dbg), 64 * 16 * 8); cudaMemset(dbg, 0, 64 * 16 * 8); }
-        e = launch_attention_tc(&mq, &mk, reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st, dbg, impl == 2);
+        e = launch_attention_tc(&mq, &mk, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st,
+                                dbg, impl == 2);
         if (timing) {
             cudaStreamSynchronize(st);
             std::vector<long long> hd(64 * 16);
