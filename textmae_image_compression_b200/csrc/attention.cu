@@ -342,6 +342,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     auto bar_oready = [&](int b) { return bar0 + 8u * (uint32_t)(10 + b); };
     auto bar_ofree = [&](int b) { return bar0 + 8u * (uint32_t)(12 + b); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    float* tail_p = reinterpret_cast<float*>(bars + 16);       // [<= 384] scores / probabilities of the tail warp's query row
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < 3; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[3 + s], kTailWarp ? 2 : 1); }   // empty: MMA commit (+ tail warp)
@@ -452,54 +453,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                             q[c * 8 + 2 * e + 1] = __uint_as_float(w4[e] & 0xffff0000u);
                         }
                     }
-                    float sc[12];                                   // Tp <= 384: at most 12 rounds of 32 keys
+                    // rolled loops (the scores live in shared memory, not in a register array): this warp's code must stay
+                    // small - a fully unrolled version thrashed the instruction cache and cost more than the tile it saved
                     float mx = -INFINITY;
+                    for (int j = lane; j < p.T; j += 32) {
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // four independent chains: the dot product is latency-bound
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) {
-                        sc[i] = -INFINITY;
-                        const int j = i * 32 + lane;
-                        if (i * 32 < p.T && j < p.T) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 kv = lds128(kb + (uint32_t)j * 128u + ((((uint32_t)c) ^ ((uint32_t)j & 7u)) << 4));
-                                const uint32_t w4[4] = {__float_as_uint(kv.x), __float_as_uint(kv.y), __float_as_uint(kv.z), __float_as_uint(kv.w)};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    acc = fmaf(q[c * 8 + 2 * e], __uint_as_float(w4[e] << 16), acc);
-                                    acc = fmaf(q[c * 8 + 2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), acc);
-                                }
-                            }
-                            sc[i] = acc * p.scale_log2e;
-                            mx = fmaxf(mx, sc[i]);
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 kv = lds128(kb + (uint32_t)j * 128u + ((((uint32_t)c) ^ ((uint32_t)j & 7u)) << 4));
+                            const uint32_t w4[4] = {__float_as_uint(kv.x), __float_as_uint(kv.y), __float_as_uint(kv.z), __float_as_uint(kv.w)};
+                            a0 = fmaf(q[c * 8 + 0], __uint_as_float(w4[0] << 16), a0);
+                            a1 = fmaf(q[c * 8 + 1], __uint_as_float(w4[0] & 0xffff0000u), a1);
+                            a2 = fmaf(q[c * 8 + 2], __uint_as_float(w4[1] << 16), a2);
+                            a3 = fmaf(q[c * 8 + 3], __uint_as_float(w4[1] & 0xffff0000u), a3);
+                            a0 = fmaf(q[c * 8 + 4], __uint_as_float(w4[2] << 16), a0);
+                            a1 = fmaf(q[c * 8 + 5], __uint_as_float(w4[2] & 0xffff0000u), a1);
+                            a2 = fmaf(q[c * 8 + 6], __uint_as_float(w4[3] << 16), a2);
+                            a3 = fmaf(q[c * 8 + 7], __uint_as_float(w4[3] & 0xffff0000u), a3);
                         }
+                        const float sv = ((a0 + a1) + (a2 + a3)) * p.scale_log2e;
+                        tail_p[j] = sv;
+                        mx = fmaxf(mx, sv);
                     }
                     mx = warp_max(mx);
                     float sum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) {
+                    const int t8 = (p.T + 7) & ~7;
+                    for (int j = lane; j < t8; j += 32) {
                         // P is rounded to bf16 before the second product, like the tensor-core path does
-                        const float pe = (sc[i] == -INFINITY) ? 0.f : ex2_approx(sc[i] - mx);
+                        const float pe = j < p.T ? ex2_approx(tail_p[j] - mx) : 0.f;
                         sum += pe;
-                        sc[i] = __bfloat162float(__float2bfloat16(pe));
+                        tail_p[j] = __bfloat162float(__float2bfloat16(pe));
                     }
                     sum = warp_sum(sum);
-                    float o0 = 0.f, o1 = 0.f;
+                    __syncwarp();
+                    // p v: lanes = dim pairs, eight keys per step (rows up to the next multiple of 8 exist in the tile, their p is 0)
+                    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+                    const uint32_t vlane = (((uint32_t)lane & 3u) * 4u);
+                    for (int j0 = 0; j0 < t8; j0 += 8) {
+                        uint32_t vw[8];
+                        float pj[8];
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) {
-                        if (i * 32 < p.T) {
-                            const int jn = min(32, p.T - i * 32);
-                            for (int jj = 0; jj < jn; ++jj) {
-                                const float pj = __shfl_sync(0xffffffffu, sc[i], jj);
-                                const int j = i * 32 + jj;
-                                uint32_t vw;
-                                asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(vw)
-                                             : "r"(vb + (uint32_t)j * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)j & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u));
-                                o0 = fmaf(pj, __uint_as_float(vw << 16), o0);
-                                o1 = fmaf(pj, __uint_as_float(vw & 0xffff0000u), o1);
-                            }
+                        for (int u = 0; u < 8; ++u) {
+                            const uint32_t jj = (uint32_t)(j0 + u);
+                            asm volatile("ld.shared.b32 %0, [%1];\n" : "=r"(vw[u])
+                                         : "r"(vb + jj * 128u + ((((uint32_t)lane >> 2) ^ (jj & 7u)) << 4) + vlane));
+                            pj[u] = tail_p[j0 + u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u += 2) {
+                            o0 = fmaf(pj[u], __uint_as_float(vw[u] << 16), o0);
+                            o1 = fmaf(pj[u], __uint_as_float(vw[u] & 0xffff0000u), o1);
+                            o2 = fmaf(pj[u + 1], __uint_as_float(vw[u + 1] << 16), o2);
+                            o3 = fmaf(pj[u + 1], __uint_as_float(vw[u + 1] & 0xffff0000u), o3);
                         }
                     }
+                    o0 += o2; o1 += o3;
+                    __syncwarp();                                     // tail_p is rewritten by the next tail row
                     const float inv = 1.f / sum;
                     *reinterpret_cast<uint32_t*>(out + (size_t)(n * p.T + t) * p.C + (size_t)h * HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
                 }
@@ -694,7 +703,7 @@ inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* 
     p.qreg = ((uint32_t)p.qrows * 128u + 1023u) & ~1023u;
     p.kreg = ((uint32_t)Tp * 128u + 1023u) & ~1023u;
     const uint32_t sp = ((uint32_t)Tp + 31u) & ~31u;
-    const size_t limit = 227 * 1024 - 256;
+    const size_t limit = 227 * 1024 - 2048;                   // barriers, TMEM slot, tail-row scratch
     const size_t stage = p.qreg + 2 * (size_t)p.kreg, pb = (size_t)p.atoms * 16384;
     p.nbuf = (2 * sp + 128 <= 512 && 2 * stage + 2 * pb <= limit) ? 2 : 1;
     if (lite) p.nbuf = 1;
@@ -709,7 +718,7 @@ inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* 
     if (need > 512) return false;
     p.scale_log2e = scale * 1.4426950408889634f;
     *out = p;
-    *smem = (size_t)p.nst * stage + (size_t)p.nbuf * pb + 256;
+    *smem = (size_t)p.nst * stage + (size_t)p.nbuf * pb + 2048;
     return true;
 }
 
