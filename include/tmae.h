@@ -225,7 +225,8 @@ TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias
 
 /* Fused softmax attention of the encoder blocks stand-alone (timm Attention.forward, MCM.py:313-322): qkv bf16 [N*T, 3*H*64]
  * with columns [3][H][64] -> out bf16 [N*T, H*64].  impl 0 = mma.sync kernel, 1 = tcgen05 / TMEM kernel (T <= 384), 2 = its
- * multi-stream form (one softmax group per CTA, two CTAs per SM; T <= 96, else the same as 1). */
+ * multi-stream form (one softmax group per CTA, two CTAs per SM; T <= 96, else the same as 1), 3 = two heads per tile
+ * (T = 65 and H even, else the same as 1; measured slower, kept as an experiment). */
 TMAE_API int  tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int impl, void* stream);
 /* C = resid + A B^T + bias (fp32 residual in, fp32 out; the proj / fc2 store phase).  pair = 1: the CTA-pair kernel
  * (tcgen05.mma.cta_group::2, 256-row tiles over two SMs; needs block_n % 32 == 0), 0: the one-CTA kernel. */

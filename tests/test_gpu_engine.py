@@ -134,8 +134,8 @@ def test_conv3x3_pair_matches_single_cta(cuda_dev, N, s, Cin, Cout, gelu):
 
 @pytest.mark.parametrize("N,T,H", [(1, 17, 2), (3, 65, 2), (64, 65, 12), (2, 145, 12), (5, 129, 3), (1, 192, 1), (4, 128, 4),
                                    (64, 145, 12), (3, 257, 16), (2, 193, 2), (2, 325, 3), (1, 384, 2), (7, 1, 1),
-                                   (2, 130, 2), (2, 264, 3), (1, 136, 1), (32, 257, 16), (2, 137, 2)])
-@pytest.mark.parametrize("impl", [0, 1, 2], ids=["mma_sync", "tcgen05", "tcgen05_lite"])
+                                   (2, 130, 2), (2, 264, 3), (1, 136, 1), (32, 257, 16), (2, 137, 2), (5, 65, 3), (9, 65, 4)])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3], ids=["mma_sync", "tcgen05", "tcgen05_lite", "tcgen05_duo"])
 def test_attention_matches_torch(cuda_dev, N, T, H, impl):
     """Both attention kernels against fp32 softmax(q k^T / sqrt(64)) v of the same bf16 q, k, v (P is rounded to bf16 before
     the second product in both kernels)."""

@@ -290,6 +290,8 @@ constexpr int kAttnTcMaxStages = 3;
 struct AttnTcParams {
     int T, Tp, H, C;
     int n_items, q_tiles;
+    int duo;                  // 1: two heads per 128-row tile (T - 1 = 64 patch queries each), S = [128 x 2 Tp]; cls queries on the tail warp
+    int Tpt;                  // key columns of the S tile: Tp, or 2 Tp in duo mode
     int tail_rows;            // query rows past the last full 128-row tile (T = 257: the 257th) computed by the tail warp on CUDA cores
     int nbuf;                 // 2: double-buffered S / O / P and both softmax groups; 1: single (Tp > 192)
     int nst;                  // Q/K/V stages
@@ -365,12 +367,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int k = 0; k < n_my; ++k) {
                 const int item = (int)blockIdx.x + k * (int)gridDim.x;
                 const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-                const int h = nh % p.H, n = nh / p.H;
+                const int hgroups = p.duo ? p.H >> 1 : p.H;
+                const int h = (nh % hgroups) << p.duo, n = nh / hgroups;
                 const int st = k % p.nst;
                 mbar_wait_a(bar_empty(st), (((uint32_t)(k / p.nst)) & 1u) ^ 1u);
                 const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
-                mbar_arrive_expect_tx_a(bar_full(st), (uint32_t)p.qrows * 128u + 2u * kbytes);
                 const int row0 = n * p.T;
+                if (p.duo) {
+                    // two heads: patch queries 1..T-1 of head h in tile rows 0..63, of head h+1 in rows 64..127; the keys / values
+                    // of the two heads one after the other (Tp rows each)
+                    mbar_arrive_expect_tx_a(bar_full(st), 2u * (uint32_t)p.qrows * 128u + 4u * kbytes);
+                    for (int sidx = 0; sidx < 2; ++sidx) {
+                        tma_load_2d_a(base + (uint32_t)sidx * 8192u, &map_q, bar_full(st), (h + sidx) * HD, row0 + 1);
+                        tma_load_2d_a(base + p.qreg + (uint32_t)sidx * kbytes, &map_kv, bar_full(st), p.C + (h + sidx) * HD, row0);
+                        tma_load_2d_a(base + p.qreg + p.kreg + (uint32_t)sidx * kbytes, &map_kv, bar_full(st), 2 * p.C + (h + sidx) * HD, row0);
+                    }
+                    continue;
+                }
+                mbar_arrive_expect_tx_a(bar_full(st), (uint32_t)p.qrows * 128u + 2u * kbytes);
                 tma_load_2d_a(base, &map_q, bar_full(st), h * HD, row0 + qt * 128);
                 for (int l = 0; l < p.kloads; ++l) {
                     tma_load_2d_a(base + p.qreg + (uint32_t)(l * p.krows) * 128u, &map_kv, bar_full(st), p.C + h * HD, row0 + l * p.krows);
@@ -389,8 +403,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 if (p.dbg && blockIdx.x == 0) p.dbg[k * 16 + 0] = clock64();
                 const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
                 const uint64_t dq = umma_smem_desc_sw128(base);
-                for (int n0 = 0; n0 < p.Tp; n0 += 256) {
-                    const int nn = min(256, p.Tp - n0);
+                for (int n0 = 0; n0 < p.Tpt; n0 += 256) {
+                    const int nn = min(256, p.Tpt - n0);
                     const uint32_t idesc = umma_idesc_bf16_f32(128, nn);
                     const uint64_t dk = umma_smem_desc_sw128(base + p.qreg + (uint32_t)n0 * 128u);
 #pragma unroll
@@ -415,7 +429,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
                 const uint64_t dp = umma_smem_desc_sw128(p_base + (uint32_t)b * p_bytes);
                 const uint64_t dv = umma_smem_desc_mn_sw128(base + p.qreg + p.kreg);
-                const int ksteps = p.Tp >> 4;
+                const int ksteps = p.Tpt >> 4;
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint64_t a_desc = dp + (uint64_t)((uint32_t)(ks >> 2) * (16384u >> 4)) + (uint64_t)(2 * (ks & 3));
                     const uint64_t b_desc = dv + (uint64_t)((uint32_t)ks * (2048u >> 4));
@@ -434,13 +448,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int k = 0; k < n_my; ++k) {
             const int item = (int)blockIdx.x + k * (int)gridDim.x;
             const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-            const int h = nh % p.H, n = nh / p.H;
+            const int hgroups = p.duo ? p.H >> 1 : p.H;
+            const int h0 = (nh % hgroups) << p.duo, n = nh / hgroups;
             const int st = k % p.nst;
             mbar_wait_a(bar_full(st), ((uint32_t)(k / p.nst)) & 1u);
             if (p.tail_rows > 0 && qt == p.q_tiles - 1) {
-                const uint32_t kb = smem0 + (uint32_t)st * stage_bytes + p.qreg, vb = kb + p.kreg;
                 for (int tr = 0; tr < p.tail_rows; ++tr) {
-                    const int t = p.q_tiles * 128 + tr;
+                    // duo: tail row tr = the cls query (token 0) of head h0 + tr, against that head's keys; else token 128 q + tr
+                    const int h = p.duo ? h0 + tr : h0;
+                    const int t = p.duo ? 0 : p.q_tiles * 128 + tr;
+                    const uint32_t kb = smem0 + (uint32_t)st * stage_bytes + p.qreg + (p.duo ? (uint32_t)tr * kbytes : 0u), vb = kb + p.kreg;
                     const uint4* qg = reinterpret_cast<const uint4*>(qkv + (size_t)(n * p.T + t) * 3 * p.C + (size_t)h * HD);
                     float q[HD];
 #pragma unroll
@@ -525,11 +542,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int k = g; k < n_my; k += p.nbuf) {
                 const int item = (int)blockIdx.x + k * (int)gridDim.x;
                 const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-                const int h = nh % p.H, n = nh / p.H;
+                const int hgroups = p.duo ? p.H >> 1 : p.H;
+                const int sub = p.duo ? quad >> 1 : 0;                  // duo: tile rows 0..63 = head h, 64..127 = head h + 1
+                const int h = ((nh % hgroups) << p.duo) + sub, n = nh / hgroups;
                 const int b = k % p.nbuf;
                 const uint32_t use = (uint32_t)(k / p.nbuf);
-                const int q0 = qt * 128;
+                const int q0 = p.duo ? 1 - sub * 64 : qt * 128;         // token of tile row r = q0 + r
                 const bool valid = q0 + row < p.T;
+                const int lo = sub * p.Tp, hi = lo + p.T;               // this row's keys are S columns [lo, hi) (warp-uniform)
                 const uint32_t s_addr = tmem + lane_off + (uint32_t)b * p.s_stride;
                 const bool stamp = p.dbg && blockIdx.x == 0 && row == 0;
                 if (stamp) p.dbg[k * 16 + 4] = clock64();
@@ -542,7 +562,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 // 32 S values at key columns [c0, c0 + 32): running maximum / exp2, row sum, bf16 P into the swizzled A tile.
                 // Columns are masked only in the 8-column group that straddles T; groups past T are written as zeros.
                 auto chunk_max = [&](const uint32_t (&sv)[32], int c0) {
-                    if (c0 + 32 <= p.T) {
+                    if (c0 >= lo && c0 + 32 <= hi) {
                         float m0 = __uint_as_float(sv[0]), m1 = __uint_as_float(sv[1]), m2 = __uint_as_float(sv[2]), m3 = __uint_as_float(sv[3]);
 #pragma unroll
                         for (int i = 4; i < 32; i += 4) {
@@ -553,39 +573,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     } else {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            if (c0 + q * 8 < p.T) {
+                            const int cq = c0 + q * 8;
+                            if (cq + 8 > lo && cq < hi) {
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) if (c0 + q * 8 + i < p.T) mx = fmaxf(mx, __uint_as_float(sv[q * 8 + i]));
+                                for (int i = 0; i < 8; ++i) if (cq + i >= lo && cq + i < hi) mx = fmaxf(mx, __uint_as_float(sv[q * 8 + i]));
                             }
                         }
                     }
                 };
                 auto chunk_exp = [&](const uint32_t (&sv)[32], int c0, float mxs) {
-                    const uint32_t abase = prow + (uint32_t)(c0 >> 6) * 16384u;
-                    const uint32_t ch = (uint32_t)(c0 & 63) >> 3;
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t pk[4] = {0u, 0u, 0u, 0u};
                         const int cq = c0 + q * 8;
-                        if (cq + 8 <= p.T) {
+                        if (cq >= lo && cq + 8 <= hi) {
                             float e[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) e[i] = ex2_approx(fmaf(__uint_as_float(sv[q * 8 + i]), p.scale_log2e, -mxs));
                             s0 += e[0] + e[4]; s1 += e[1] + e[5]; s2 += e[2] + e[6]; s3 += e[3] + e[7];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) pk[i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
-                        } else if (cq < p.T) {
+                        } else if (cq + 8 > lo && cq < hi) {
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int c = cq + 2 * i;
-                                const float p0 = (c < p.T) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i]), p.scale_log2e, -mxs)) : 0.f;
-                                const float p1 = (c + 1 < p.T) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i + 1]), p.scale_log2e, -mxs)) : 0.f;
+                                const float p0 = (c >= lo && c < hi) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i]), p.scale_log2e, -mxs)) : 0.f;
+                                const float p1 = (c + 1 >= lo && c + 1 < hi) ? ex2_approx(fmaf(__uint_as_float(sv[q * 8 + 2 * i + 1]), p.scale_log2e, -mxs)) : 0.f;
                                 s0 += p0 + p1;
                                 pk[i] = pack_bf16x2(p0, p1);
                             }
                         }
-                        if (cq < p.Tp) sts128(abase + (((ch + (uint32_t)q) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        // 8-key group cq of the P tile: 64-key atom cq / 64, 16-byte chunk (cq % 64) / 8 (c0 need not be 64-aligned)
+                        if (cq < p.Tpt)
+                            sts128(prow + (uint32_t)(cq >> 6) * 16384u + (((((uint32_t)cq & 63u) >> 3) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
                     }
                     sum += (s0 + s1) + (s2 + s3);
                 };
@@ -593,15 +614,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     // the whole S row in registers: one round of TMEM loads, one wait
                     uint32_t sv[NCH][32];
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(s_addr + (uint32_t)(32 * c), sv[c]);
+                    for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(s_addr + (uint32_t)(lo + 32 * c), sv[c]);   // this row's own keys
                     tmem_ld_wait();
                     if (stamp) p.dbg[k * 16 + 6] = clock64();
                     if (valid) {
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_max(sv[c], 32 * c);
+                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_max(sv[c], lo + 32 * c);
                         const float mxs = mx * p.scale_log2e;
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_exp(sv[c], 32 * c, mxs);
+                        for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_exp(sv[c], lo + 32 * c, mxs);
+                        if (p.duo) {                                  // block-diagonal P: zeros against the other head's keys
+                            const int olo = p.Tp - lo;
+                            for (int cq = olo; cq < olo + p.Tp; cq += 8)
+                                sts128(prow + (uint32_t)(cq >> 6) * 16384u + (((((uint32_t)cq & 63u) >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
+                        }
                     }
                 } else {
                     // long rows: two passes over tensor memory, the load of the next 32 columns in flight while this one is used
@@ -610,8 +636,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                     for (int pass = 0; pass < 2; ++pass) {
                         tmem_ld_32x32b_x32(s_addr, sa);
                         tmem_ld_wait();
-                        for (int c0 = 0; c0 < p.Tp; c0 += 64) {
-                            const bool has_b = c0 + 32 < p.Tp, has_a2 = c0 + 64 < p.Tp;
+                        for (int c0 = 0; c0 < p.Tpt; c0 += 64) {
+                            const bool has_b = c0 + 32 < p.Tpt, has_a2 = c0 + 64 < p.Tpt;
                             if (has_b) tmem_ld_32x32b_x32(s_addr + (uint32_t)(c0 + 32), sb);
                             if (valid) { if (pass == 0) chunk_max(sa, c0); else chunk_exp(sa, c0, mxs); }
                             tmem_ld_wait();
@@ -663,7 +689,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                 __syncwarp();
                 {
                     const int rows_left = p.T - q0 - quad * 32;                    // valid rows of this warp's 32
-                    __nv_bfloat16* wdst = out + ((size_t)(n * p.T + q0 + quad * 32)) * p.C + (size_t)h * HD;
+                    __nv_bfloat16* wdst = out + ((size_t)(n * p.T) + (size_t)(q0 + quad * 32)) * p.C + (size_t)h * HD;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int r = 4 * i + (lane >> 3);
@@ -686,11 +712,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 }
 
 // shared-memory / tensor-memory plan of the tcgen05 kernel for T tokens; returns false when it does not fit
-inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* out, size_t* smem, bool lite = false) {
+inline bool attn_tc_plan(int T, int H, int C, int N, float scale, AttnTcParams* out, size_t* smem, bool lite = false, bool duo = false) {
     AttnTcParams p = {};
     const int Tp = attn_tp(T);
     if (Tp > kAttnTcMaxTp) return false;
     p.T = T; p.Tp = Tp; p.H = H; p.C = C;
+    if (duo) {
+        // two heads per tile: T - 1 = 64 patch queries per head (the K = 64 configuration), cls queries on the tail warp
+        if (T != 65 || (H & 1) != 0 || lite) return false;
+        p.duo = 1; p.Tpt = 2 * Tp;
+        p.q_tiles = 1; p.tail_rows = 2;
+        p.n_items = N * (H / 2);
+        p.qrows = 64; p.kloads = 1; p.krows = Tp;
+        p.atoms = (p.Tpt + 63) / 64;
+        p.qreg = 16384;
+        p.kreg = ((uint32_t)p.Tpt * 128u + 1023u) & ~1023u;
+        const uint32_t sp2 = ((uint32_t)p.Tpt + 31u) & ~31u;
+        const size_t stage2 = p.qreg + 2 * (size_t)p.kreg, pb2 = (size_t)p.atoms * 16384;
+        p.nbuf = 2; p.nst = 2;
+        if (2 * sp2 + 128 > 512 || 2 * stage2 + 2 * pb2 > 227 * 1024 - 2048) return false;
+        p.s_stride = sp2; p.o_col0 = 2 * sp2; p.tmem_cols = 512;
+        p.scale_log2e = scale * 1.4426950408889634f;
+        *out = p;
+        *smem = 2 * stage2 + 2 * pb2 + 2048;
+        return true;
+    }
+    p.Tpt = Tp;
     p.q_tiles = (T + 127) / 128;
     p.tail_rows = 0;
     static const bool no_tail = getenv("TMAE_NO_ATTN_TAIL") != nullptr;
@@ -764,19 +811,33 @@ bool attention_tc_eligible(int T) {
     return !off && attention_tc_supported(T);
 }
 int attention_tc_tp(int T) { return attn_tp(T); }
-void attention_tc_boxes(int T, int* q_rows, int* kv_rows) {
+// Which form of the kernel serves (T, H): lite (one softmax group, two CTAs per SM) for short rows while several streams
+// share the GPU, else the full form; TMAE_ATTN_LITE=1 / 0 forces lite on / off (A/B runs).
+// duo (two heads per 128-row tile at T = 65, cls queries on the tail warp) is OPT-IN (mode 3 / TMAE_ATTN_DUO=1): measured
+// slower than the plain form on B200 (0.285 vs 0.227 ms for the 12 launches of the B-64 forward) - the softmax is
+// issue-bound, so filling all four TMEM lane quarters doubles the per-item softmax time while the items halve, and the
+// 56 KB stages leave a 2-deep pipeline.
+static void attn_mode(int T, int H, int mode, bool* lite, bool* duo) {
+    static const char* lite_env = getenv("TMAE_ATTN_LITE");
+    static const bool duo_env = getenv("TMAE_ATTN_DUO") != nullptr;
+    const bool share_sm = mode == 2;
+    *duo = (mode == 3 || duo_env) && T == 65 && (H & 1) == 0;
+    *lite = !*duo && attn_tp(T) <= 96 && (lite_env ? lite_env[0] == '1' : share_sm);
+}
+void attention_tc_boxes(int T, int H, int mode, int* q_rows, int* kv_rows) {
     AttnTcParams p = {}; size_t smem = 0;
-    attn_tc_plan(T, 1, HD, 1, 0.125f, &p, &smem);
+    bool lite, duo;
+    attn_mode(T, H, mode, &lite, &duo);
+    attn_tc_plan(T, H, H * HD, 1, 0.125f, &p, &smem, lite, duo);
     *q_rows = p.qrows; *kv_rows = p.krows;
 }
 cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int N,
-                                int T, int H, int C, float scale, cudaStream_t st, long long* dbg, bool share_sm) {
+                                int T, int H, int C, float scale, cudaStream_t st, long long* dbg, int mode) {
     if (C != H * HD) return cudaErrorInvalidValue;
     AttnTcParams p; size_t smem;
-    // lite form: short rows while several streams share the GPU (TMAE_ATTN_LITE=0 / 1 forces it off / on for A/B runs)
-    static const char* lite_env = getenv("TMAE_ATTN_LITE");
-    const bool lite = attn_tp(T) <= 96 && (lite_env ? lite_env[0] == '1' : share_sm);
-    if (!attn_tc_plan(T, H, C, N, scale, &p, &smem, lite)) return cudaErrorInvalidValue;
+    bool lite, duo;
+    attn_mode(T, H, mode, &lite, &duo);
+    if (!attn_tc_plan(T, H, C, N, scale, &p, &smem, lite, duo)) return cudaErrorInvalidValue;
     p.dbg = dbg;
     static int sms = 0;
     if (sms == 0) {
@@ -794,6 +855,7 @@ cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map
     }
     const int grid = p.n_items < sms ? p.n_items : sms;
     const dim3 blk(kAttnTcThreads + 32);          // + the tail warp
+    if (p.duo) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
     if (p.Tp <= 96) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
     if (p.Tp <= 128) return launch_k(attention_tc_kernel<4, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
     return launch_k(attention_tc_kernel<0, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);

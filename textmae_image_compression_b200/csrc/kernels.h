@@ -39,9 +39,10 @@ cudaError_t launch_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int N
 bool attention_tc_supported(int T);   // kernel limits (Tp <= 384: shared memory and the 512 TMEM columns)
 bool attention_tc_eligible(int T);    // policy: the tcgen05 kernel whenever it is supported (TMAE_NO_TC_ATTN=1 -> mma.sync kernel)
 int attention_tc_tp(int T);
-void attention_tc_boxes(int T, int* q_rows, int* kv_rows);   // TMA box rows of the Q map and of the K / V map
+// mode: 1 = full form, 2 = several streams share the GPU (lite form for short rows), 3 = duo (two heads per tile, T = 65; opt-in)
+void attention_tc_boxes(int T, int H, int mode, int* q_rows, int* kv_rows);   // TMA box rows of the Q map and of the K / V map
 cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int N,
-                                int T, int H, int C, float scale, cudaStream_t st, long long* dbg = nullptr, bool share_sm = false);
+                                int T, int H, int C, float scale, cudaStream_t st, long long* dbg = nullptr, int mode = 1);
 // precise mode: fp32 softmax attention on CUDA cores over split-bf16 (hi + lo plane) q, k, v; writes both planes
 cudaError_t launch_attention_f32(const __nv_bfloat16* qkv, long long qkv_lo, __nv_bfloat16* out, long long out_lo, int N,
                                  int T, int H, int C, float scale, cudaStream_t st);

@@ -798,9 +798,9 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
 }
 
 // Tensor maps of the tcgen05 attention kernel: Q and K / V tiles of one (image, head) are 64-column boxes of qkv [rows, 3C]
-int make_attention_maps(tmae_handle* h, const __nv_bfloat16* qkv, long long rows, int C, int T, CUtensorMap* mq, CUtensorMap* mkv) {
+int make_attention_maps(tmae_handle* h, const __nv_bfloat16* qkv, long long rows, int C, int T, int mode, CUtensorMap* mq, CUtensorMap* mkv) {
     int q_rows = 0, kv_rows = 0;
-    attention_tc_boxes(T, &q_rows, &kv_rows);
+    attention_tc_boxes(T, C / 64, mode, &q_rows, &kv_rows);
     cuuint64_t gdim[2] = {(cuuint64_t)(3 * C), (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)(3 * C) * 2};
     cuuint32_t estr[2] = {1, 1};
@@ -851,7 +851,7 @@ int build_plan(tmae_handle* h, int N, Plan** out, bool forced = false) {
     auto simple = [&](StepKind k, int fam, const char* t) { Step st; st.kind = k; st.family = fam; st.tag = t; pl.steps.push_back(st); };
 
     if (!h->precise_enc && !(h->cfg.flags & TMAE_FLAG_DEBUG_SIMT) && attention_tc_eligible(T)) {
-        if ((rc = make_attention_maps(h, w.qkv.p, rt, C, T, &pl.attn_q, &pl.attn_k))) return rc;
+        if ((rc = make_attention_maps(h, w.qkv.p, rt, C, T, (h->cfg.flags & TMAE_FLAG_SHARE_SM) ? 2 : 1, &pl.attn_q, &pl.attn_k))) return rc;
         pl.attn_tc = true;
     }
     simple(ST_ZERO_RATE, FAM_MISC, "zero_rate");
@@ -1205,7 +1205,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                     CUDA_TRY(h, launch_attention_f32(w.qkv.p, w.qkv.lo, w.attn.p, w.attn.lo, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 else if (pl.attn_tc)
                     CUDA_TRY(h, launch_attention_tc(&pl.attn_q, &pl.attn_k, w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st, nullptr,
-                                                    (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0));
+                                                    (h->cfg.flags & TMAE_FLAG_SHARE_SM) ? 2 : 1));
                 else
                     CUDA_TRY(h, launch_attention(w.qkv.p, w.attn.p, N, T, h->H, C, 1.0f / sqrtf((float)h->hd), st));
                 break;
@@ -1891,17 +1891,17 @@ int tmae_attention_bf16(const void* qkv, void* out, int N, int T, int H, int imp
     const int C = H * 64;
     cudaError_t e = attention_configure(T);
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "attention configure: %s", cudaGetErrorString(e));
-    if (impl == 1 || impl == 2) {          // 2 = the multi-stream ("lite") form of the tcgen05 kernel for short rows
+    if (impl >= 1 && impl <= 3) {          // 2 = the multi-stream ("lite") form of the tcgen05 kernel for short rows, 3 = duo (T = 65)
         if (!attention_tc_supported(T)) return fail(nullptr, TMAE_EINVAL, "tcgen05 attention needs T <= 384");
         CUtensorMap mq, mk;
-        if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, &mq, &mk))) {
+        if ((rc = make_attention_maps(tmp.get(), reinterpret_cast<const __nv_bfloat16*>(qkv), (long long)N * T, C, T, impl, &mq, &mk))) {
             g_create_error = tmp->err; return rc;
         }
         long long* dbg = nullptr;
         const bool timing = getenv("TMAE_ATTN_TIMING") != nullptr;      // bring-up aid: per-phase clock64 stamps of CTA 0
         if (timing) { cudaMalloc(reinterpret_cast<void**>(&dbg), 64 * 16 * 8); cudaMemset(dbg, 0, 64 * 16 * 8); }
         e = launch_attention_tc(&mq, &mk, reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), N, T, H, C, 0.125f, st,
-                                dbg, impl == 2);
+                                dbg, impl);
         if (timing) {
             cudaStreamSynchronize(st);
             std::vector<long long> hd(64 * 16);
