@@ -323,7 +323,8 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr) 
 // WGS = softmax groups per CTA.  2: one 320-thread CTA per SM with double-buffered S / O / P (or 1 buffer for long rows).
 // 1 ("lite", Tp <= 96): 192 threads, one buffer, two pipeline stages, 256 TMEM columns, <= 93 KB shared memory - two such CTAs
 // share an SM, or one of them shares it with a GEMM CTA of another stream (multi-stream mode, TMAE_FLAG_SHARE_SM).
-template <int NCH, int WGS>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
+// DUO = the two-heads-per-tile experiment (compile-time, so the plain forms carry none of its address arithmetic).
+template <int NCH, int WGS, bool DUO = false>      // S row held in NCH x 32 registers (Tp <= 32 NCH); 0 = streamed from tensor memory in two passes
 __global__ void __launch_bounds__(64 + 128 * WGS + (WGS == 2 ? 32 : 0), WGS == 1 ? 2 : 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                     const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, const AttnTcParams p) {
@@ -367,13 +368,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int k = 0; k < n_my; ++k) {
                 const int item = (int)blockIdx.x + k * (int)gridDim.x;
                 const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-                const int hgroups = p.duo ? p.H >> 1 : p.H;
-                const int h = (nh % hgroups) << p.duo, n = nh / hgroups;
+                const int hgroups = DUO ? p.H >> 1 : p.H;
+                const int h = (nh % hgroups) << (DUO ? 1 : 0), n = nh / hgroups;
                 const int st = k % p.nst;
                 mbar_wait_a(bar_empty(st), (((uint32_t)(k / p.nst)) & 1u) ^ 1u);
                 const uint32_t base = smem0 + (uint32_t)st * stage_bytes;
                 const int row0 = n * p.T;
-                if (p.duo) {
+                if (DUO) {
                     // two heads: patch queries 1..T-1 of head h in tile rows 0..63, of head h+1 in rows 64..127; the keys / values
                     // of the two heads one after the other (Tp rows each)
                     mbar_arrive_expect_tx_a(bar_full(st), 2u * (uint32_t)p.qrows * 128u + 4u * kbytes);
@@ -448,16 +449,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         for (int k = 0; k < n_my; ++k) {
             const int item = (int)blockIdx.x + k * (int)gridDim.x;
             const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-            const int hgroups = p.duo ? p.H >> 1 : p.H;
-            const int h0 = (nh % hgroups) << p.duo, n = nh / hgroups;
+            const int hgroups = DUO ? p.H >> 1 : p.H;
+            const int h0 = (nh % hgroups) << (DUO ? 1 : 0), n = nh / hgroups;
             const int st = k % p.nst;
             mbar_wait_a(bar_full(st), ((uint32_t)(k / p.nst)) & 1u);
             if (p.tail_rows > 0 && qt == p.q_tiles - 1) {
                 for (int tr = 0; tr < p.tail_rows; ++tr) {
                     // duo: tail row tr = the cls query (token 0) of head h0 + tr, against that head's keys; else token 128 q + tr
-                    const int h = p.duo ? h0 + tr : h0;
-                    const int t = p.duo ? 0 : p.q_tiles * 128 + tr;
-                    const uint32_t kb = smem0 + (uint32_t)st * stage_bytes + p.qreg + (p.duo ? (uint32_t)tr * kbytes : 0u), vb = kb + p.kreg;
+                    const int h = DUO ? h0 + tr : h0;
+                    const int t = DUO ? 0 : p.q_tiles * 128 + tr;
+                    const uint32_t kb = smem0 + (uint32_t)st * stage_bytes + p.qreg + (DUO ? (uint32_t)tr * kbytes : 0u), vb = kb + p.kreg;
                     const uint4* qg = reinterpret_cast<const uint4*>(qkv + (size_t)(n * p.T + t) * 3 * p.C + (size_t)h * HD);
                     float q[HD];
 #pragma unroll
@@ -542,14 +543,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
             for (int k = g; k < n_my; k += p.nbuf) {
                 const int item = (int)blockIdx.x + k * (int)gridDim.x;
                 const int qt = item % p.q_tiles, nh = item / p.q_tiles;
-                const int hgroups = p.duo ? p.H >> 1 : p.H;
-                const int sub = p.duo ? quad >> 1 : 0;                  // duo: tile rows 0..63 = head h, 64..127 = head h + 1
-                const int h = ((nh % hgroups) << p.duo) + sub, n = nh / hgroups;
+                const int hgroups = DUO ? p.H >> 1 : p.H;
+                const int sub = DUO ? quad >> 1 : 0;                  // duo: tile rows 0..63 = head h, 64..127 = head h + 1
+                const int h = ((nh % hgroups) << (DUO ? 1 : 0)) + sub, n = nh / hgroups;
                 const int b = k % p.nbuf;
                 const uint32_t use = (uint32_t)(k / p.nbuf);
-                const int q0 = p.duo ? 1 - sub * 64 : qt * 128;         // token of tile row r = q0 + r
+                const int q0 = DUO ? 1 - sub * 64 : qt * 128;         // token of tile row r = q0 + r
                 const bool valid = q0 + row < p.T;
-                const int lo = sub * p.Tp, hi = lo + p.T;               // this row's keys are S columns [lo, hi) (warp-uniform)
+                const int lo = DUO ? sub * p.Tp : 0, hi = lo + p.T;               // this row's keys are S columns [lo, hi) (warp-uniform)
                 const uint32_t s_addr = tmem + lane_off + (uint32_t)b * p.s_stride;
                 const bool stamp = p.dbg && blockIdx.x == 0 && row == 0;
                 if (stamp) p.dbg[k * 16 + 4] = clock64();
@@ -604,9 +605,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                                 pk[i] = pack_bf16x2(p0, p1);
                             }
                         }
-                        // 8-key group cq of the P tile: 64-key atom cq / 64, 16-byte chunk (cq % 64) / 8 (c0 need not be 64-aligned)
-                        if (cq < p.Tpt)
-                            sts128(prow + (uint32_t)(cq >> 6) * 16384u + (((((uint32_t)cq & 63u) >> 3) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                        if (cq < p.Tpt) {
+                            if constexpr (DUO)     // c0 is not 32-aligned: 64-key atom cq / 64, 16-byte chunk (cq % 64) / 8 per group
+                                sts128(prow + (uint32_t)(cq >> 6) * 16384u + (((((uint32_t)cq & 63u) >> 3) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                            else                   // c0 % 32 == 0: the four groups of a chunk stay inside one atom
+                                sts128(prow + (uint32_t)(c0 >> 6) * 16384u + ((((((uint32_t)c0 & 63u) >> 3) + (uint32_t)q) ^ rsw) << 4), pk[0], pk[1],
+                                       pk[2], pk[3]);
+                        }
                     }
                     sum += (s0 + s1) + (s2 + s3);
                 };
@@ -623,7 +628,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
                         const float mxs = mx * p.scale_log2e;
 #pragma unroll
                         for (int c = 0; c < NCH; ++c) if (32 * c < p.Tp) chunk_exp(sv[c], lo + 32 * c, mxs);
-                        if (p.duo) {                                  // block-diagonal P: zeros against the other head's keys
+                        if constexpr (DUO) {                          // block-diagonal P: zeros against the other head's keys
                             const int olo = p.Tp - lo;
                             for (int cq = olo; cq < olo + p.Tp; cq += 8)
                                 sts128(prow + (uint32_t)(cq >> 6) * 16384u + (((((uint32_t)cq & 63u) >> 3) ^ rsw) << 4), 0u, 0u, 0u, 0u);
@@ -855,7 +860,12 @@ cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map
     }
     const int grid = p.n_items < sms ? p.n_items : sms;
     const dim3 blk(kAttnTcThreads + 32);          // + the tail warp
-    if (p.duo) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
+    if (p.duo) {
+        TMAE_CARVEOUT_ONCE((attention_tc_kernel<3, 2, true>));
+        static const cudaError_t cfg = cudaFuncSetAttribute(attention_tc_kernel<3, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (cfg != cudaSuccess) return cfg;
+        return launch_k(attention_tc_kernel<3, 2, true>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
+    }
     if (p.Tp <= 96) return launch_k(attention_tc_kernel<3, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
     if (p.Tp <= 128) return launch_k(attention_tc_kernel<4, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
     return launch_k(attention_tc_kernel<0, 2>, dim3(grid), blk, smem, st, true, *map_q, *map_kv, qkv, out, p);
