@@ -218,6 +218,11 @@ TMAE_API int  tmae_huffman_decompress(const tmae_huffman* h, const uint8_t* h_bi
  * run on the tcgen05 kernel (impl 0) or the CUDA-core checker (impl 1). A, B bf16 row-major, C f32. */
 TMAE_API int  tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* C, int M, int N, int K,
                     int block_n, int impl, void* stream);
+/* C (bf16) = act(A B^T + bias), act = exact-erf GELU when gelu != 0: the bf16 store phases of the engine (QKV / fc1 style layers).
+ * variant 0 = one tile per CTA (the one-CTA persistent kernel above two tiles per SM), 1 = CTA pairs, 2 = persistent CTA pairs
+ * (double-buffered tensor memory, 74 clusters), 3 = CUDA-core checker. */
+TMAE_API int  tmae_gemm_bf16_out(const void* A, const void* B, const float* bias, void* C, int M, int N, int K, int block_n,
+                        int gelu, int variant, void* stream);
 /* 3x3 pad-1 stride-1 convolution on the engine: x bf16 [N, s, s, Cin] NHWC, w f32 [Cout, Cin, 3, 3] -> f32 NHWC.
  * impl 2 = the CTA-pair (cta_group::2) launch of the tcgen05 kernel. */
 TMAE_API int  tmae_conv3x3_bf16(const void* x, const float* w, const float* bias, float* out, int N, int s,

@@ -45,6 +45,17 @@ def attention(qkv_bf16, N, T, H, impl=0):
     return out
 
 
+def gemm_bf16_out(A_bf16, B_bf16, bias, block_n=0, gelu=False, variant=0):
+    """bf16 C = act(A @ B^T + bias): variant 0 one tile per CTA / one-CTA persistent, 1 CTA pairs, 2 persistent CTA pairs, 3 checker."""
+    M, K = A_bf16.shape
+    N = B_bf16.shape[0]
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=A_bf16.device)
+    rc = _native.load().tmae_gemm_bf16_out(ptr(A_bf16), ptr(B_bf16), ptr(bias), ptr(out), M, N, K, block_n, 1 if gelu else 0, variant, stream())
+    _native.check(rc, None, RuntimeError)
+    torch.cuda.synchronize()
+    return out
+
+
 def gemm_resid(A_bf16, B_bf16, bias, resid, block_n=0, pair=0, impl=0):
     """C = resid + A @ B^T + bias (proj / fc2 store phase); pair=1 -> CTA-pair (cta_group::2) kernel."""
     M, K = A_bf16.shape

@@ -147,3 +147,22 @@ def test_attention_matches_torch(cuda_dev, N, T, H, impl):
     err = G.rel_err(out, ref)
     assert err < 6e-3, f"impl={impl} rel err {err}"
     assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("M,N,K,bn,gelu", [(4160, 2304, 768, 192, False), (4160, 3072, 768, 256, True), (2100, 1536, 512, 128, True),
+                                           (9252, 1024, 1024, 256, False), (4160, 768, 256, 64, False), (300, 512, 128, 128, True)])
+def test_gemm_bf16_out_variants_agree(cuda_dev, M, N, K, bn, gelu):
+    """The bf16 store phases of the engine (QKV / fc1 style): one tile per CTA or one-CTA persistent (0), CTA pairs (1) and the
+    persistent CTA-pair kernel (2: double-buffered tensor memory, tiles round-robin over 74 clusters) run the same k order, so
+    they must agree bit for bit; all against the fp32 product of the same bf16 operands."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(cuda_dev).bfloat16()
+    B = (torch.randn(N, K, generator=g) * 0.05).to(cuda_dev).bfloat16()
+    bias = torch.randn(N, generator=g).to(cuda_dev)
+    ref = A.float() @ B.float().t() + bias
+    if gelu:
+        ref = F.gelu(ref)
+    outs = [G.gemm_bf16_out(A, B, bias, block_n=bn, gelu=gelu, variant=v) for v in (0, 1, 2)]
+    for o in outs:
+        assert G.rel_err(o.float(), ref) < 4e-3, G.rel_err(o.float(), ref)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])

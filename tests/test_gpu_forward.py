@@ -563,7 +563,7 @@ print(json.dumps(dict(ids=bool(torch.equal(out["ids_restore"].cpu(), ref["ids_re
 
 @pytest.mark.parametrize("switch", ["TMAE_NO_GRAPH", "TMAE_NO_PDL", "TMAE_NO_TMA_STORE", "TMAE_NO_CONV_REUSE",
                                     "TMAE_NO_WEIGHT_PREFETCH", "TMAE_TWO_PRODUCERS", "TMAE_KGROUP", "TMAE_NO_PAIR", "TMAE_NO_PAIR_CONV",
-                                    "TMAE_NO_LN_FOLD", "TMAE_NO_TC_ATTN", "TMAE_NO_GC_FUSE"])
+                                    "TMAE_NO_LN_FOLD", "TMAE_NO_TC_ATTN", "TMAE_NO_GC_FUSE", "TMAE_NO_PAIR_PERSISTENT", "TMAE_NO_ATTN_TAIL"])
 def test_ab_switches_keep_parity(cuda_dev, switch):
     """Every A/B switch named in INTEGRATION.md selects a path that still meets the parity bar (the switches are read
     once per process, hence one subprocess each)."""

@@ -401,6 +401,30 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// arrive on an mbarrier of another CTA of the cluster (address from mapa_shared), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(bar_cluster) : "memory");
+}
+// wait on a LOCAL mbarrier whose arrivals may come from the other CTA of the cluster (acquire at cluster scope); bounded
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("tmae: cluster mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
 // TMA load into THIS CTA's shared memory whose completion bytes are signalled on an mbarrier of either CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar_cluster, int32_t c0, int32_t c1) {
     asm volatile(

@@ -1096,6 +1096,103 @@ gemm_tc_pair_kernel(const GemmParams* __restrict__ params, int stages, const Gem
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Persistent CTA-pair variant (encoder QKV / fc1 with one batch in flight): 74 clusters of two CTAs walk a static round-robin
+// list of 256 x block_n tiles.  It combines the two mechanisms above: the pair halves the weight traffic per SM, and the
+// accumulator is double buffered in tensor memory (2 x 256 columns in EACH CTA) so the 16 epilogue warps of a CTA drain tile
+// i while the pair's main loop runs tile i + 1 - in the one-tile-per-CTA pair kernel the two phases alternate (main loop
+// 7 us, store phase 3-7 us per tile) and the second wave of a 1.3-wave grid leaves most SMs idle.
+//   full[s]    in the LEADER, completed by both CTAs' TMA loads          empty[s]  in each CTA (multicast commit)
+//   tfull[b]   in each CTA (multicast commit after the tile's last MMA)  tempty[b] in the LEADER: 2 x 16 arrivals, one per
+//              epilogue warp of BOTH CTAs (the follower's arrive through the cluster address)
+// ---------------------------------------------------------------------------------------------------------
+template <int ACT, int EPI>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tc_pair_persistent_kernel(const GemmParams* __restrict__ params, int stages, int m_pairs, int n_tiles,
+                               const GemmParams* __restrict__ next, int next_groups) {
+    pdl_launch_dependents();
+    if (next != nullptr && threadIdx.x == 64) prefetch_next_weights(next, next_groups, blockIdx.x, gridDim.x);
+    const GemmParams& p = params[0];
+    const uint32_t rank = cluster_ctarank();
+    const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int block_n = p.block_n;
+    const int half_n = block_n >> 1;
+    const int stage_bytes = kAStageBytes + half_n * kBlockK * 2;
+    uint8_t* pipe = smem + kEpiStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(pipe + (size_t)stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* tfull_bar = empty_bar + stages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int total_kb = 0;
+    for (int sg = 0; sg < p.num_segs; ++sg) total_kb += p.seg_kblocks[sg];
+    total_kb *= p.num_taps;
+    const int total_tiles = m_pairs * n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * kPersistEpiWarps); }
+        fence_barrier_init();
+        for (int sg = 0; sg < p.num_segs; ++sg) tma_prefetch_desc(&p.a_map[sg]);
+        tma_prefetch_desc(&p.b_map_pair);
+    }
+    if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    tc_fence_before();
+    cluster_sync_all();                                   // both CTAs' barriers exist before anything signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+    const uint32_t pipe_base = smem_u32(pipe);
+    const uint32_t full_a = smem_u32(full_bar), empty_a = smem_u32(empty_bar);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A, own half of the weight tile =====
+        int stage = 0;
+        uint32_t phase = 0, stage_off = 0;
+        const uint32_t full_leader = mapa_shared(full_a, 0);
+        for (int t = pair_id; t < total_tiles; t += num_pairs)
+            produce_tile(p, 2 * (t / n_tiles) + (int)rank, (t % n_tiles) * block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a,
+                         stage, phase, stage_off, nullptr, 0, 1, 1, rank, full_leader);
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===== MMA issuer (leader only) =====
+            int stage = 0, it = 0;
+            uint32_t phase = 0, stage_off = 0;
+            for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+                const int buf = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait_cluster(&tempty_bar[buf], acc_phase ^ 1u);      // both CTAs' epilogues have drained this buffer
+                tc_fence_after();
+                mma_tile(block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, tmem_base + (uint32_t)buf * 256u,
+                         smem_u32(&tfull_bar[buf]), stage, phase, stage_off, nullptr, -1, -1, 0u, 0u, 1);
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs, own TMEM lanes = own 128 rows) =====
+        const EpiCtx e = load_epi(p);
+        const uint32_t stage_base = smem_u32(smem);
+        const uint32_t tempty_leader = mapa_shared(smem_u32(tempty_bar), 0);
+        int it = 0;
+        for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
+            const int buf = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            epilogue_tile<ACT, EPI>(e, 2 * (t / n_tiles) + (int)rank, (t % n_tiles) * block_n, block_n, tmem_base + (uint32_t)buf * 256u,
+                                    stage_base, warp, lane, &tfull_bar[buf], acc_phase, nullptr, kPersistEpiWarps / 4);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * (uint32_t)buf);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // neither CTA leaves while the other may still signal its barriers
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // CUDA-core checker: same parameter block, same epilogue, plain loads.  Bring-up / tests only.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -1204,6 +1301,16 @@ cudaError_t gemm_tc_configure() {
         if ((e = cfgp(gemm_tc_pair_kernel<ACT_GELU, EPI_GENERIC>)) != cudaSuccess) return e;
         if ((e = cfgp(gemm_tc_pair_kernel<ACT_HALF_TANH, EPI_GENERIC>)) != cudaSuccess) return e;
     }
+    {
+        auto cfgpp = [](auto kernel) {
+            prefer_max_smem_carveout(kernel);
+            return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        };
+        if ((e = cfgpp(gemm_tc_pair_persistent_kernel<ACT_NONE, EPI_BF16_TMA>)) != cudaSuccess) return e;
+        if ((e = cfgpp(gemm_tc_pair_persistent_kernel<ACT_GELU, EPI_BF16_TMA>)) != cudaSuccess) return e;
+        if ((e = cfgpp(gemm_tc_pair_persistent_kernel<ACT_NONE, EPI_BF16_SAME>)) != cudaSuccess) return e;
+        if ((e = cfgpp(gemm_tc_pair_persistent_kernel<ACT_GELU, EPI_BF16_SAME>)) != cudaSuccess) return e;
+    }
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>);
     prefer_max_smem_carveout(gemm_tc_persistent_kernel<ACT_GELU, EPI_BF16_TMA>);
     if ((e = cudaFuncSetAttribute(gemm_tc_persistent_kernel<ACT_NONE, EPI_BF16_TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)) != cudaSuccess) return e;
@@ -1247,6 +1354,16 @@ bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pa
     return (epi == EPI_BF16_SAME || epi == EPI_BF16_TMA) && (act == ACT_NONE || act == ACT_GELU);
 }
 
+// Persistent pairs: a linear layer that already qualifies for pairs, bf16 same-row output, one batch in flight (a persistent
+// launch owns every SM) and more pair tiles than one round of the 74 clusters.  TMAE_NO_PAIR_PERSISTENT=1 = A/B switch.
+bool gemm_use_pair_persistent(int groups, int epi, int act, int max_M, int max_N, int block_n, bool share_sm, bool conv) {
+    static const bool off = getenv("TMAE_NO_PAIR_PERSISTENT") != nullptr;
+    if (off || share_sm || conv || groups != 1) return false;
+    if ((epi != EPI_BF16_SAME && epi != EPI_BF16_TMA) || (act != ACT_NONE && act != ACT_GELU)) return false;
+    const int m_pairs = ((max_M + kBlockM - 1) / kBlockM + 1) / 2, n_tiles = (max_N + block_n - 1) / block_n;
+    return m_pairs * n_tiles > 74;
+}
+
 template <int ACT, int EPI>
 static cudaError_t launch_pair(dim3 grid, int smem, cudaStream_t stream, const GemmParams* d_params, int stages, const GemmParams* d_next,
                                int next_groups) {
@@ -1256,7 +1373,7 @@ static cudaError_t launch_pair(dim3 grid, int smem, cudaStream_t stream, const G
 // params: device array of `groups` GemmParams; max_M / max_N / block_n describe the largest member.
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream, const GemmParams* d_next, int next_groups,
-                        int conv_reuse_stage_bytes, bool pair) {
+                        int conv_reuse_stage_bytes, int pair) {
     if (simt) {
         dim3 grid(max_M, 1, groups);
         gemm_simt_kernel<<<grid, 128, 0, stream>>>(d_params);
@@ -1267,6 +1384,24 @@ cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int m
     if (pair) {                                               // the plan's policy (gemm_use_pair) decided
         if ((block_n & 15) != 0) return cudaErrorInvalidConfiguration;
         dim3 pgrid((grid.x + 1) / 2 * 2, grid.y, groups);      // whole pairs along x
+        if (pair == 2) {
+            // persistent pairs (plan policy gemm_use_pair_persistent): one cluster per TPC, tiles round-robin
+            if (groups != 1 || conv_reuse_stage_bytes != 0 || (epi != EPI_BF16_SAME && epi != EPI_BF16_TMA) || (act != ACT_NONE && act != ACT_GELU))
+                return cudaErrorInvalidConfiguration;
+            const int stage_bytes = kAStageBytes + (block_n / 2) * kBlockK * 2;
+            const int overhead = 1024 + 256 + kEpiStageBytes;
+            int pst = (226 * 1024 - overhead) / stage_bytes;
+            if (pst > 8) pst = 8;
+            if (pst < 2) return cudaErrorInvalidConfiguration;
+            const int psmem = overhead + pst * stage_bytes;
+            const int m_pairs = (int)pgrid.x / 2, tiles = m_pairs * (int)grid.y;
+            const int pairs = tiles < 74 ? tiles : 74;
+            const dim3 g2(2 * pairs), blk(kPersistThreads);
+            if (epi == EPI_BF16_TMA && act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_persistent_kernel<ACT_GELU, EPI_BF16_TMA>, g2, blk, psmem, stream, true, 2, d_params, pst, m_pairs, (int)grid.y, d_next, next_groups);
+            if (epi == EPI_BF16_TMA) return launch_k_cluster(gemm_tc_pair_persistent_kernel<ACT_NONE, EPI_BF16_TMA>, g2, blk, psmem, stream, true, 2, d_params, pst, m_pairs, (int)grid.y, d_next, next_groups);
+            if (act == ACT_GELU) return launch_k_cluster(gemm_tc_pair_persistent_kernel<ACT_GELU, EPI_BF16_SAME>, g2, blk, psmem, stream, true, 2, d_params, pst, m_pairs, (int)grid.y, d_next, next_groups);
+            return launch_k_cluster(gemm_tc_pair_persistent_kernel<ACT_NONE, EPI_BF16_SAME>, g2, blk, psmem, stream, true, 2, d_params, pst, m_pairs, (int)grid.y, d_next, next_groups);
+        }
         // conv_reuse_stage_bytes is the PAIR stage here (haloed A box + three half B atoms), computed by the plan
         const int stage_bytes = conv_reuse_stage_bytes > 0 ? conv_reuse_stage_bytes : kAStageBytes + (block_n / 2) * kBlockK * 2;
         const int overhead = 256;

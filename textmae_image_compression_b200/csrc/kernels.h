@@ -23,8 +23,9 @@ int gemm_pick_stages(int block_n, int total_ctas, bool share_sm, int* smem_bytes
 int gemm_epi_kind(const GemmParams& p);
 cudaError_t gemm_launch(const GemmParams* d_params, int groups, int max_M, int max_N, int block_n, int act, int epi,
                         bool simt, bool share_sm, cudaStream_t stream,
-                        const GemmParams* d_next = nullptr, int next_groups = 0, int conv_reuse_stage_bytes = 0, bool pair = false);
+                        const GemmParams* d_next = nullptr, int next_groups = 0, int conv_reuse_stage_bytes = 0, int pair = 0);   // pair: 1 = CTA pairs, 2 = persistent CTA pairs
 bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pair_ok, bool conv);
+bool gemm_use_pair_persistent(int groups, int epi, int act, int max_M, int max_N, int block_n, bool share_sm, bool conv);
 int gemm_reuse_stages(int stage_bytes, int total_ctas, bool share_sm, int* smem_bytes);
 
 // mask.cu

@@ -64,6 +64,7 @@ struct Step {
     int next_index = -1, next_groups = 0;      // parameter blocks of the next GEMM step (weight prefetch target)
     int conv_reuse_stage_bytes = 0;            // > 0: 3x3 conv launch with haloed-box A reuse, stage size in bytes
     bool pair = false;                         // CTA-pair (cta_group::2) launch
+    bool pair_persist = false;                 // ... as the persistent pair kernel (one batch in flight, several tiles per cluster)
     double flops = 0, bytes = 0;
     int mma_terms = 1;                         // 3 for precise (split-bf16) GEMM steps
     // LN
@@ -788,6 +789,8 @@ int add_gemm_group(tmae_handle* h, Plan& pl, const GemmDesc* descs, int groups, 
         return fail(h, TMAE_EINVAL, "%s: LayerNorm statistics need the fp32 residual epilogue (epi %d)", tag, st.epi);
     st.max_M = max_M; st.max_N = max_N; st.block_n = bn; st.act = descs[0].act;
     if (st.pair && !pl.host_params[st.param_index].pair_ok) st.pair = false;
+    st.pair_persist = st.pair && gemm_use_pair_persistent(groups, st.epi, st.act, max_M, max_N, bn, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0,
+                                                          descs[0].in_mode == IN_CONV);
     static const bool plan_debug = getenv("TMAE_PLAN_DEBUG") != nullptr;
     if (plan_debug)
         fprintf(stderr, "[plan] %-14s groups %2d M %6d N %4d bn %3d ctas %4d epi %d conv_reuse_stage %6d B pair %d\n", tag, groups, max_M, max_N, bn,
@@ -1188,7 +1191,7 @@ int run_steps(tmae_handle* h, Plan& pl, const RunArgs& a, cudaStream_t st) {
                 break;
             case ST_GEMM:
                 CUDA_TRY(h, gemm_launch(pl.d_params + sp.param_index, sp.groups, sp.max_M, sp.max_N, sp.block_n, sp.act, sp.epi, simt, (h->cfg.flags & TMAE_FLAG_SHARE_SM) != 0, st,
-                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes, sp.pair));
+                                        sp.next_index >= 0 ? pl.d_params + sp.next_index : nullptr, sp.next_groups, sp.conv_reuse_stage_bytes, sp.pair ? (sp.pair_persist ? 2 : 1) : 0));
                 break;
             case ST_FORCE:
                 CUDA_TRY(h, launch_f32_to_bf16_cols(w.yhat_force + sp.slice * h->sc, w.yhat_bf.p + sp.slice * h->sc, (long long)N * K, h->sc,
@@ -1703,7 +1706,7 @@ int tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int 
 }
 
 // ---- engine self-tests ---------------------------------------------------------------------------------
-static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st, bool pair = false) {
+static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, int impl, cudaStream_t st, int pair = 0) {
     GemmParams p;
     GemmDesc d = d_in;
     int reuse_bytes = 0;
@@ -1711,7 +1714,7 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
         const int mt = (d.M + kBlockM - 1) / kBlockM;
         const int bn = block_n > 0 ? block_n : pick_block_n(mt, d.layer->Cout, 1);
         block_n = bn;
-        reuse_bytes = conv_reuse_stage_bytes(tmp, d, bn, (d.layer->Cout + bn - 1) / bn, 1, pair && impl == 0);
+        reuse_bytes = conv_reuse_stage_bytes(tmp, d, bn, (d.layer->Cout + bn - 1) / bn, 1, pair != 0 && impl == 0);
         d.conv_reuse = reuse_bytes > 0;
     }
     int rc = fill_params(tmp, d, 1, &p, block_n);
@@ -1735,7 +1738,7 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
     if (pair && !p.pair_ok) { cudaFree(dp); return fail(tmp, TMAE_EINVAL, "pair launch needs a linear layer with block_n %% 32 == 0"); }
-    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes, pair && impl == 0);
+    cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes, impl == 0 ? pair : 0);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
         cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
@@ -1840,6 +1843,40 @@ int tmae_gemm_bf16(const void* A, const void* B, const float* bias, float* Cmat,
     d.a_rows = M; d.M = M;
     d.out0 = outspec(Cmat, N, OUT_F32, MAP_SAME);
     rc = engine_common(tmp.get(), d, block_n, impl, st);
+    if (rc) g_create_error = tmp->err;
+    free_pool(pool);
+    return rc;
+}
+
+// C (bf16) = act(A B^T + bias): the bf16 same-row store phases (TMA-store epilogue when block_n % 32 == 0).  variant 0 = one
+// tile per CTA (or the one-CTA persistent kernel when the grid has more than two tiles per SM), 1 = CTA pairs, 2 = persistent
+// CTA pairs, 3 = CUDA-core checker.
+int tmae_gemm_bf16_out(const void* A, const void* B, const float* bias, void* Cmat, int M, int N, int K, int block_n, int gelu,
+                       int variant, void* stream) {
+    if (!A || !B || !Cmat || M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || N % 8 != 0 || variant < 0 || variant > 3)
+        return fail(nullptr, TMAE_EINVAL, "tmae_gemm_bf16_out: invalid argument (need K %% 8 == 0, N %% 8 == 0, variant 0..3)");
+    std::unique_ptr<tmae_handle> tmp;
+    int rc = make_tmp_handle(tmp);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int Kp = pad64(K);
+    __nv_bfloat16* wp = nullptr;
+    float* bz = nullptr;
+    std::vector<void*> pool;
+    if ((rc = dev_alloc(tmp.get(), pool, &wp, (size_t)N * Kp)) || (rc = dev_alloc(tmp.get(), pool, &bz, (size_t)N))) {
+        g_create_error = tmp->err; free_pool(pool); return rc;
+    }
+    cudaMemcpy2DAsync(wp, (size_t)Kp * 2, B, (size_t)K * 2, (size_t)K * 2, N, cudaMemcpyDeviceToDevice, st);
+    if (bias) cudaMemcpyAsync(bz, bias, (size_t)N * 4, cudaMemcpyDeviceToDevice, st);
+    Layer L;
+    L.w = wp; L.bias = bz; L.Cout = N; L.Cin = K; L.taps = 1; L.nseg = 1; L.segc[0] = K; L.Kp = Kp; L.kb_tap = Kp / 64;
+    GemmDesc d;
+    d.layer = &L;
+    d.seg[0] = seg(reinterpret_cast<const __nv_bfloat16*>(A), K, K);
+    d.a_rows = M; d.M = M;
+    d.act = gelu ? ACT_GELU : ACT_NONE;
+    d.out0 = outspec(Cmat, N, OUT_BF16, MAP_SAME);
+    rc = engine_common(tmp.get(), d, block_n, variant == 3 ? 1 : 0, st, variant == 3 ? 0 : variant);
     if (rc) g_create_error = tmp->err;
     free_pool(pool);
     return rc;
