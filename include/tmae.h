@@ -190,6 +190,7 @@ typedef struct {
     uint8_t* segmented;       /* [n, height, width]       the image after Recursion / Merge (utils/map.py:35-42) */
 } tmae_score_outputs;
 TMAE_API size_t tmae_scores_workspace_bytes(int n, int height, int width, int out_side);   /* 0 = invalid geometry */
+/* workspace: device memory, 256-byte aligned, >= tmae_scores_workspace_bytes(...); n <= 65535 images per call. */
 TMAE_API int  tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int out_side,
                           const tmae_score_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -1699,6 +1699,9 @@ int tmae_generate_scores(const uint8_t* gray, int n, int height, int width, int 
                     height, width, out_side);
     if (workspace_bytes < score_workspace_bytes(g, n))
         return fail(nullptr, TMAE_EINVAL, "workspace too small: %zu < %zu bytes", workspace_bytes, score_workspace_bytes(g, n));
+    if (n > 0 && (reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return fail(nullptr, TMAE_EINVAL, "workspace must be 256-byte aligned (histograms, tickets and the segmented image are carved out of it)");
+    if (n > 65535) return fail(nullptr, TMAE_EINVAL, "at most 65535 images per call (got %d)", n);
     cudaError_t e = launch_generate_scores(gray, n, g, out->scores, out->s_map, out->t_map, out->segmented, workspace,
                                            reinterpret_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(nullptr, TMAE_ECUDA, "generate_scores: %s", cudaGetErrorString(e));
