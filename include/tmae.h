@@ -271,6 +271,12 @@ TMAE_API int  tmae_profile_read_steps(tmae_handle* h, tmae_profile_step* steps, 
 /* Number of kernels tmae_forward launches for batch N (after planning). */
 TMAE_API int  tmae_launch_count(tmae_handle* h, int N);
 
+/* Host-only: how the tcgen05 attention kernel is set up for T tokens, H heads, N images in `mode` (1 full form, 2 several
+ * streams share the GPU, 3 two-heads-per-tile experiment).  out[12] = {supported (0 -> the mma.sync kernel serves this T), Tp,
+ * query tiles, tail rows (computed on CUDA cores), items, S/O/P buffers, pipeline stages, TMEM columns, shared-memory bytes,
+ * Q box rows, K/V box rows, form (0 full, 1 lite, 2 duo)}. */
+TMAE_API int  tmae_attention_plan(int T, int H, int N, int mode, int* out);
+
 /* Host-only (no device needed): the CTA tiling the conv engine uses for an s x s grid of n_img images.
  * out[6] = {box_y, box_n, y_tiles, m_tiles, rows_used, reuse_ok}.  A tile covers image rows [y0, y0 + box_y) of images
  * [n0, n0 + box_n); rows_used = s * box_y * box_n <= 128 accumulator rows; reuse_ok = the haloed-box A reuse applies

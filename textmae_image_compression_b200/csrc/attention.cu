@@ -836,6 +836,17 @@ void attention_tc_boxes(int T, int H, int mode, int* q_rows, int* kv_rows) {
     attn_tc_plan(T, H, H * HD, 1, 0.125f, &p, &smem, lite, duo);
     *q_rows = p.qrows; *kv_rows = p.krows;
 }
+// host-only view of the plan (tests): out[12] = {supported, Tp, q_tiles, tail_rows, n_items, nbuf, nst, tmem_cols, smem_bytes,
+// q_box_rows, kv_box_rows, form (0 full, 1 lite, 2 duo)}
+bool attention_tc_describe(int T, int H, int N, int mode, int* out) {
+    AttnTcParams p = {}; size_t smem = 0;
+    bool lite, duo;
+    attn_mode(T, H, mode, &lite, &duo);
+    const bool ok = attn_tc_plan(T, H, H * HD, N, 0.125f, &p, &smem, lite, duo);
+    out[0] = ok ? 1 : 0; out[1] = attn_tp(T); out[2] = p.q_tiles; out[3] = p.tail_rows; out[4] = p.n_items; out[5] = p.nbuf; out[6] = p.nst;
+    out[7] = (int)p.tmem_cols; out[8] = (int)smem; out[9] = p.qrows; out[10] = p.krows; out[11] = duo ? 2 : (lite ? 1 : 0);
+    return ok;
+}
 cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int N,
                                 int T, int H, int C, float scale, cudaStream_t st, long long* dbg, int mode) {
     if (C != H * HD) return cudaErrorInvalidValue;

@@ -41,6 +41,7 @@ bool attention_tc_supported(int T);   // kernel limits (Tp <= 384: shared memory
 bool attention_tc_eligible(int T);    // policy: the tcgen05 kernel whenever it is supported (TMAE_NO_TC_ATTN=1 -> mma.sync kernel)
 int attention_tc_tp(int T);
 // mode: 1 = full form, 2 = several streams share the GPU (lite form for short rows), 3 = duo (two heads per tile, T = 65; opt-in)
+bool attention_tc_describe(int T, int H, int N, int mode, int* out12);        // host-only: the plan for (T, H, N) in `mode`
 void attention_tc_boxes(int T, int H, int mode, int* q_rows, int* kv_rows);   // TMA box rows of the Q map and of the K / V map
 cudaError_t launch_attention_tc(const CUtensorMap* map_q, const CUtensorMap* map_kv, const __nv_bfloat16* qkv, __nv_bfloat16* out, int N,
                                 int T, int H, int C, float scale, cudaStream_t st, long long* dbg = nullptr, int mode = 1);

@@ -1505,6 +1505,12 @@ int tmae_reserve(tmae_handle* h, int N) {
     return build_plan(h, N, &pl);
 }
 
+int tmae_attention_plan(int T, int H, int N, int mode, int* out) {
+    if (!out || T <= 0 || H <= 0 || N <= 0 || mode < 1 || mode > 3) return fail(nullptr, TMAE_EINVAL, "tmae_attention_plan: invalid argument");
+    attention_tc_describe(T, H, N, mode, out);
+    return TMAE_OK;
+}
+
 int tmae_conv_geometry(int s, int n_img, int* out) {
     ConvGeom cg;
     if (!out || !conv_geom(s, n_img, &cg)) return TMAE_EINVAL;
