@@ -1132,6 +1132,8 @@ gemm_tc_pair_persistent_kernel(const GemmParams* __restrict__ params, int stages
     for (int sg = 0; sg < p.num_segs; ++sg) total_kb += p.seg_kblocks[sg];
     total_kb *= p.num_taps;
     const int total_tiles = m_pairs * n_tiles;
+    long long* ticks = p.dbg_ticks ? p.dbg_ticks + (size_t)blockIdx.x * 16 : nullptr;     // bring-up: phase stamps of the first 3 tiles
+    if (ticks && threadIdx.x == 0) ticks[0] = globaltimer_ns();
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -1168,7 +1170,7 @@ gemm_tc_pair_persistent_kernel(const GemmParams* __restrict__ params, int stages
                 mbar_wait_cluster(&tempty_bar[buf], acc_phase ^ 1u);      // both CTAs' epilogues have drained this buffer
                 tc_fence_after();
                 mma_tile(block_n, total_kb, stages, 1, stage_bytes, pipe_base, full_a, empty_a, tmem_base + (uint32_t)buf * 256u,
-                         smem_u32(&tfull_bar[buf]), stage, phase, stage_off, nullptr, -1, -1, 0u, 0u, 1);
+                         smem_u32(&tfull_bar[buf]), stage, phase, stage_off, it < 3 ? ticks : nullptr, 1 + 4 * it, 2 + 4 * it, 0u, 0u, 1);
             }
         }
     } else {
@@ -1180,8 +1182,11 @@ gemm_tc_pair_persistent_kernel(const GemmParams* __restrict__ params, int stages
         for (int t = pair_id; t < total_tiles; t += num_pairs, ++it) {
             const int buf = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            long long tk[16];
             epilogue_tile<ACT, EPI>(e, 2 * (t / n_tiles) + (int)rank, (t % n_tiles) * block_n, block_n, tmem_base + (uint32_t)buf * 256u,
-                                    stage_base, warp, lane, &tfull_bar[buf], acc_phase, nullptr, kPersistEpiWarps / 4);
+                                    stage_base, warp, lane, &tfull_bar[buf], acc_phase, (ticks && warp == 2 && it < 3) ? tk : nullptr,
+                                    kPersistEpiWarps / 4);
+            if (ticks && warp == 2 && lane == 0 && it < 3) { ticks[3 + 4 * it] = tk[5]; ticks[4 + 4 * it] = globaltimer_ns(); }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_leader + 8u * (uint32_t)buf);
@@ -1189,6 +1194,7 @@ gemm_tc_pair_persistent_kernel(const GemmParams* __restrict__ params, int stages
     }
     tc_fence_before();
     cluster_sync_all();                                   // neither CTA leaves while the other may still signal its barriers
+    if (ticks && threadIdx.x == 0) ticks[13] = globaltimer_ns();
     if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
@@ -1358,7 +1364,8 @@ bool gemm_use_pair(int groups, int epi, int act, int max_M, int block_n, bool pa
 // launch owns every SM) and more pair tiles than one round of the 74 clusters.  TMAE_NO_PAIR_PERSISTENT=1 = A/B switch.
 bool gemm_use_pair_persistent(int groups, int epi, int act, int max_M, int max_N, int block_n, bool share_sm, bool conv) {
     static const bool off = getenv("TMAE_NO_PAIR_PERSISTENT") != nullptr;
-    if (off || share_sm || conv || groups != 1) return false;
+    static const bool in_share = getenv("TMAE_PP_SHARE") != nullptr;          // experiment: also while several streams share the GPU
+    if (off || (share_sm && !in_share) || conv || groups != 1) return false;
     if ((epi != EPI_BF16_SAME && epi != EPI_BF16_TMA) || (act != ACT_NONE && act != ACT_GELU)) return false;
     const int m_pairs = ((max_M + kBlockM - 1) / kBlockM + 1) / 2, n_tiles = (max_N + block_n - 1) / block_n;
     return m_pairs * n_tiles > 74;

@@ -1747,6 +1747,47 @@ static int engine_common(tmae_handle* tmp, const GemmDesc& d_in, int block_n, in
     }
     cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
     if (pair && !p.pair_ok) { cudaFree(dp); return fail(tmp, TMAE_EINVAL, "pair launch needs a linear layer with block_n %% 32 == 0"); }
+    if (pair == 2 && getenv("TMAE_GEMM_TIMING") != nullptr && impl == 0) {
+        // bring-up aid for the persistent pair kernel: phase stamps of the first three tiles of every CTA
+        long long* dt = nullptr;
+        cudaMalloc(reinterpret_cast<void**>(&dt), (size_t)148 * 16 * sizeof(long long));
+        cudaMemset(dt, 0, (size_t)148 * 16 * sizeof(long long));
+        p.dbg_ticks = dt;
+        cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
+        gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, 0, 2);      // cold
+        cudaStreamSynchronize(st);
+        cudaEvent_t ev0, ev1; cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, st);
+        cudaError_t e2 = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, 0, 2);
+        cudaEventRecord(ev1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0; cudaEventElapsedTime(&ms, ev0, ev1);
+        std::vector<long long> t((size_t)148 * 16);
+        cudaMemcpy(t.data(), dt, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        double avg[16] = {0}; int nc = 0;
+        for (int c = 0; c < 148; c += 2) if (t[c * 16]) { ++nc; for (int k = 1; k < 14; ++k) avg[k] += (double)(t[c * 16 + k] - t[c * 16]); }
+        for (int k = 1; k < 14; ++k) avg[k] /= nc > 0 ? nc : 1;
+        fprintf(stderr, "[pair-persistent timing] M=%d N=%d K=%d bn=%d leaders=%d | kernel %.1f us | ns since entry, tiles 0/1/2: mma_first %.0f/%.0f/%.0f  mma_last %.0f/%.0f/%.0f  "
+                "accum_seen %.0f/%.0f/%.0f  epi_done %.0f/%.0f/%.0f | exit %.0f (%s)\n", p.M, p.N, p.b_kb_per_tap * 64, p.block_n, nc, ms * 1e3,
+                avg[1], avg[5], avg[9], avg[2], avg[6], avg[10], avg[3], avg[7], avg[11], avg[4], avg[8], avg[12], avg[13], cudaGetErrorString(e2));
+        p.dbg_ticks = nullptr;
+        cudaMemcpyAsync(dp, &p, sizeof(p), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+        cudaFree(dt);
+        // steady state, 50 launches back to back on the stream (PDL overlaps ramp and drain): the three bf16 store kernels
+        for (int variant = 0; variant < 3; ++variant) {
+            for (int i = 0; i < 3; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, 0, variant);
+            cudaStreamSynchronize(st);
+            cudaEventRecord(ev0, st);
+            for (int i = 0; i < 50; ++i) gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), false, false, st, nullptr, 0, 0, variant);
+            cudaEventRecord(ev1, st);
+            cudaStreamSynchronize(st);
+            float msv = 0; cudaEventElapsedTime(&msv, ev0, ev1);
+            fprintf(stderr, "[pair-persistent timing]   back-to-back x50, %s: %.2f us/launch = %.0f TFLOP/s\n",
+                    variant == 0 ? "one CTA per tile / one-CTA persistent" : (variant == 1 ? "CTA pairs" : "persistent CTA pairs"),
+                    msv * 1e3 / 50, 2.0 * p.M * p.N * p.b_kb_per_tap * 64 / (msv * 1e-3 / 50) / 1e12);
+        }
+    }
     cudaError_t e = gemm_launch(dp, 1, p.M, p.N, p.block_n, p.act, gemm_epi_kind(p), impl == 1, false, st, nullptr, 0, reuse_bytes, impl == 0 ? pair : 0);
     if (timing) {                      // second, warm launch is the one reported
         cudaStreamSynchronize(st);
